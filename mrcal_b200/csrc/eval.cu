@@ -1,0 +1,643 @@
+// Kernel family 1: the cost function. residuals x and the block-sparse
+// Jacobian dx/db_packed, written in the reference's CSR order.
+//
+// What these kernels compute is the reference's optimizer_callback()
+// (mrcal.c:4444-5970): board rows (:4604-4900), discrete-point rows
+// (:4902-5176), regularization rows (:5655-5955). How: the unit of parallel
+// work is the board OBSERVATION (one CTA) and the board CORNER (one thread);
+// the two Rodrigues rotations of an observation are expanded once per CTA into
+// shared memory; each thread evaluates its corner's projection and gradients
+// in registers and writes its two fixed-width Jacobian rows. Row positions are
+// analytic (fixed nnz per row class), so there is no serial fill pointer.
+#include "device_math.cuh"
+#include "problem.h"
+
+namespace mb200 {
+
+// b_packed -> unpacked intrinsics / poses / points / warp, falling back to the
+// seed values for whatever is not being optimised (mrcal.c:4534-4601)
+__global__ void unpack_state_kernel(DevProblem P, const double* __restrict__ b)
+{
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    const int n_intr = P.Ncam_i * P.Nintr;
+    const int n_cam  = P.Ncam_e * 6;
+    const int n_frm  = P.Nframes * 6;
+    const int n_pt   = P.Npoints * 3;
+    int i = t;
+    if(i < n_intr)
+    {
+        const int cam = i / P.Nintr, k = i - cam * P.Nintr;
+        double v;
+        if(k < 4)
+        {
+            if(P.opt_core) v = b[P.i_intr0 + cam * P.Nintr_state + k] * (k < 2 ? kScaleFocal : kScaleCenter);
+            else           v = P.in_intrinsics[i];
+        }
+        else
+        {
+            if(P.opt_dist) v = b[P.i_intr0 + cam * P.Nintr_state + P.Ncore_state + (k - 4)] * kScaleDistortion;
+            else           v = P.in_intrinsics[i];
+        }
+        P.u_intr[i] = v;
+        return;
+    }
+    i -= n_intr;
+    if(i < n_cam)
+    {
+        const int k = i % 6;
+        P.u_rtcam[i] = P.opt_extr ? b[P.i_extr0 + i] * (k < 3 ? kScaleRotCam : kScaleTransCam) : P.in_rt_cam[i];
+        return;
+    }
+    i -= n_cam;
+    if(i < n_frm)
+    {
+        const int k = i % 6;
+        P.u_rtframe[i] = P.opt_frames ? b[P.i_frame0 + i] * (k < 3 ? kScaleRotFrame : kScaleTransFrame) : P.in_rt_frame[i];
+        return;
+    }
+    i -= n_frm;
+    if(i < n_pt)
+    {
+        const int ipt = i / 3;
+        P.u_points[i] = (P.opt_frames && ipt < P.Npoints_variable) ? b[P.i_point0 + i] * kScalePoint : P.in_points[i];
+        return;
+    }
+    i -= n_pt;
+    if(i < 2)
+    {
+        if(P.opt_warp)        P.u_warp[i] = b[P.i_warp0 + i] * kScaleWarp;
+        else if(P.have_warp)  P.u_warp[i] = P.in_warp[i];
+        else                  P.u_warp[i] = 0.;
+    }
+}
+
+__device__ __forceinline__ double block_sum(double v, double* sh /* >= 32 doubles */)
+{
+#pragma unroll
+    for(int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    if(lane == 0) sh[warp] = v;
+    __syncthreads();
+    if(warp == 0)
+    {
+        v = lane < (int)((blockDim.x + 31) >> 5) ? sh[lane] : 0.;
+#pragma unroll
+        for(int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
+    }
+    return v;   // valid in thread 0
+}
+
+// Intrinsics part of one measurement row. i_xy selects the x or the y row.
+//   g_f      dq_k/df_k (core)
+//   ddist    dense distortion gradient of this row (parametric models)
+//   wx,wy    spline basis (splined models); ivar0s = knot offset within the STATE block
+template <int KIND>
+__device__ __forceinline__ int emit_intrinsics(double* __restrict__ jv, int* __restrict__ jc,
+                                               const DevProblem& P, int i_var_intr, int i_xy, double w, bool zero,
+                                               double g_f, const double* ddist,
+                                               const double* wx, const double* wy, int ivar0s, double f_xy)
+{
+    int n = 0;
+    if(P.opt_core)
+    {
+        jc[n] = i_var_intr + i_xy;     jv[n] = zero ? 0. : g_f * w * kScaleFocal;  n++;
+        jc[n] = i_var_intr + i_xy + 2; jv[n] = zero ? 0. : w * kScaleCenter;       n++;
+    }
+    if(P.opt_dist)
+    {
+        if constexpr(LensTraits<KIND>::SPLINED)
+        {
+            constexpr int RUN = LensTraits<KIND>::RUN;
+#pragma unroll
+            for(int iy = 0; iy < RUN; iy++)
+#pragma unroll
+                for(int ix = 0; ix < RUN; ix++)
+                {
+                    jc[n] = i_var_intr + ivar0s + iy * 2 * P.Nx + ix * 2 + i_xy;
+                    jv[n] = zero ? 0. : wx[ix] * wy[iy] * f_xy * w * kScaleDistortion;
+                    n++;
+                }
+        }
+        else
+        {
+            constexpr int ND = LensTraits<KIND>::NDIST;
+#pragma unroll
+            for(int i = 0; i < ND; i++)
+            {
+                jc[n] = i_var_intr + P.Ncore_state + i;
+                jv[n] = zero ? 0. : ddist[i] * w * kScaleDistortion;
+                n++;
+            }
+        }
+    }
+    return n;
+}
+
+struct ObsGeometry   // per observation, in shared memory
+{
+    double Rf[9], dRf[27], tf[3];
+    double Rc[9], dRc[27], tc[3];
+};
+
+// One CTA per board observation, one thread per corner (strided if W*H > blockDim)
+template <int KIND, bool WITH_J>
+__global__ void __launch_bounds__(256)
+eval_boards_kernel(DevProblem P, double* __restrict__ x, double* __restrict__ Jval, int* __restrict__ Jcol,
+                   double* __restrict__ norm2)
+{
+    __shared__ ObsGeometry G;
+    __shared__ double red[32];
+
+    const int iobs   = blockIdx.x;
+    const int icam_i = P.obs_board[3 * iobs + 0];
+    const int icam_e = P.obs_board[3 * iobs + 1];
+    const int iframe = P.obs_board[3 * iobs + 2];
+    const bool cam_identity = icam_e < 0;
+
+    if(threadIdx.x == 0)
+    {
+        const double* rt = &P.u_rtframe[6 * iframe];
+        rodrigues(G.Rf, G.dRf, rt);
+        G.tf[0] = rt[3]; G.tf[1] = rt[4]; G.tf[2] = rt[5];
+    }
+    if(threadIdx.x == 32 % blockDim.x && !cam_identity)
+    {
+        const double* rt = &P.u_rtcam[6 * icam_e];
+        rodrigues(G.Rc, G.dRc, rt);
+        G.tc[0] = rt[3]; G.tc[1] = rt[4]; G.tc[2] = rt[5];
+    }
+    __syncthreads();
+
+    const double* __restrict__ intr = &P.u_intr[(size_t)icam_i * P.Nintr];
+    const int i_var_intr  = P.i_intr0 + icam_i * P.Nintr_state;
+    const int i_var_cam   = P.i_extr0 + 6 * icam_e;
+    const int i_var_frame = P.i_frame0 + 6 * iframe;
+    const bool emit_cam   = P.opt_extr && !cam_identity;
+    const int nnz_row     = P.nnz_row_intr + (emit_cam ? 6 : 0) + P.nnz_row_board_geom;
+    const int NWH         = P.W * P.H;
+    const double wx2 = P.u_warp[0], wy2 = P.u_warp[1];
+
+    double sumsq = 0.;
+    for(int ipt = threadIdx.x; ipt < NWH; ipt += blockDim.x)
+    {
+        const int cx = ipt % P.W, cy = ipt / P.W;
+        // the board point, with the parabolic warp (mrcal.c:2794-2819)
+        double pt[3] = {(double)cx * P.spacing, (double)cy * P.spacing, 0.};
+        double dz[2] = {0., 0.};
+        if(P.have_warp)
+        {
+            const double xr = (double)cx / (double)(P.W - 1);
+            const double yr = (double)cy / (double)(P.H - 1);
+            dz[0] = 4. * xr * (1. - xr);
+            dz[1] = 4. * yr * (1. - yr);
+            pt[2] += wx2 * dz[0];
+            pt[2] += wy2 * dz[1];
+        }
+        // v = Rf pt + tf (reference coords); p = Rc v + tc (camera coords)
+        double v[3], p[3];
+        mat3_vec(v, G.Rf, pt);
+        v[0] += G.tf[0]; v[1] += G.tf[1]; v[2] += G.tf[2];
+        if(cam_identity) { p[0] = v[0]; p[1] = v[1]; p[2] = v[2]; }
+        else
+        {
+            mat3_vec(p, G.Rc, v);
+            p[0] += G.tc[0]; p[1] += G.tc[1]; p[2] += G.tc[2];
+        }
+
+        double q[2], dq_dp[2][3];
+        double ddist[2][LensTraits<KIND>::NDIST > 0 ? LensTraits<KIND>::NDIST : 1];
+        double wx[4], wy[4], upd[2] = {0., 0.};
+        int ivar0 = 0;
+        if constexpr(LensTraits<KIND>::SPLINED)
+            project_splined<LensTraits<KIND>::RUN>(q, dq_dp, wx, wy, &ivar0, upd, p, intr, P.Nx, P.Ny, P.segments_per_u);
+        else
+            project_parametric<KIND>(q, dq_dp, WITH_J ? ddist : nullptr, p, intr);
+
+        const size_t ifeat = (size_t)iobs * NWH + ipt;
+        const double qx_obs = P.obs_board_pool[3 * ifeat + 0];
+        const double qy_obs = P.obs_board_pool[3 * ifeat + 1];
+        const double w      = P.obs_board_pool[3 * ifeat + 2];
+        const bool outlier  = !(w >= 0.0);   // mrcal.c:4695
+        const double e0 = outlier ? 0. : (q[0] - qx_obs) * w;
+        const double e1 = outlier ? 0. : (q[1] - qy_obs) * w;
+        x[2 * ifeat + 0] = e0;
+        x[2 * ifeat + 1] = e1;
+        sumsq += e0 * e0 + e1 * e1;
+
+        if constexpr(WITH_J)
+        {
+            // G2 = dq/dv : gradient wrt the point in reference coords
+            double G2[2][3];
+            if(cam_identity)
+            {
+#pragma unroll
+                for(int k = 0; k < 2; k++) { G2[k][0] = dq_dp[k][0]; G2[k][1] = dq_dp[k][1]; G2[k][2] = dq_dp[k][2]; }
+            }
+            else
+            {
+#pragma unroll
+                for(int k = 0; k < 2; k++)
+#pragma unroll
+                    for(int j = 0; j < 3; j++)
+                        G2[k][j] = dq_dp[k][0] * G.Rc[j] + dq_dp[k][1] * G.Rc[3 + j] + dq_dp[k][2] * G.Rc[6 + j];
+            }
+            // frame rotation: dv/drf_k = dRf[k] pt
+            double dq_drf[2][3], dq_drc[2][3];
+            if(P.opt_frames)
+            {
+#pragma unroll
+                for(int k = 0; k < 3; k++)
+                {
+                    double dv[3];
+                    mat3_vec(dv, &G.dRf[9 * k], pt);
+                    dq_drf[0][k] = G2[0][0] * dv[0] + G2[0][1] * dv[1] + G2[0][2] * dv[2];
+                    dq_drf[1][k] = G2[1][0] * dv[0] + G2[1][1] * dv[1] + G2[1][2] * dv[2];
+                }
+            }
+            if(emit_cam)
+            {
+#pragma unroll
+                for(int k = 0; k < 3; k++)
+                {
+                    double dp[3];
+                    mat3_vec(dp, &G.dRc[9 * k], v);
+                    dq_drc[0][k] = dq_dp[0][0] * dp[0] + dq_dp[0][1] * dp[1] + dq_dp[0][2] * dp[2];
+                    dq_drc[1][k] = dq_dp[1][0] * dp[0] + dq_dp[1][1] * dp[1] + dq_dp[1][2] * dp[2];
+                }
+            }
+            // warp: dpt_z/dwarp_i = dz[i], and d v/d pt_z = Rf[:,2]  (mrcal.c:2529-2558)
+            double dq_dz[2];
+#pragma unroll
+            for(int k = 0; k < 2; k++) dq_dz[k] = G2[k][0] * G.Rf[2] + G2[k][1] * G.Rf[5] + G2[k][2] * G.Rf[8];
+
+            const int ivar0s = ivar0 - (P.opt_core ? 0 : 4);
+            const size_t jbase = (size_t)P.board_j0[iobs] + (size_t)(2 * ipt) * nnz_row;
+#pragma unroll
+            for(int i_xy = 0; i_xy < 2; i_xy++)
+            {
+                double* jv = Jval + jbase + (size_t)i_xy * nnz_row;
+                int*    jc = Jcol + jbase + (size_t)i_xy * nnz_row;
+                double g_f;
+                if constexpr(LensTraits<KIND>::SPLINED) g_f = upd[i_xy];
+                else                                    g_f = (q[i_xy] - intr[2 + i_xy]) / intr[i_xy];   // mrcal.c:1427-1431
+                int n = emit_intrinsics<KIND>(jv, jc, P, i_var_intr, i_xy, w, outlier, g_f, ddist[i_xy], wx, wy, ivar0s, intr[i_xy]);
+                if(emit_cam)
+                {
+#pragma unroll
+                    for(int k = 0; k < 3; k++) { jc[n] = i_var_cam + k;     jv[n] = outlier ? 0. : dq_drc[i_xy][k] * w * kScaleRotCam;   n++; }
+#pragma unroll
+                    for(int k = 0; k < 3; k++) { jc[n] = i_var_cam + 3 + k; jv[n] = outlier ? 0. : dq_dp[i_xy][k] * w * kScaleTransCam;  n++; }
+                }
+                if(P.opt_frames)
+                {
+#pragma unroll
+                    for(int k = 0; k < 3; k++) { jc[n] = i_var_frame + k;     jv[n] = outlier ? 0. : dq_drf[i_xy][k] * w * kScaleRotFrame; n++; }
+#pragma unroll
+                    for(int k = 0; k < 3; k++) { jc[n] = i_var_frame + 3 + k; jv[n] = outlier ? 0. : G2[i_xy][k] * w * kScaleTransFrame;   n++; }
+                }
+                if(P.opt_warp)
+                {
+#pragma unroll
+                    for(int k = 0; k < 2; k++) { jc[n] = P.i_warp0 + k; jv[n] = outlier ? 0. : dq_dz[i_xy] * dz[k] * w * kScaleWarp; n++; }
+                }
+            }
+        }
+    }
+    const double s = block_sum(sumsq, red);
+    if(threadIdx.x == 0 && s != 0.) atomicAdd(norm2, s);
+}
+
+// One thread per discrete-point observation (two rows). mrcal.c:4902-5176
+template <int KIND, bool WITH_J>
+__global__ void __launch_bounds__(128)
+eval_points_kernel(DevProblem P, double* __restrict__ x, double* __restrict__ Jval, int* __restrict__ Jcol,
+                   double* __restrict__ norm2)
+{
+    __shared__ double red[32];
+    const int iobs = blockIdx.x * blockDim.x + threadIdx.x;
+    double sumsq = 0.;
+    if(iobs < P.Nobs_point)
+    {
+        const int icam_i  = P.obs_point[3 * iobs + 0];
+        const int icam_e  = P.obs_point[3 * iobs + 1];
+        const int i_point = P.obs_point[3 * iobs + 2];
+        const bool cam_identity = icam_e < 0;
+        const bool point_in_state = P.opt_frames && i_point < P.Npoints_variable;
+        const bool emit_cam = P.opt_extr && !cam_identity;
+        const double* __restrict__ intr = &P.u_intr[(size_t)icam_i * P.Nintr];
+        const int i_var_intr  = P.i_intr0 + icam_i * P.Nintr_state;
+        const int i_var_cam   = P.i_extr0 + 6 * icam_e;
+        const int i_var_point = P.i_point0 + 3 * i_point;
+        const int nnz_row = P.nnz_row_intr + (emit_cam ? 6 : 0) + (point_in_state ? 3 : 0);
+
+        const double w = P.obs_point_pool[3 * iobs + 2];
+        const bool outlier = w <= 0.0;   // mrcal.c:4918 (note: <=, unlike boards)
+        const int m = P.m_point0 + 2 * iobs;
+
+        double q[2] = {0., 0.}, dq_dp[2][3] = {};
+        double ddist[2][LensTraits<KIND>::NDIST > 0 ? LensTraits<KIND>::NDIST : 1] = {};
+        double wx[4] = {}, wy[4] = {}, upd[2] = {0., 0.};
+        double Rc[9], dRc[27], pr[3] = {0., 0., 0.};
+        int ivar0 = 4;   // outliers name the first control points (mrcal.c:4965-4975)
+        if(!outlier)
+        {
+            pr[0] = P.u_points[3 * i_point + 0];
+            pr[1] = P.u_points[3 * i_point + 1];
+            pr[2] = P.u_points[3 * i_point + 2];
+            double p[3] = {pr[0], pr[1], pr[2]};
+            if(!cam_identity)
+            {
+                const double* rt = &P.u_rtcam[6 * icam_e];
+                rodrigues(Rc, WITH_J ? dRc : nullptr, rt);
+                mat3_vec(p, Rc, pr);
+                p[0] += rt[3]; p[1] += rt[4]; p[2] += rt[5];
+            }
+            if constexpr(LensTraits<KIND>::SPLINED)
+                project_splined<LensTraits<KIND>::RUN>(q, dq_dp, wx, wy, &ivar0, upd, p, intr, P.Nx, P.Ny, P.segments_per_u);
+            else
+                project_parametric<KIND>(q, dq_dp, WITH_J ? ddist : nullptr, p, intr);
+        }
+        const double e0 = outlier ? 0. : (q[0] - P.obs_point_pool[3 * iobs + 0]) * w;
+        const double e1 = outlier ? 0. : (q[1] - P.obs_point_pool[3 * iobs + 1]) * w;
+        x[m + 0] = e0;
+        x[m + 1] = e1;
+        sumsq = e0 * e0 + e1 * e1;
+
+        if constexpr(WITH_J)
+        {
+            const int ivar0s = ivar0 - (P.opt_core ? 0 : 4);
+            const size_t jbase = (size_t)P.point_j0[iobs];
+#pragma unroll
+            for(int i_xy = 0; i_xy < 2; i_xy++)
+            {
+                double* jv = Jval + jbase + (size_t)i_xy * nnz_row;
+                int*    jc = Jcol + jbase + (size_t)i_xy * nnz_row;
+                double g_f = 0.;
+                if(!outlier)
+                {
+                    if constexpr(LensTraits<KIND>::SPLINED) g_f = upd[i_xy];
+                    else                                    g_f = (q[i_xy] - intr[2 + i_xy]) / intr[i_xy];
+                }
+                int n;
+                if(outlier && LensTraits<KIND>::SPLINED)
+                {
+                    // structural zeros at the first RUN*RUN distortion columns, contiguous (mrcal.c:4960-4976)
+                    n = 0;
+                    if(P.opt_core)
+                    {
+                        jc[n] = i_var_intr + i_xy;     jv[n] = 0.; n++;
+                        jc[n] = i_var_intr + i_xy + 2; jv[n] = 0.; n++;
+                    }
+                    if(P.opt_dist)
+                        for(int i = 0; i < LensTraits<KIND>::RUN * LensTraits<KIND>::RUN; i++)
+                        { jc[n] = i_var_intr + P.Ncore_state + i; jv[n] = 0.; n++; }
+                }
+                else
+                    n = emit_intrinsics<KIND>(jv, jc, P, i_var_intr, i_xy, w, outlier, g_f, ddist[i_xy], wx, wy, ivar0s, intr[i_xy]);
+                if(emit_cam)
+                {
+#pragma unroll
+                    for(int k = 0; k < 3; k++)
+                    {
+                        double val = 0.;
+                        if(!outlier)
+                        {
+                            double dp[3];
+                            mat3_vec(dp, &dRc[9 * k], pr);
+                            val = (dq_dp[i_xy][0] * dp[0] + dq_dp[i_xy][1] * dp[1] + dq_dp[i_xy][2] * dp[2]) * w * kScaleRotCam;
+                        }
+                        jc[n] = i_var_cam + k; jv[n] = val; n++;
+                    }
+#pragma unroll
+                    for(int k = 0; k < 3; k++) { jc[n] = i_var_cam + 3 + k; jv[n] = outlier ? 0. : dq_dp[i_xy][k] * w * kScaleTransCam; n++; }
+                }
+                if(point_in_state)
+                {
+#pragma unroll
+                    for(int k = 0; k < 3; k++)
+                    {
+                        double val = 0.;
+                        if(!outlier)
+                        {
+                            if(cam_identity) val = dq_dp[i_xy][k];
+                            else             val = dq_dp[i_xy][0] * Rc[k] + dq_dp[i_xy][1] * Rc[3 + k] + dq_dp[i_xy][2] * Rc[6 + k];
+                            val *= w * kScalePoint;
+                        }
+                        jc[n] = i_var_point + k; jv[n] = val; n++;
+                    }
+                }
+            }
+        }
+    }
+    const double s = block_sum(sumsq, red);
+    if(threadIdx.x == 0 && s != 0.) atomicAdd(norm2, s);
+}
+
+// Regularization rows, one thread each. mrcal.c:5655-5955
+template <bool WITH_J>
+__global__ void __launch_bounds__(128)
+eval_regularization_kernel(DevProblem P, bool splined, double* __restrict__ x, double* __restrict__ Jval,
+                           int* __restrict__ Jcol, double* __restrict__ norm2)
+{
+    __shared__ double red[32];
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    const int Ndist_rows   = (P.reg && P.opt_dist) ? P.Ncam_i * (P.Nintr - 4) : 0;
+    const int Ncenter_rows = (P.reg && P.opt_core) ? P.Ncam_i * 2 : 0;
+    const int Nunity_rows  = P.reg_unity ? 1 : 0;
+    const double nominal_pixel_error = 0.1;
+    double err = 0.;
+    if(t < Ndist_rows)
+    {
+        const int m = P.m_reg0 + t;
+        if(splined)
+        {
+            // per knot: a radial row then a (10x heavier) tangential row (:5709-5786)
+            const double scale = nominal_pixel_error / 10.0;
+            const int per_cam = P.Nintr - 4;
+            const int cam = t / per_cam, r = t - cam * per_cam;
+            const int knot = r >> 1, which = r & 1;
+            const int iy = knot / P.Nx, ix = knot - iy * P.Nx;
+            const double* d = &P.u_intr[(size_t)cam * P.Nintr + 4 + 2 * knot];
+            double ux = (double)(2 * ix - P.Nx + 1), uy = (double)(2 * iy - P.Ny + 1);
+            bool anisotropic = true;
+            if(2 * ix == P.Nx - 1 && 2 * iy == P.Ny - 1) { ux = 1.0; anisotropic = false; }
+            else { const double mag = sqrt(ux * ux + uy * uy); ux /= mag; uy /= mag; }
+            const int col = P.i_intr0 + cam * P.Nintr_state + P.Ncore_state + 2 * knot;
+            double g0, g1;
+            if(which == 0) { err = scale * (d[0] * ux + d[1] * uy); g0 = scale * ux; g1 = scale * uy; }
+            else
+            {
+                const double extra = anisotropic ? 10. : 1.;
+                err = scale * extra * (d[0] * uy - d[1] * ux);
+                g0 = scale * extra * uy; g1 = -scale * extra * ux;
+            }
+            x[m] = err;
+            if constexpr(WITH_J)
+            {
+                const size_t j = (size_t)P.reg_j0 + 2 * (size_t)t;
+                Jcol[j] = col;     Jval[j]     = g0 * kScaleDistortion;
+                Jcol[j + 1] = col + 1; Jval[j + 1] = g1 * kScaleDistortion;
+            }
+        }
+        else
+        {
+            // L2 on each distortion; the rational denominator terms of OPENCV8+ 5x heavier (:5787-5850)
+            const double scale = nominal_pixel_error / 1.0;
+            const int per_cam = P.Nintr - 4;
+            const int cam = t / per_cam, j = t - cam * per_cam;
+            const double scale_here = (P.opencv8plus && 5 <= j && j <= 7) ? scale * 5. : scale;
+            err = scale_here * P.u_intr[(size_t)cam * P.Nintr + 4 + j];
+            x[m] = err;
+            if constexpr(WITH_J)
+            {
+                const size_t jj = (size_t)P.reg_j0 + t;
+                Jcol[jj] = P.i_intr0 + cam * P.Nintr_state + P.Ncore_state + j;
+                Jval[jj] = scale_here * kScaleDistortion;
+            }
+        }
+    }
+    else if(t < Ndist_rows + Ncenter_rows)
+    {
+        // optical centre near the middle of the imager (:5853-5901). The scale is
+        // derived from camera 0's width for every camera, as in the reference
+        const int r = t - Ndist_rows;
+        const int cam = r >> 1, k = r & 1;
+        const double scale = nominal_pixel_error / ((double)P.imagersizes[0] * 0.1);
+        const double target = 0.5 * (double)(P.imagersizes[2 * cam + k] - 1);
+        err = scale * (P.u_intr[(size_t)cam * P.Nintr + 2 + k] - target);
+        x[P.m_reg0 + t] = err;
+        if constexpr(WITH_J)
+        {
+            const size_t jj = (size_t)P.reg_j0 + (size_t)(splined ? 2 : 1) * Ndist_rows + r;
+            Jcol[jj] = P.i_intr0 + cam * P.Nintr_state + 2 + k;
+            Jval[jj] = scale * kScaleCenter;
+        }
+    }
+    else if(t < Ndist_rows + Ncenter_rows + Nunity_rows)
+    {
+        // |t_cam0|^2 -> 1 (:5903-5954)
+        const double scale = nominal_pixel_error / 0.01;
+        const double* tt = &P.u_rtcam[3];
+        err = scale * (tt[0] * tt[0] + tt[1] * tt[1] + tt[2] * tt[2] - 1.);
+        x[P.m_reg0 + t] = err;
+        if constexpr(WITH_J)
+        {
+            const size_t jj = (size_t)P.reg_j0 + (size_t)(splined ? 2 : 1) * Ndist_rows + Ncenter_rows;
+            for(int i = 0; i < 3; i++)
+            {
+                Jcol[jj + i] = P.i_extr0 + 3 + i;
+                Jval[jj + i] = scale * kScaleTransCam * 2. * tt[i];
+            }
+        }
+    }
+    const double s = block_sum(err * err, red);
+    if(threadIdx.x == 0 && s != 0.) atomicAdd(norm2, s);
+}
+
+// CSR row pointers. Analytic: every row of an observation has the same width
+__global__ void fill_rowptr_kernel(DevProblem P, bool splined, int nnz_total, int* __restrict__ rowptr)
+{
+    const int m = blockIdx.x * blockDim.x + threadIdx.x;
+    if(m > P.Nmeas) return;
+    if(m == P.Nmeas) { rowptr[m] = nnz_total; return; }
+    if(m < P.m_point0)
+    {
+        const int per_obs = 2 * P.W * P.H;
+        const int iobs = m / per_obs, r = m - iobs * per_obs;
+        const int j0 = P.board_j0[iobs], j1 = P.board_j0[iobs + 1];
+        rowptr[m] = j0 + r * ((j1 - j0) / per_obs);
+    }
+    else if(m < P.m_reg0)
+    {
+        const int r = m - P.m_point0;
+        const int iobs = r >> 1;
+        const int j0 = P.point_j0[iobs], j1 = P.point_j0[iobs + 1];
+        rowptr[m] = j0 + (r & 1) * ((j1 - j0) / 2);
+    }
+    else
+    {
+        const int t = m - P.m_reg0;
+        const int Ndist_rows   = (P.reg && P.opt_dist) ? P.Ncam_i * (P.Nintr - 4) : 0;
+        const int Ncenter_rows = (P.reg && P.opt_core) ? P.Ncam_i * 2 : 0;
+        const int wd = splined ? 2 : 1;
+        if(t < Ndist_rows)                      rowptr[m] = P.reg_j0 + wd * t;
+        else if(t < Ndist_rows + Ncenter_rows)  rowptr[m] = P.reg_j0 + wd * Ndist_rows + (t - Ndist_rows);
+        else                                    rowptr[m] = P.reg_j0 + wd * Ndist_rows + Ncenter_rows;
+    }
+}
+
+template <int KIND>
+static bool launch_kind(const DevProblem& dp, const EvalBuffers& out, bool with_j, cudaStream_t stream, int* nlaunch)
+{
+    if(dp.Nobs_board > 0)
+    {
+        int threads = ((dp.W * dp.H + 31) / 32) * 32;
+        if(threads > 256) threads = 256;
+        if(threads < 64) threads = 64;
+        if(with_j) eval_boards_kernel<KIND, true ><<<dp.Nobs_board, threads, 0, stream>>>(dp, out.x, out.Jval, out.Jcol, out.norm2);
+        else       eval_boards_kernel<KIND, false><<<dp.Nobs_board, threads, 0, stream>>>(dp, out.x, out.Jval, out.Jcol, out.norm2);
+        (*nlaunch)++;
+    }
+    if(dp.Nobs_point > 0)
+    {
+        const int threads = 128, blocks = (dp.Nobs_point + threads - 1) / threads;
+        if(with_j) eval_points_kernel<KIND, true ><<<blocks, threads, 0, stream>>>(dp, out.x, out.Jval, out.Jcol, out.norm2);
+        else       eval_points_kernel<KIND, false><<<blocks, threads, 0, stream>>>(dp, out.x, out.Jval, out.Jcol, out.norm2);
+        (*nlaunch)++;
+    }
+    return true;
+}
+
+bool launch_unpack_state(const DevProblem& dp, const double* b_packed, cudaStream_t stream, int* nlaunch)
+{
+    const int n = dp.Ncam_i * dp.Nintr + dp.Ncam_e * 6 + dp.Nframes * 6 + dp.Npoints * 3 + 2;
+    unpack_state_kernel<<<(n + 255) / 256, 256, 0, stream>>>(dp, b_packed);
+    if(nlaunch) (*nlaunch)++;
+    MB200_CUDA_CHECK(cudaGetLastError());
+    return true;
+}
+
+bool launch_evaluate(const DevProblem& dp, const EvalBuffers& out, bool with_jacobian,
+                     int* Jrowptr, cudaStream_t stream, int* nlaunch)
+{
+    int dummy = 0;
+    if(nlaunch == nullptr) nlaunch = &dummy;
+    MB200_CUDA_CHECK(cudaMemsetAsync(out.norm2, 0, sizeof(double), stream));
+    if(!launch_unpack_state(dp, out.p, stream, nlaunch)) return false;
+    switch(dp.lens_kind)
+    {
+    case LENS_PINHOLE:       launch_kind<LENS_PINHOLE>(dp, out, with_jacobian, stream, nlaunch); break;
+    case LENS_STEREOGRAPHIC: launch_kind<LENS_STEREOGRAPHIC>(dp, out, with_jacobian, stream, nlaunch); break;
+    case LENS_LONLAT:        launch_kind<LENS_LONLAT>(dp, out, with_jacobian, stream, nlaunch); break;
+    case LENS_LATLON:        launch_kind<LENS_LATLON>(dp, out, with_jacobian, stream, nlaunch); break;
+    case LENS_OPENCV4:       launch_kind<LENS_OPENCV4>(dp, out, with_jacobian, stream, nlaunch); break;
+    case LENS_OPENCV5:       launch_kind<LENS_OPENCV5>(dp, out, with_jacobian, stream, nlaunch); break;
+    case LENS_OPENCV8:       launch_kind<LENS_OPENCV8>(dp, out, with_jacobian, stream, nlaunch); break;
+    case LENS_OPENCV12:      launch_kind<LENS_OPENCV12>(dp, out, with_jacobian, stream, nlaunch); break;
+    case LENS_SPLINED3:      launch_kind<LENS_SPLINED3>(dp, out, with_jacobian, stream, nlaunch); break;
+    case LENS_SPLINED2:      launch_kind<LENS_SPLINED2>(dp, out, with_jacobian, stream, nlaunch); break;
+    default: set_error("lens model kind %d has no CUDA implementation", dp.lens_kind); return false;
+    }
+    const bool splined = dp.lens_kind == LENS_SPLINED3 || dp.lens_kind == LENS_SPLINED2;
+    const int Nreg = dp.Nmeas - dp.m_reg0;
+    if(Nreg > 0)
+    {
+        const int threads = 128, blocks = (Nreg + threads - 1) / threads;
+        if(with_jacobian) eval_regularization_kernel<true ><<<blocks, threads, 0, stream>>>(dp, splined, out.x, out.Jval, out.Jcol, out.norm2);
+        else              eval_regularization_kernel<false><<<blocks, threads, 0, stream>>>(dp, splined, out.x, out.Jval, out.Jcol, out.norm2);
+        (*nlaunch)++;
+    }
+    if(Jrowptr != nullptr)
+    {
+        // nnz_total: after the last regularization entry
+        const int Ndist_rows   = (dp.reg && dp.opt_dist) ? dp.Ncam_i * (dp.Nintr - 4) : 0;
+        const int Ncenter_rows = (dp.reg && dp.opt_core) ? dp.Ncam_i * 2 : 0;
+        const int nnz_total = dp.reg_j0 + (splined ? 2 : 1) * Ndist_rows + Ncenter_rows + (dp.reg_unity ? 3 : 0);
+        fill_rowptr_kernel<<<(dp.Nmeas + 1 + 255) / 256, 256, 0, stream>>>(dp, splined, nnz_total, Jrowptr);
+        (*nlaunch)++;
+    }
+    MB200_CUDA_CHECK(cudaGetLastError());
+    return true;
+}
+
+}  // namespace mb200

@@ -1,0 +1,90 @@
+"""Small seeded problems shared by the golden-fixture generator and the tests.
+
+Every case is rebuilt from mrcal_b200.synthetic.make_problem() with a fixed seed,
+so the inputs exist wherever the repo does; tests/golden/callback_cases.npz holds
+what the COMPILED REFERENCE computed for them (tests/golden/make_golden.py)."""
+import numpy as np
+
+from mrcal_b200 import synthetic
+
+SPL3 = "LENSMODEL_SPLINED_STEREOGRAPHIC_order=3_Nx=11_Ny=8_fov_x_deg=150"
+SPL2 = "LENSMODEL_SPLINED_STEREOGRAPHIC_order=2_Nx=12_Ny=9_fov_x_deg=150"
+SPL3_BIG = "LENSMODEL_SPLINED_STEREOGRAPHIC_order=3_Nx=30_Ny=20_fov_x_deg=170"
+
+
+def _sel(core, dist, extr, frames, warp, reg=True, unity=False):
+    return dict(do_optimize_intrinsics_core=core, do_optimize_intrinsics_distortions=dist,
+                do_optimize_extrinsics=extr, do_optimize_frames=frames, do_optimize_calobject_warp=warp,
+                do_apply_regularization=reg, do_apply_regularization_unity_cam01=unity)
+
+
+def _mark_outliers(inputs, n, seed):
+    rng = np.random.default_rng(seed)
+    o = inputs["observations_board"]
+    flat = o.reshape(-1, 3)
+    i = rng.choice(flat.shape[0], n, replace=False)
+    flat[i, 2] *= -1.
+    return inputs
+
+
+def golden_cases():
+    """(name, optimization_inputs). Small: the whole set evaluates in seconds."""
+    cases = []
+
+    def add(name, lensmodel, Ncameras, Nframes, sel=None, W=6, H=5, outliers=0, Npoints=0, Npoints_fixed=0,
+            which="all", point_outliers=0, seed=3, nowarp=False):
+        inp, _ = synthetic.make_problem(lensmodel=lensmodel, Ncameras=Ncameras, Nframes=Nframes, W=W, H=H,
+                                        seed=seed, pixel_noise=0.3, which=which, Npoints=Npoints,
+                                        Npoints_fixed=Npoints_fixed)
+        inp["calobject_warp"] = np.array((1e-3, -2e-3))   # away from 0 so its gradient is exercised
+        if nowarp:
+            del inp["calobject_warp"]
+            inp["do_optimize_calobject_warp"] = False
+        if sel is not None:
+            inp.update(sel)
+        if outliers:
+            _mark_outliers(inp, outliers, seed)
+        if point_outliers:
+            # both flavours of "outlier" for points: weight <0 and weight ==0 (mrcal.c:4918)
+            inp["observations_point"][:point_outliers, 2] = np.array((-1., 0.))[np.arange(point_outliers) % 2]
+        cases.append((name, inp))
+
+    for lm, tag in (("LENSMODEL_PINHOLE", "pinhole"), ("LENSMODEL_STEREOGRAPHIC", "stereographic"),
+                    ("LENSMODEL_LONLAT", "lonlat"), ("LENSMODEL_LATLON", "latlon"),
+                    ("LENSMODEL_OPENCV4", "opencv4"), ("LENSMODEL_OPENCV5", "opencv5"),
+                    ("LENSMODEL_OPENCV8", "opencv8"), ("LENSMODEL_OPENCV12", "opencv12")):
+        add(f"{tag}_2cam_all", lm, 2, 4, _sel(True, True, True, True, True))
+    add("splined3_2cam_corelocked", SPL3, 2, 4, _sel(False, True, True, True, True), outliers=7)
+    add("splined3_3cam_all", SPL3, 3, 3, _sel(True, True, True, True, True), which="some")
+    add("splined2_2cam_corelocked", SPL2, 2, 4, _sel(False, True, True, True, True), outliers=5)
+    add("splined2_2cam_coreonly", SPL2, 2, 3, _sel(True, False, True, True, False))
+    add("opencv8_1cam", "LENSMODEL_OPENCV8", 1, 5, _sel(True, True, False, True, True))
+    add("opencv8_intrinsics_only", "LENSMODEL_OPENCV8", 2, 3, _sel(True, True, False, False, False))
+    add("opencv8_frames_only", "LENSMODEL_OPENCV8", 2, 3, _sel(False, False, False, True, False))
+    add("opencv8_extrinsics_warp", "LENSMODEL_OPENCV8", 3, 3, _sel(False, False, True, False, True, reg=False))
+    add("opencv4_unity", "LENSMODEL_OPENCV4", 3, 3, _sel(True, True, True, True, True, unity=True), outliers=4)
+    add("opencv8_noreg_outliers", "LENSMODEL_OPENCV8", 2, 4, _sel(True, True, True, True, True, reg=False), outliers=9)
+    add("opencv8_nowarp_input", "LENSMODEL_OPENCV8", 2, 3, _sel(True, True, True, True, False), nowarp=True)
+    add("opencv8_points", "LENSMODEL_OPENCV8", 2, 3, _sel(True, True, True, True, True), Npoints=7, point_outliers=2)
+    add("opencv8_points_fixed", "LENSMODEL_OPENCV8", 3, 3, _sel(True, True, True, True, True), Npoints=8,
+        Npoints_fixed=3, which="some")
+    add("splined3_points", SPL3, 2, 3, _sel(False, True, True, True, True), Npoints=6, point_outliers=1)
+    add("splined3_points_core", SPL3, 2, 3, _sel(True, True, True, True, True), Npoints=6, Npoints_fixed=2,
+        point_outliers=2)
+    add("pinhole_points_noframes", "LENSMODEL_PINHOLE", 2, 3, _sel(True, False, True, False, False), Npoints=5)
+    return cases
+
+
+def layout_numbers(P):
+    """A fixed list of layout integers for an oracle Problem (oracle/ref.py)."""
+    out = [P.num_states(), P.num_measurements(), P.num_j_nonzero()]
+    for what in ("intrinsics", "extrinsics", "frames", "points", "calobject_warp"):
+        out.append(P.num_states_of(what))
+    for what, i in (("intrinsics", 0), ("intrinsics", 1), ("extrinsics", 0), ("extrinsics", 1), ("frames", 0),
+                    ("frames", 2), ("points", 0), ("points", 3), ("calobject_warp", 0)):
+        out.append(P.state_index(what, i))
+    for what, i in (("boards", 0), ("boards", 2), ("points", 0), ("points", 1), ("regularization", 0)):
+        out.append(P.measurement_index(what, i))
+    for what in ("boards", "points", "regularization"):
+        out.append(P.num_measurements_of(what))
+    return out
