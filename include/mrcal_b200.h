@@ -448,6 +448,13 @@ bool mrcal_b200_problem_optimize(mrcal_b200_problem_t* problem,
                                  const mrcal_b200_solver_parameters_t* parameters,
                                  mrcal_stats_t* stats, mrcal_b200_solve_info_t* info);
 
+// Introspection (tests, debugging): the reduced normal equations at the current
+// state, after the frame/point blocks have been eliminated. n_reduced <- number
+// of shared unknowns; S_out [n_reduced][n_reduced] row-major, LOWER triangle
+// valid; g_reduced [n_reduced]; g_full [Nstate] = J'x. Any output may be NULL
+bool mrcal_b200_problem_reduced_system(mrcal_b200_problem_t* problem, double lambda, int* n_reduced,
+                                       double* S_out, double* g_reduced, double* g_full);
+
 // Copy results to the host: the packed state, the residuals, the unpacked
 // solution and the (possibly outlier-marked) board observation pool. Any may be NULL
 bool mrcal_b200_problem_download(mrcal_b200_problem_t* problem,

@@ -99,6 +99,7 @@ EXPORTED_SYMBOLS = (
     "mrcal_b200_problem_num_states", "mrcal_b200_problem_num_measurements",
     "mrcal_b200_problem_num_j_nonzero", "mrcal_b200_problem_reset", "mrcal_b200_problem_upload",
     "mrcal_b200_problem_callback", "mrcal_b200_problem_optimize", "mrcal_b200_problem_download",
+    "mrcal_b200_problem_reduced_system",
     "mrcal_b200_problem_time_callback",
     "mrcal_b200_nccl_get_unique_id", "mrcal_b200_nccl_comm_init", "mrcal_b200_nccl_comm_destroy",
     "mrcal_b200_problem_set_sharding",
@@ -122,7 +123,7 @@ for _n in _int_fns + ["mrcal_lensmodel_num_params", "mrcal_lensmodel_type_from_n
 for _n in ["mrcal_lensmodel_from_name", "mrcal_lensmodel_name", "mrcal_knots_for_splined_models",
            "mrcal_corresponding_icam_extrinsics", "mrcal_optimizer_callback",
            "mrcal_b200_problem_reset", "mrcal_b200_problem_upload", "mrcal_b200_problem_callback",
-           "mrcal_b200_problem_optimize", "mrcal_b200_problem_download",
+           "mrcal_b200_problem_optimize", "mrcal_b200_problem_download", "mrcal_b200_problem_reduced_system",
            "mrcal_b200_nccl_get_unique_id", "mrcal_b200_nccl_comm_init", "mrcal_b200_problem_set_sharding",
            "mrcal_b200_factorization_solve_xt_JtJ_bt"]:
     getattr(lib, _n).restype = C.c_bool

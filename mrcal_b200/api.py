@@ -442,6 +442,19 @@ class Problem:
         return dict(b_packed=b, x=x, intrinsics=intr, rt_cam_ref=rtc, rt_ref_frame=rtf, points=pts,
                     calobject_warp=warp, observations_board=obs)
 
+    def reduced_system(self, lambda_=0.0):
+        """(S, g_reduced, g_full): the Schur-reduced normal equations at the current state (introspection)."""
+        n = C.c_int(0)
+        if not lib.mrcal_b200_problem_reduced_system(self._h, C.c_double(lambda_), C.byref(n), None, None, None):
+            raise RuntimeError(_capi.last_error())
+        S = np.zeros((n.value, n.value))
+        g = np.zeros(n.value)
+        gf = np.zeros(self.Nstate)
+        if not lib.mrcal_b200_problem_reduced_system(self._h, C.c_double(lambda_), C.byref(n), _ptr(S), _ptr(g), _ptr(gf)):
+            raise RuntimeError(_capi.last_error())
+        S = np.tril(S) + np.tril(S, -1).T
+        return S, g, gf
+
     def time_callback(self, N=10, jacobian=True):
         ms = lib.mrcal_b200_problem_time_callback(self._h, int(N), C.c_bool(jacobian))
         if ms < 0:

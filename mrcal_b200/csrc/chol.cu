@@ -1,0 +1,424 @@
+// Kernel family 2b: dense Cholesky factorization and triangular solves of the
+// reduced (camera) normal equations, fp64, on the DMMA (fp64 tensor) pipe.
+//
+// Stands in for what the reference gets from CHOLMOD through libdogleg
+// (cholmod_factorize / cholmod_solve; call sites mrcal.c:6435 and
+// mrcal-pywrap.c:196-212, 557). The reference factors the full sparse JtJ with
+// a simplicial LDL'; here the frame/point blocks have already been eliminated
+// (normal.cu), what is left is small and dense, and it is factored as L L'
+// with a two-level blocked right-looking algorithm:
+//
+//   for each 256-column outer panel:
+//       for each 64-column inner block of it:
+//           potrf_diag   one CTA: factor the 64x64 diagonal block in shared
+//                        memory, and invert the factor (for the TRSMs/solves)
+//           trsm         rows below: X <- A inv(L_kk)'   (small GEMM)
+//           syrk (K=64)  update of the REST OF THE PANEL only
+//       syrk (K=256)     one DMMA update of the whole trailing matrix
+//
+// Storage: row-major n x n, lower triangle, n padded to a multiple of 64 (the
+// caller puts 1 on the padding diagonal). Rows are K-contiguous, which is what
+// mma.sync.m8n8k4.row.col.f64 wants for both operands of  C -= P P'.
+#include <cuda_runtime.h>
+#include <cstdint>
+
+#include "chol.h"
+#include "problem.h"
+
+namespace mb200 {
+
+constexpr int NB = 64;     // inner block
+constexpr int NBO = 256;   // outer panel
+
+////////////////////////////////////////////////////////////////////////////////
+// diagonal block: Cholesky + inverse of the factor, one CTA of 256 threads
+////////////////////////////////////////////////////////////////////////////////
+__global__ void __launch_bounds__(256)
+potrf_diag_kernel(double* __restrict__ A, int ld, int k0, double* __restrict__ invL, int* __restrict__ info, int nreal)
+{
+    extern __shared__ __align__(16) double dsm[];
+    double (*s)[NB + 1] = reinterpret_cast<double (*)[NB + 1]>(dsm);
+    double (*x)[NB + 1] = reinterpret_cast<double (*)[NB + 1]>(dsm + NB * (NB + 1));
+    __shared__ int bad;
+    const int tid = threadIdx.x;
+    if(tid == 0) bad = 0;
+    for(int e = tid; e < NB * NB; e += 256)
+    {
+        const int i = e / NB, j = e % NB;
+        s[i][j] = j <= i ? A[(size_t)(k0 + i) * ld + k0 + j] : 0.;
+    }
+    __syncthreads();
+    for(int j = 0; j < NB; j++)
+    {
+        if(tid == 0)
+        {
+            const double d = s[j][j];
+            if(!(d > 0.))
+            {
+                // not positive definite. Remember the first failing pivot; keep
+                // going with a harmless value so the kernel chain terminates
+                if(k0 + j < nreal && bad == 0) { bad = 1; atomicCAS(info, 0, k0 + j + 1); }
+                s[j][j] = 1.;
+            }
+            else
+                s[j][j] = sqrt(d);
+        }
+        __syncthreads();
+        const double djj = s[j][j];
+        if(tid > j && tid < NB) s[tid][j] /= djj;
+        __syncthreads();
+        // trailing update of the block: s[i][k] -= s[i][j] s[k][j], j < k <= i
+        const int m = NB - 1 - j;
+        for(int e = tid; e < m * m; e += 256)
+        {
+            const int i = j + 1 + e / m, k = j + 1 + e % m;
+            if(k <= i) s[i][k] -= s[i][j] * s[k][j];
+        }
+        __syncthreads();
+    }
+    for(int e = tid; e < NB * NB; e += 256)
+    {
+        const int i = e / NB, j = e % NB;
+        if(j <= i) A[(size_t)(k0 + i) * ld + k0 + j] = s[i][j];
+    }
+    // X = inv(L): 4 threads per column c share each dot product
+    {
+        const int c = tid >> 2, part = tid & 3;
+        for(int i = 0; i < NB; i++)
+        {
+            double acc = 0.;
+            if(i > c)
+                for(int k = c + part; k < i; k += 4) acc += s[i][k] * x[k][c];
+            acc += __shfl_xor_sync(0xffffffffu, acc, 1);
+            acc += __shfl_xor_sync(0xffffffffu, acc, 2);
+            if(part == 0) x[i][c] = i < c ? 0. : (i == c ? 1. / s[i][i] : -acc / s[i][i]);
+            __syncwarp();
+        }
+    }
+    __syncthreads();
+    for(int e = tid; e < NB * NB; e += 256) invL[e] = x[e / NB][e % NB];
+}
+
+////////////////////////////////////////////////////////////////////////////////
+// panel: X[i][c] = sum_m A[i][k0+m] invL[c][m], rows i >= k0+64, in place
+////////////////////////////////////////////////////////////////////////////////
+__global__ void __launch_bounds__(256)
+trsm_kernel(double* __restrict__ A, int ld, int k0, const double* __restrict__ invL, int n)
+{
+    extern __shared__ __align__(16) double dsm[];
+    double (*sa)[NB + 1] = reinterpret_cast<double (*)[NB + 1]>(dsm);
+    double (*sl)[NB + 1] = reinterpret_cast<double (*)[NB + 1]>(dsm + NB * (NB + 1));
+    const int row0 = k0 + NB + blockIdx.x * NB;
+    const int tid = threadIdx.x;
+    for(int e = tid; e < NB * NB; e += 256)
+    {
+        const int i = e / NB, j = e % NB;
+        sa[i][j] = A[(size_t)(row0 + i) * ld + k0 + j];
+        sl[i][j] = invL[e];
+    }
+    __syncthreads();
+    // each thread: a 4x4 block of outputs
+    const int ti = (tid / 16) * 4, tc = (tid % 16) * 4;
+    double acc[4][4] = {};
+    for(int m = 0; m < NB; m++)
+    {
+        double a[4], l[4];
+#pragma unroll
+        for(int r = 0; r < 4; r++) { a[r] = sa[ti + r][m]; l[r] = sl[tc + r][m]; }
+#pragma unroll
+        for(int r = 0; r < 4; r++)
+#pragma unroll
+            for(int c = 0; c < 4; c++) acc[r][c] += a[r] * l[c];
+    }
+#pragma unroll
+    for(int r = 0; r < 4; r++)
+#pragma unroll
+        for(int c = 0; c < 4; c++) A[(size_t)(row0 + ti + r) * ld + k0 + tc + c] = acc[r][c];
+    (void)n;
+}
+
+////////////////////////////////////////////////////////////////////////////////
+// C(i,j) -= sum_{m in [k0,k1)} A(i,m) A(j,m)   for j in [c0,c1), i in [c0,n), i >= j
+// 128x128 tiles, 8 warps (4 x 2), warp tile 32 x 64 = 4 x 8 DMMA.8x8x4 tiles.
+// Operands staged through shared memory with cp.async, 3 stages of BK=16.
+////////////////////////////////////////////////////////////////////////////////
+constexpr int BM = 128, BK = 16, LDS = BK + 4, STAGES = 3;
+
+__device__ __forceinline__ void cp_async16(void* smem, const void* gmem, bool valid)
+{
+    const unsigned s = (unsigned)__cvta_generic_to_shared(smem);
+    const int sz = valid ? 16 : 0;   // src-size 0: zero-fill
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;\n" ::"r"(s), "l"(gmem), "r"(sz));
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::); }
+template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;\n" ::"n"(N)); }
+
+__device__ __forceinline__ void dmma(double& c0, double& c1, double a, double b)
+{
+    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n"
+                 : "+d"(c0), "+d"(c1) : "d"(a), "d"(b));
+}
+
+__global__ void __launch_bounds__(256, 1)
+syrk_dmma_kernel(double* __restrict__ A, int ld, int n, int c0, int c1, int k0, int k1)
+{
+    const int tj = blockIdx.x, ti = blockIdx.y;
+    if(ti < tj) return;
+    extern __shared__ __align__(16) double smem[];
+    double* sA = smem;                               // [STAGES][BM][LDS]
+    double* sB = smem + (size_t)STAGES * BM * LDS;   // [STAGES][BM][LDS]
+
+    const int row0 = c0 + ti * BM, col0 = c0 + tj * BM;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int wm = warp >> 1, wn = warp & 1;   // 4 x 2 warps
+    const int g = lane >> 2, t = lane & 3;
+
+    double acc[4][8][2];
+#pragma unroll
+    for(int i = 0; i < 4; i++)
+#pragma unroll
+        for(int j = 0; j < 8; j++) acc[i][j][0] = acc[i][j][1] = 0.;
+
+    const int nk = (k1 - k0) / BK;
+    // each thread copies 4 x 16B per operand per stage: 128 rows x 8 chunks = 1024 chunks
+    auto load_stage = [&](int stage, int kb)
+    {
+        const int kk = k0 + kb * BK;
+#pragma unroll
+        for(int it = 0; it < 4; it++)
+        {
+            const int chunk = tid + it * 256;
+            const int r = chunk >> 3, cc = (chunk & 7) * 2;
+            const int gi = row0 + r, gj = col0 + r;
+            cp_async16(&sA[((size_t)stage * BM + r) * LDS + cc], &A[(size_t)(gi < n ? gi : 0) * ld + kk + cc], gi < n);
+            cp_async16(&sB[((size_t)stage * BM + r) * LDS + cc], &A[(size_t)(gj < c1 ? gj : 0) * ld + kk + cc], gj < c1);
+        }
+    };
+#pragma unroll
+    for(int s = 0; s < STAGES - 1; s++)
+    {
+        if(s < nk) load_stage(s, s);
+        cp_async_commit();
+    }
+    for(int kb = 0; kb < nk; kb++)
+    {
+        cp_async_wait<STAGES - 2>();
+        __syncthreads();
+        {
+            const int nxt = kb + STAGES - 1;
+            if(nxt < nk) load_stage(nxt % STAGES, nxt);
+            cp_async_commit();
+        }
+        const double* a_s = &sA[((size_t)(kb % STAGES) * BM + wm * 32) * LDS];
+        const double* b_s = &sB[((size_t)(kb % STAGES) * BM + wn * 64) * LDS];
+#pragma unroll
+        for(int ks = 0; ks < BK / 4; ks++)
+        {
+            double af[4], bf[8];
+#pragma unroll
+            for(int i = 0; i < 4; i++) af[i] = a_s[(i * 8 + g) * LDS + ks * 4 + t];
+#pragma unroll
+            for(int j = 0; j < 8; j++) bf[j] = b_s[(j * 8 + g) * LDS + ks * 4 + t];
+#pragma unroll
+            for(int i = 0; i < 4; i++)
+#pragma unroll
+                for(int j = 0; j < 8; j++) dmma(acc[i][j][0], acc[i][j][1], af[i], bf[j]);
+        }
+    }
+    cp_async_wait<0>();
+
+    // C -= acc, lower triangle only
+#pragma unroll
+    for(int i = 0; i < 4; i++)
+    {
+        const int gi = row0 + wm * 32 + i * 8 + g;
+        if(gi >= n) continue;
+#pragma unroll
+        for(int j = 0; j < 8; j++)
+        {
+            const int gj = col0 + wn * 64 + j * 8 + 2 * t;
+            if(gj >= c1) continue;
+            double* p = &A[(size_t)gi * ld + gj];
+            if(gj + 1 <= gi)
+            {
+                double2 v = *reinterpret_cast<double2*>(p);
+                v.x -= acc[i][j][0];
+                v.y -= acc[i][j][1];
+                *reinterpret_cast<double2*>(p) = v;
+            }
+            else if(gj <= gi)
+                p[0] -= acc[i][j][0];
+        }
+    }
+}
+
+static const size_t kSyrkSmem = (size_t)2 * STAGES * BM * LDS * sizeof(double);
+static const size_t kBlockSmem = (size_t)2 * NB * (NB + 1) * sizeof(double);   // potrf_diag / trsm
+
+static bool configure_kernels()
+{
+    static bool configured = false;
+    if(configured) return true;
+    MB200_CUDA_CHECK(cudaFuncSetAttribute(syrk_dmma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSyrkSmem));
+    MB200_CUDA_CHECK(cudaFuncSetAttribute(potrf_diag_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kBlockSmem));
+    MB200_CUDA_CHECK(cudaFuncSetAttribute(trsm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kBlockSmem));
+    configured = true;
+    return true;
+}
+
+static bool syrk_update(double* A, int ld, int n, int c0, int c1, int k0, int k1, cudaStream_t s, int* nlaunch)
+{
+    if(c1 <= c0 || n <= c0) return true;
+    dim3 grid((c1 - c0 + BM - 1) / BM, (n - c0 + BM - 1) / BM);
+    syrk_dmma_kernel<<<grid, 256, kSyrkSmem, s>>>(A, ld, n, c0, c1, k0, k1);
+    if(nlaunch) (*nlaunch)++;
+    return true;
+}
+
+bool chol_factor(double* A, int npad, int nreal, double* invL, int* d_info, cudaStream_t s, int* nlaunch)
+{
+    if(!configure_kernels()) return false;
+    MB200_CUDA_CHECK(cudaMemsetAsync(d_info, 0, sizeof(int), s));
+    for(int K0 = 0; K0 < npad; K0 += NBO)
+    {
+        const int K1 = K0 + NBO < npad ? K0 + NBO : npad;
+        for(int k0 = K0; k0 < K1; k0 += NB)
+        {
+            potrf_diag_kernel<<<1, 256, kBlockSmem, s>>>(A, npad, k0, invL + (size_t)(k0 / NB) * NB * NB, d_info, nreal);
+            if(nlaunch) (*nlaunch)++;
+            const int nrows_below = npad - (k0 + NB);
+            if(nrows_below > 0)
+            {
+                trsm_kernel<<<nrows_below / NB, 256, kBlockSmem, s>>>(A, npad, k0, invL + (size_t)(k0 / NB) * NB * NB, npad);
+                if(nlaunch) (*nlaunch)++;
+                // rest of this outer panel only
+                if(!syrk_update(A, npad, npad, k0 + NB, K1, k0, k0 + NB, s, nlaunch)) return false;
+            }
+        }
+        // the whole trailing matrix, K = width of the panel
+        if(!syrk_update(A, npad, npad, K1, npad, K0, K1, s, nlaunch)) return false;
+    }
+    MB200_CUDA_CHECK(cudaGetLastError());
+    return true;
+}
+
+////////////////////////////////////////////////////////////////////////////////
+// triangular solves, Nrhs right-hand sides stored as rows: B[rhs][n]
+////////////////////////////////////////////////////////////////////////////////
+// y_k = invL_kk b_k  (transpose=false)  or  invL_kk' b_k (transpose=true); one CTA per rhs
+__global__ void __launch_bounds__(64)
+solve_diag_kernel(const double* __restrict__ invL, double* __restrict__ B, int ldb, int k0, bool transpose)
+{
+    __shared__ double b[NB];
+    double* v = B + (size_t)blockIdx.x * ldb + k0;
+    const int i = threadIdx.x;
+    b[i] = v[i];
+    __syncthreads();
+    double acc = 0.;
+    if(!transpose) { for(int m = 0; m <= i; m++) acc += invL[i * NB + m] * b[m]; }
+    else           { for(int m = i; m < NB; m++) acc += invL[m * NB + i] * b[m]; }
+    v[i] = acc;
+}
+
+// forward:  b_i -= L(i, k0:k0+64) y_k for rows i >= k0+64. One warp per row, all rhs
+__global__ void __launch_bounds__(256)
+solve_update_fwd_kernel(const double* __restrict__ L, int ld, int n, double* __restrict__ B, int ldb, int nrhs, int k0)
+{
+    const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    const int i = k0 + NB + warp;
+    if(i >= n) return;
+    const double l0 = L[(size_t)i * ld + k0 + lane], l1 = L[(size_t)i * ld + k0 + 32 + lane];
+    for(int r = 0; r < nrhs; r++)
+    {
+        const double* y = B + (size_t)r * ldb + k0;
+        double acc = l0 * y[lane] + l1 * y[32 + lane];
+#pragma unroll
+        for(int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+        if(lane == 0) B[(size_t)r * ldb + i] -= acc;
+    }
+}
+
+// backward: b_j -= sum_r L(k0+r, j) z_k[r] for columns j < k0. One thread per column, all rhs
+__global__ void __launch_bounds__(256)
+solve_update_bwd_kernel(const double* __restrict__ L, int ld, double* __restrict__ B, int ldb, int nrhs, int k0)
+{
+    __shared__ double z[NB];
+    const int j = blockIdx.x * blockDim.x + threadIdx.x;
+    for(int r = 0; r < nrhs; r++)
+    {
+        __syncthreads();
+        if(threadIdx.x < NB) z[threadIdx.x] = B[(size_t)r * ldb + k0 + threadIdx.x];
+        __syncthreads();
+        if(j < k0)
+        {
+            double acc = 0.;
+#pragma unroll 8
+            for(int m = 0; m < NB; m++) acc += L[(size_t)(k0 + m) * ld + j] * z[m];
+            B[(size_t)r * ldb + j] -= acc;
+        }
+    }
+}
+
+bool chol_solve(const double* L, int npad, const double* invL, double* B, int ldb, int nrhs, cudaStream_t s, int* nlaunch)
+{
+    const int nblk = npad / NB;
+    for(int k = 0; k < nblk; k++)
+    {
+        const int k0 = k * NB;
+        solve_diag_kernel<<<nrhs, NB, 0, s>>>(invL + (size_t)k * NB * NB, B, ldb, k0, false);
+        if(nlaunch) (*nlaunch)++;
+        const int below = npad - k0 - NB;
+        if(below > 0)
+        {
+            solve_update_fwd_kernel<<<(below * 32 + 255) / 256, 256, 0, s>>>(L, npad, npad, B, ldb, nrhs, k0);
+            if(nlaunch) (*nlaunch)++;
+        }
+    }
+    for(int k = nblk - 1; k >= 0; k--)
+    {
+        const int k0 = k * NB;
+        solve_diag_kernel<<<nrhs, NB, 0, s>>>(invL + (size_t)k * NB * NB, B, ldb, k0, true);
+        if(nlaunch) (*nlaunch)++;
+        if(k0 > 0)
+        {
+            solve_update_bwd_kernel<<<(k0 + 255) / 256, 256, 0, s>>>(L, npad, B, ldb, nrhs, k0);
+            if(nlaunch) (*nlaunch)++;
+        }
+    }
+    MB200_CUDA_CHECK(cudaGetLastError());
+    return true;
+}
+
+// min/max of the diagonal of L (for rcond)
+__global__ void diag_minmax_kernel(const double* __restrict__ L, int ld, int n, double* out)
+{
+    __shared__ double smin[256], smax[256];
+    double mn = 1e300, mx = 0.;
+    for(int i = threadIdx.x; i < n; i += blockDim.x)
+    {
+        const double d = L[(size_t)i * ld + i];
+        mn = d < mn ? d : mn;
+        mx = d > mx ? d : mx;
+    }
+    smin[threadIdx.x] = mn; smax[threadIdx.x] = mx;
+    __syncthreads();
+    for(int o = 128; o > 0; o >>= 1)
+    {
+        if(threadIdx.x < o)
+        {
+            smin[threadIdx.x] = fmin(smin[threadIdx.x], smin[threadIdx.x + o]);
+            smax[threadIdx.x] = fmax(smax[threadIdx.x], smax[threadIdx.x + o]);
+        }
+        __syncthreads();
+    }
+    if(threadIdx.x == 0) { out[0] = smin[0]; out[1] = smax[0]; }
+}
+
+bool chol_diag_minmax(const double* L, int npad, int nreal, double* d_out2, cudaStream_t s)
+{
+    diag_minmax_kernel<<<1, 256, 0, s>>>(L, npad, nreal, d_out2);
+    MB200_CUDA_CHECK(cudaGetLastError());
+    return true;
+}
+
+}  // namespace mb200

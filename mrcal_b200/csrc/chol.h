@@ -1,0 +1,22 @@
+// Internal: dense Cholesky on the device (chol.cu)
+#pragma once
+#include <cuda_runtime.h>
+
+namespace mb200 {
+
+constexpr int kCholBlock = 64;
+inline int chol_padded(int n) { return ((n + kCholBlock - 1) / kCholBlock) * kCholBlock; }
+
+// A: row-major npad x npad, lower triangle holds the matrix; rows/cols >= nreal
+// are padding (1 on the diagonal). On return the lower triangle holds L.
+// invL: [npad/64][64*64] inverses of the diagonal blocks of L.
+// d_info: device int; 0 if positive definite, else 1 + index of the first bad pivot.
+bool chol_factor(double* A, int npad, int nreal, double* invL, int* d_info, cudaStream_t s, int* nlaunch);
+
+// Solve L L' X = B in place for nrhs right-hand sides stored as rows B[r][0..npad)
+bool chol_solve(const double* L, int npad, const double* invL, double* B, int ldb, int nrhs, cudaStream_t s, int* nlaunch);
+
+// d_out2[0] = min, d_out2[1] = max of diag(L)[0..nreal)
+bool chol_diag_minmax(const double* L, int npad, int nreal, double* d_out2, cudaStream_t s);
+
+}  // namespace mb200

@@ -1,0 +1,497 @@
+// Kernel family 2a: the normal equations. From the Jacobian strips written by
+// eval.cu, form JtJ in its block-diagonal + arrowhead structure, eliminate the
+// per-frame (6x6) and per-point (3x3) blocks (Schur complement), and leave the
+// small dense reduced system S, g' of the shared unknowns (all intrinsics, all
+// extrinsics, the board warp) for chol.cu:
+//
+//     [ A  B ] [ds]     [gs]        S  = A  - sum_j B_j D_j^-1 B_j'
+//     [ B' D ] [df] = - [gf]        g' = gs - sum_j B_j D_j^-1 gf_j
+//                                   df_j = -D_j^-1 (gf_j + B_j' ds)
+//
+// This replaces what the reference gets from libdogleg/CHOLMOD (Jt*x, the
+// symbolic+numeric factorization of the whole sparse JtJ; call site
+// mrcal.c:6435). The unit of work is the OBSERVATION: one CTA per board
+// observation (or point observation) builds the Gram matrix of that
+// observation's rows over the few columns they touch, in shared memory, and
+// only the reduced result goes to global memory. For splined models the touched
+// knot columns are data-dependent (mrcal.c:2171-2185), so each CTA discovers
+// its own local column set every time.
+#include "normal.h"
+
+namespace mb200 {
+
+constexpr int kMaxRowNnz = 40;     // widest row: 16 intrinsics + 6 + 6 + 2 (any model here <= 30)
+constexpr int kGramMax   = 216;    // largest local column count whose Gram matrix lives in shared memory
+
+struct ItemDesc
+{
+    int rows, nnz_row, nI, j0, m0;
+    int cbase, clen;       // the camera's intrinsics block in the state vector
+    int cam0;              // first extrinsics column, or -1
+    int elim0, nelim;      // first eliminated column, count (6 frame / 3 point / 0)
+    int warp0;             // first warp column or -1
+    int group;             // elimination group or -1
+};
+
+__device__ __forceinline__ ItemDesc describe_item(const DevProblem& P, int w, int Nframe_groups)
+{
+    ItemDesc d;
+    d.nI = P.nnz_row_intr;
+    d.clen = P.Nintr_state;
+    if(w < P.Nobs_board)
+    {
+        const int icam_i = P.obs_board[3 * w + 0], icam_e = P.obs_board[3 * w + 1], iframe = P.obs_board[3 * w + 2];
+        d.rows = 2 * P.W * P.H;
+        d.j0 = P.board_j0[w];
+        d.nnz_row = (P.board_j0[w + 1] - d.j0) / d.rows;
+        d.m0 = d.rows * w;
+        d.cbase = P.i_intr0 + icam_i * P.Nintr_state;
+        d.cam0 = (P.opt_extr && icam_e >= 0) ? P.i_extr0 + 6 * icam_e : -1;
+        d.nelim = P.opt_frames ? 6 : 0;
+        d.elim0 = P.opt_frames ? P.i_frame0 + 6 * iframe : -1;
+        d.warp0 = P.opt_warp ? P.i_warp0 : -1;
+        d.group = P.opt_frames ? iframe : -1;
+    }
+    else
+    {
+        const int o = w - P.Nobs_board;
+        const int icam_i = P.obs_point[3 * o + 0], icam_e = P.obs_point[3 * o + 1], ipt = P.obs_point[3 * o + 2];
+        const bool in_state = P.opt_frames && ipt < P.Npoints_variable;
+        d.rows = 2;
+        d.j0 = P.point_j0[o];
+        d.nnz_row = (P.point_j0[o + 1] - d.j0) / 2;
+        d.m0 = P.m_point0 + 2 * o;
+        d.cbase = P.i_intr0 + icam_i * P.Nintr_state;
+        d.cam0 = (P.opt_extr && icam_e >= 0) ? P.i_extr0 + 6 * icam_e : -1;
+        d.nelim = in_state ? 3 : 0;
+        d.elim0 = in_state ? P.i_point0 + 3 * ipt : -1;
+        d.warp0 = -1;
+        d.group = in_state ? Nframe_groups + ipt : -1;
+    }
+    return d;
+}
+
+__device__ __forceinline__ int tri(int a, int b) { return a * (a + 1) / 2 + b; }   // a >= b
+
+// One CTA per work item (board observation or point observation)
+__global__ void __launch_bounds__(256)
+assemble_items_kernel(DevProblem P, NormalBuffers N, const double* __restrict__ x,
+                      const double* __restrict__ Jval, const int* __restrict__ Jcol)
+{
+    extern __shared__ __align__(16) double dsm[];
+    __shared__ int   s_scan[256];
+    __shared__ int   s_nloc;
+    __shared__ short s_lidx[2][kMaxRowNnz];
+    __shared__ double s_val[2][kMaxRowNnz];
+    __shared__ double s_xr[2];
+    __shared__ unsigned char s_pa[kMaxRowNnz * (kMaxRowNnz + 1) / 2], s_pb[kMaxRowNnz * (kMaxRowNnz + 1) / 2];
+
+    const int w = blockIdx.x, tid = threadIdx.x;
+    const ItemDesc d = describe_item(P, w, N.Nframe_groups);
+    const int ncam = d.cam0 >= 0 ? 6 : 0, nwarp = d.warp0 >= 0 ? 2 : 0;
+
+    // ---- 1. local numbering of the touched intrinsics columns
+    short* lmap = reinterpret_cast<short*>(dsm);                       // [clen]
+    const int lmap_doubles = (d.clen * (int)sizeof(short) + 7) / 8;
+    double* gram = dsm + lmap_doubles;
+    for(int i = tid; i < d.clen; i += 256) lmap[i] = 0;
+    for(int e = tid; e < kMaxRowNnz * (kMaxRowNnz + 1) / 2; e += 256)
+    {
+        // decode pair index e -> (a >= b)
+        int a = (int)((sqrtf(8.f * e + 1.f) - 1.f) * 0.5f);
+        while(a * (a + 1) / 2 > e) a--;
+        while((a + 1) * (a + 2) / 2 <= e) a++;
+        s_pa[e] = (unsigned char)a;
+        s_pb[e] = (unsigned char)(e - a * (a + 1) / 2);
+    }
+    __syncthreads();
+    if(d.nI > 0)
+        for(int e = tid; e < d.rows * d.nI; e += 256)
+        {
+            const int r = e / d.nI, k = e - r * d.nI;
+            lmap[Jcol[(size_t)d.j0 + (size_t)r * d.nnz_row + k] - d.cbase] = 1;
+        }
+    __syncthreads();
+    // exclusive scan over clen flags, 256 threads each owning a contiguous chunk
+    {
+        const int per = (d.clen + 255) / 256;
+        const int lo = tid * per, hi = min(lo + per, d.clen);
+        int cnt = 0;
+        for(int i = lo; i < hi; i++) cnt += lmap[i];
+        s_scan[tid] = cnt;
+        __syncthreads();
+        for(int o = 1; o < 256; o <<= 1)
+        {
+            const int v = tid >= o ? s_scan[tid - o] : 0;
+            __syncthreads();
+            s_scan[tid] += v;
+            __syncthreads();
+        }
+        int base = s_scan[tid] - cnt;
+        for(int i = lo; i < hi; i++) { const int f = lmap[i]; lmap[i] = f ? (short)base : (short)-1; base += f; }
+        if(tid == 255) s_nloc = s_scan[255];
+        __syncthreads();
+    }
+    const int nloc = s_nloc;
+    const int nsh = nloc + ncam + nwarp, ntot = nsh + d.nelim;
+    const bool big = ntot > kGramMax;   // Gram matrix does not fit: shared x shared goes straight to global
+
+    // the item's shared columns, in reduced numbering (increasing)
+    int* cols = N.wi_cols + (size_t)w * N.cap;
+    for(int i = tid; i < d.clen; i += 256)
+        if(lmap[i] >= 0) cols[lmap[i]] = N.reduced_index(d.cbase + i);
+    if(tid < ncam)  cols[nloc + tid] = N.reduced_index(d.cam0 + tid);
+    if(tid < nwarp) cols[nloc + ncam + tid] = N.reduced_index(d.warp0 + tid);
+    if(tid == 0) N.wi_nsh[w] = nsh;
+
+    // ---- 2. accumulate. gram: lower-packed ntot x ntot, or (big) the nelim x ntot strip
+    const int ngram = big ? d.nelim * ntot : ntot * (ntot + 1) / 2;
+    double* gvec = gram + ngram;   // [ntot] J'x of this item
+    for(int i = tid; i < ngram + ntot; i += 256) gram[i] = 0.;
+    __syncthreads();
+
+    const int npairs = d.nnz_row * (d.nnz_row + 1) / 2;
+    for(int r = 0; r < d.rows; r++)
+    {
+        const int buf = r & 1;
+        if(tid < d.nnz_row)
+        {
+            const size_t j = (size_t)d.j0 + (size_t)r * d.nnz_row + tid;
+            const int k = tid;
+            int l;
+            if(k < d.nI)                          l = lmap[Jcol[j] - d.cbase];
+            else if(k < d.nI + ncam)              l = nloc + (k - d.nI);
+            else if(k < d.nI + ncam + d.nelim)    l = nsh + (k - d.nI - ncam);
+            else                                  l = nloc + ncam + (k - d.nI - ncam - d.nelim);
+            s_lidx[buf][k] = (short)l;
+            s_val[buf][k] = Jval[j];
+        }
+        if(tid == 32) s_xr[buf] = x[d.m0 + r];
+        __syncthreads();   // the only barrier per row: the staging buffers alternate
+        for(int e = tid; e < npairs; e += 256)
+        {
+            const int a = s_pa[e], b = s_pb[e];
+            const double v = s_val[buf][a] * s_val[buf][b];
+            if(v == 0.) continue;
+            int la = s_lidx[buf][a], lb = s_lidx[buf][b];
+            if(la < lb) { const int t = la; la = lb; lb = t; }
+            if(!big) gram[tri(la, lb)] += v;
+            else if(la >= nsh) gram[(la - nsh) * ntot + lb] += v;          // eliminated x anything
+            else atomicAdd(&N.S[(size_t)cols[la] * N.ldS + cols[lb]], v);    // shared x shared
+        }
+        if(tid >= 64 && tid < 64 + d.nnz_row)
+        {
+            const int k = tid - 64;
+            gvec[s_lidx[buf][k]] += s_val[buf][k] * s_xr[buf];
+        }
+        // No second barrier: the next row stages into the OTHER buffer, and nobody can pass that
+        // row's barrier (hence touch gram again, or restage this buffer) before everybody has
+        // finished this row. Within one row, distinct (a,b) hit distinct gram entries.
+    }
+    __syncthreads();
+
+    // ---- 3. write out
+    // shared x shared -> S (lower triangle, reduced numbering)
+    if(!big)
+        for(int e = tid; e < nsh * (nsh + 1) / 2; e += 256)
+        {
+            int a = (int)((sqrt(8. * e + 1.) - 1.) * 0.5);
+            while(a * (a + 1) / 2 > e) a--;
+            while((a + 1) * (a + 2) / 2 <= e) a++;
+            const int b = e - a * (a + 1) / 2;
+            const double v = gram[e];
+            if(v != 0.) atomicAdd(&N.S[(size_t)cols[a] * N.ldS + cols[b]], v);
+        }
+    // gradient of the shared unknowns: into g' (completed by the Schur kernel) and into the full J'x
+    for(int l = tid; l < nsh; l += 256)
+        if(gvec[l] != 0.)
+        {
+            atomicAdd(&N.gs[cols[l]], gvec[l]);
+            atomicAdd(&N.g_full[N.state_index(cols[l])], gvec[l]);
+        }
+    // eliminated block of this item: B (nelim x nsh), D (nelim x nelim), gf (nelim)
+    if(d.nelim > 0)
+    {
+        double* B = N.wi_B + (size_t)w * 6 * N.cap;
+        for(int e = tid; e < d.nelim * nsh; e += 256)
+        {
+            const int p = e / nsh, l = e - p * nsh;
+            B[(size_t)p * N.cap + l] = big ? gram[p * ntot + l] : gram[tri(nsh + p, l)];
+        }
+        if(tid < 36)
+        {
+            const int p = tid / 6, q = tid % 6;
+            double v = 0.;
+            if(p < d.nelim && q < d.nelim)
+            {
+                const int hi = p > q ? p : q, lo = p > q ? q : p;
+                v = big ? gram[hi * ntot + nsh + lo] : gram[tri(nsh + hi, nsh + lo)];
+            }
+            N.wi_D[(size_t)w * 36 + tid] = v;
+        }
+        if(tid < 6) N.wi_gf[(size_t)w * 6 + tid] = tid < d.nelim ? gvec[nsh + tid] : 0.;
+    }
+}
+
+// Regularization rows touch shared unknowns only: one thread per row
+__global__ void assemble_reg_kernel(DevProblem P, NormalBuffers N, const double* __restrict__ x,
+                                    const double* __restrict__ Jval, const int* __restrict__ Jcol,
+                                    const int* __restrict__ rowptr)
+{
+    const int m = P.m_reg0 + blockIdx.x * blockDim.x + threadIdx.x;
+    if(m >= P.Nmeas) return;
+    const int j0 = rowptr[m], j1 = rowptr[m + 1];
+    const double xm = x[m];
+    for(int a = j0; a < j1; a++)
+    {
+        const int ca = N.reduced_index(Jcol[a]);
+        const double va = Jval[a];
+        atomicAdd(&N.gs[ca], va * xm);
+        atomicAdd(&N.g_full[Jcol[a]], va * xm);
+        for(int b = j0; b <= a; b++)
+        {
+            const int cb = N.reduced_index(Jcol[b]);
+            const int hi = ca > cb ? ca : cb, lo = ca > cb ? cb : ca;
+            atomicAdd(&N.S[(size_t)hi * N.ldS + lo], va * Jval[b] * ((ca == cb && a != b) ? 2. : 1.));
+        }
+    }
+}
+
+// 6x6 (or 3x3) SPD inverse by Cholesky, in registers of one thread. Returns false if not PD
+__device__ bool spd_inverse(double* Dinv, const double* D, int n)
+{
+    double L[6][6] = {};
+    for(int j = 0; j < n; j++)
+    {
+        double s = D[j * 6 + j];
+        for(int k = 0; k < j; k++) s -= L[j][k] * L[j][k];
+        if(!(s > 0.)) return false;
+        L[j][j] = sqrt(s);
+        for(int i = j + 1; i < n; i++)
+        {
+            double t = D[i * 6 + j];
+            for(int k = 0; k < j; k++) t -= L[i][k] * L[j][k];
+            L[i][j] = t / L[j][j];
+        }
+    }
+    double X[6][6] = {};   // inv(L)
+    for(int c = 0; c < n; c++)
+    {
+        X[c][c] = 1. / L[c][c];
+        for(int i = c + 1; i < n; i++)
+        {
+            double t = 0.;
+            for(int k = c; k < i; k++) t += L[i][k] * X[k][c];
+            X[i][c] = -t / L[i][i];
+        }
+    }
+    for(int i = 0; i < 6; i++)
+        for(int j = 0; j < 6; j++)
+        {
+            double t = 0.;
+            if(i < n && j < n)
+                for(int k = (i > j ? i : j); k < n; k++) t += X[k][i] * X[k][j];
+            Dinv[i * 6 + j] = t;
+        }
+    return true;
+}
+
+// One CTA per elimination group (a frame, or a point): S -= B' D^-1 B over all
+// pairs of the group's items, g' = gs - B' D^-1 gf
+__global__ void __launch_bounds__(256)
+schur_groups_kernel(NormalBuffers N, double lambda)
+{
+    extern __shared__ __align__(16) double dsm[];   // C1[6][cap]
+    __shared__ double s_Dinv[36], s_h[6], s_D[36], s_gf[6];
+    __shared__ int s_ok;
+    const int grp = blockIdx.x, tid = threadIdx.x;
+    const int i0 = N.grp_ptr[grp], i1 = N.grp_ptr[grp + 1];
+    const int nelim = grp < N.Nframe_groups ? 6 : 3;
+    if(tid < 36)
+    {
+        double v = 0.;
+        for(int i = i0; i < i1; i++) v += N.wi_D[(size_t)N.grp_items[i] * 36 + tid];
+        const int p = tid / 6, q = tid % 6;
+        if(p == q && p < nelim) v += lambda;
+        s_D[tid] = v;
+    }
+    if(tid >= 64 && tid < 70)
+    {
+        double v = 0.;
+        for(int i = i0; i < i1; i++) v += N.wi_gf[(size_t)N.grp_items[i] * 6 + (tid - 64)];
+        s_gf[tid - 64] = v;
+    }
+    __syncthreads();
+    if(tid == 0)
+    {
+        double Dinv[36];
+        // a group nobody observes (or all of whose observations are outliers) has D = 0: the
+        // reference would hand CHOLMOD a singular matrix here (mrcal.c:4826-4833); report it
+        s_ok = spd_inverse(Dinv, s_D, nelim) ? 1 : 0;
+        if(!s_ok) { atomicCAS(N.info, 0, 1000000000 + grp); for(int i = 0; i < 36; i++) Dinv[i] = 0.; }
+        for(int i = 0; i < 36; i++) s_Dinv[i] = Dinv[i];
+        // the eliminated part of the full gradient
+        for(int p = 0; p < nelim; p++) N.g_full[N.e0 + (grp < N.Nframe_groups ? 6 * grp : 6 * N.Nframe_groups + 3 * (grp - N.Nframe_groups)) + p] = s_gf[p];
+        for(int p = 0; p < 6; p++)
+        {
+            double t = 0.;
+            for(int q = 0; q < 6; q++) t += Dinv[p * 6 + q] * s_gf[q];
+            s_h[p] = t;
+        }
+    }
+    __syncthreads();
+    if(tid < 36) N.grp_Dinv[(size_t)grp * 36 + tid] = s_Dinv[tid];
+    if(tid < 6)  N.grp_gf[(size_t)grp * 6 + tid] = s_gf[tid];
+
+    double* C1 = dsm;   // [6][cap]: Dinv B1
+    for(int a1 = i0; a1 < i1; a1++)
+    {
+        const int w1 = N.grp_items[a1];
+        const int n1 = N.wi_nsh[w1];
+        const double* B1 = N.wi_B + (size_t)w1 * 6 * N.cap;
+        const int* c1 = N.wi_cols + (size_t)w1 * N.cap;
+        __syncthreads();
+        for(int e = tid; e < nelim * n1; e += 256)
+        {
+            const int p = e / n1, l = e - p * n1;
+            double t = 0.;
+            for(int q = 0; q < nelim; q++) t += s_Dinv[p * 6 + q] * B1[(size_t)q * N.cap + l];
+            C1[p * N.cap + l] = t;
+        }
+        __syncthreads();
+        // reduced gradient
+        for(int l = tid; l < n1; l += 256)
+        {
+            double t = 0.;
+            for(int p = 0; p < nelim; p++) t += B1[(size_t)p * N.cap + l] * s_h[p];
+            if(t != 0.) atomicAdd(&N.gs[c1[l]], -t);
+        }
+        for(int a2 = i0; a2 <= a1; a2++)
+        {
+            const int w2 = N.grp_items[a2];
+            const int n2 = N.wi_nsh[w2];
+            const double* B2 = N.wi_B + (size_t)w2 * 6 * N.cap;
+            const int* c2 = N.wi_cols + (size_t)w2 * N.cap;
+            const bool same = a1 == a2;
+            for(int e = tid; e < n1 * n2; e += 256)
+            {
+                const int a = e / n2, b = e - a * n2;
+                if(same && b > a) continue;
+                double v = 0.;
+                for(int p = 0; p < nelim; p++) v += C1[p * N.cap + a] * B2[(size_t)p * N.cap + b];
+                if(v == 0.) continue;
+                const int r = c1[a], c = c2[b];
+                if(r > c)       atomicAdd(&N.S[(size_t)r * N.ldS + c], -v);
+                else if(r < c)  atomicAdd(&N.S[(size_t)c * N.ldS + r], -v);
+                else            atomicAdd(&N.S[(size_t)r * N.ldS + r], same ? -v : -2. * v);
+            }
+        }
+    }
+}
+
+// df_j = -D_j^-1 (gf_j + B_j ds): one warp per group. ds is the reduced solution (npad, reduced numbering)
+__global__ void __launch_bounds__(256)
+backsub_groups_kernel(NormalBuffers N, const double* __restrict__ ds, double* __restrict__ step_full, int e0)
+{
+    const int grp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    if(grp >= N.Ngroups) return;
+    const int nelim = grp < N.Nframe_groups ? 6 : 3;
+    double t[6] = {0., 0., 0., 0., 0., 0.};
+    for(int i = N.grp_ptr[grp]; i < N.grp_ptr[grp + 1]; i++)
+    {
+        const int w = N.grp_items[i];
+        const int n = N.wi_nsh[w];
+        const double* B = N.wi_B + (size_t)w * 6 * N.cap;
+        const int* c = N.wi_cols + (size_t)w * N.cap;
+        for(int l = lane; l < n; l += 32)
+        {
+            const double d = ds[c[l]];
+            for(int p = 0; p < nelim; p++) t[p] += B[(size_t)p * N.cap + l] * d;
+        }
+    }
+    for(int p = 0; p < 6; p++)
+        for(int o = 16; o > 0; o >>= 1) t[p] += __shfl_xor_sync(0xffffffffu, t[p], o);
+    if(lane < nelim)
+    {
+        double v = 0.;
+        for(int q = 0; q < nelim; q++) v += N.grp_Dinv[(size_t)grp * 36 + lane * 6 + q] * (N.grp_gf[(size_t)grp * 6 + q] + t[q]);
+        const int col = grp < N.Nframe_groups ? e0 + 6 * grp : e0 + 6 * N.Nframe_groups + 3 * (grp - N.Nframe_groups);
+        step_full[col + lane] = -v;
+    }
+}
+
+__global__ void set_diagonal_kernel(double* S, int ld, int i0, int i1, double v, bool add)
+{
+    const int i = i0 + blockIdx.x * blockDim.x + threadIdx.x;
+    if(i < i1) { if(add) S[(size_t)i * ld + i] += v; else S[(size_t)i * ld + i] = v; }
+}
+
+bool normal_assemble(const DevProblem& dp, const NormalBuffers& N, const EvalBuffers& op, const int* d_rowptr,
+                     double lambda, cudaStream_t s, int* nlaunch)
+{
+    static bool configured = false;
+    // Gram matrix (+J'x) of the widest item that can occur, capped at kGramMax; wider items keep
+    // only their eliminated strip in shared memory
+    const int ntot_max = N.cap + 6;
+    const int ng = ntot_max < kGramMax ? ntot_max : kGramMax;
+    size_t gram_doubles = (size_t)ng * (ng + 1) / 2 + ng;
+    if(ntot_max > kGramMax && (size_t)7 * ntot_max > gram_doubles) gram_doubles = (size_t)7 * ntot_max;
+    const size_t smem_items = ((size_t)(dp.Nintr_state * sizeof(short) + 7) / 8 + gram_doubles + 16) * sizeof(double);
+    const size_t smem_schur = (size_t)6 * N.cap * sizeof(double);
+    if(!configured)
+    {
+        MB200_CUDA_CHECK(cudaFuncSetAttribute(assemble_items_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
+        MB200_CUDA_CHECK(cudaFuncSetAttribute(schur_groups_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
+        configured = true;
+    }
+    if(smem_items > 220 * 1024 || smem_schur > 100 * 1024)
+    {
+        set_error("lens model with %d intrinsics per camera is too large for the assembly kernels", dp.Nintr_state);
+        return false;
+    }
+    MB200_CUDA_CHECK(cudaMemsetAsync(N.S, 0, (size_t)N.ldS * N.ldS * sizeof(double), s));
+    MB200_CUDA_CHECK(cudaMemsetAsync(N.gs, 0, (size_t)N.ldS * sizeof(double), s));
+    MB200_CUDA_CHECK(cudaMemsetAsync(N.g_full, 0, (size_t)dp.Nstate * sizeof(double), s));
+    MB200_CUDA_CHECK(cudaMemsetAsync(N.info, 0, sizeof(int), s));
+    const int Nwi = dp.Nobs_board + dp.Nobs_point;
+    if(Nwi > 0)
+    {
+        assemble_items_kernel<<<Nwi, 256, smem_items, s>>>(dp, N, op.x, op.Jval, op.Jcol);
+        (*nlaunch)++;
+    }
+    const int Nreg = dp.Nmeas - dp.m_reg0;
+    if(Nreg > 0)
+    {
+        assemble_reg_kernel<<<(Nreg + 127) / 128, 128, 0, s>>>(dp, N, op.x, op.Jval, op.Jcol, d_rowptr);
+        (*nlaunch)++;
+    }
+    if(N.Ngroups > 0)
+    {
+        schur_groups_kernel<<<N.Ngroups, 256, smem_schur, s>>>(N, lambda);
+        (*nlaunch)++;
+    }
+    // padding rows of the factorization; diagonal loading of the shared block
+    if(N.ldS > N.n_r)
+    {
+        set_diagonal_kernel<<<(N.ldS - N.n_r + 255) / 256, 256, 0, s>>>(N.S, N.ldS, N.n_r, N.ldS, 1., false);
+        (*nlaunch)++;
+    }
+    if(lambda > 0. && N.n_r > 0)
+    {
+        set_diagonal_kernel<<<(N.n_r + 255) / 256, 256, 0, s>>>(N.S, N.ldS, 0, N.n_r, lambda, true);
+        (*nlaunch)++;
+    }
+    MB200_CUDA_CHECK(cudaGetLastError());
+    return true;
+}
+
+bool normal_backsubstitute(const NormalBuffers& N, const double* ds, double* step_full, int e0, cudaStream_t s, int* nlaunch)
+{
+    if(N.Ngroups <= 0) return true;
+    backsub_groups_kernel<<<(N.Ngroups * 32 + 255) / 256, 256, 0, s>>>(N, ds, step_full, e0);
+    (*nlaunch)++;
+    MB200_CUDA_CHECK(cudaGetLastError());
+    return true;
+}
+
+}  // namespace mb200

@@ -1,0 +1,564 @@
+// The trust-region loop: Powell's dogleg, as the reference runs it through
+// libdogleg's dogleg_optimize2() (call site mrcal.c:6435; parameters
+// mrcal.c:6289-6299), and the outlier-rejection outer loop around it
+// (mrcal.c:6430-6481, markOutliers mrcal.c:3978-4402).
+//
+// libdogleg is not part of the reference tree; the step logic below restates
+// its published algorithm (the same restatement, in numpy, is the parity oracle:
+// oracle/dogleg_np.py). What differs is where the work happens: the state, the
+// residuals, the Jacobian strips, the reduced normal equations and their factor
+// never leave the GPU; the host only sees a handful of scalars per iteration
+// and takes the accept/reject decisions.
+#include <algorithm>
+#include <cmath>
+
+#include "chol.h"
+#include "normal.h"
+#include "problem_impl.h"
+
+namespace mb200 {
+
+bool comm_active();                                                             // nccl.cu
+bool comm_allreduce_sum(double* d_buf, size_t count, cudaStream_t s);           // nccl.cu
+int  comm_rank();
+
+struct SolverWorkspace
+{
+    DeviceArena arena;
+    NormalBuffers N{};
+    double* invL = nullptr;
+    double* rhs = nullptr;        // [ldS] reduced solution
+    double* step_gn = nullptr;    // [Nstate]
+    double* step = nullptr;       // [Nstate]
+    double* scal = nullptr;       // [16] device scalars
+    double* h_scal = nullptr;     // pinned mirror
+    int*    h_info = nullptr;     // pinned
+    std::vector<cudaEvent_t> ev;
+    ~SolverWorkspace()
+    {
+        if(h_scal) cudaFreeHost(h_scal);
+        if(h_info) cudaFreeHost(h_info);
+        for(auto e : ev) cudaEventDestroy(e);
+    }
+};
+static void delete_ws(SolverWorkspace* w) { delete w; }
+
+////////////////////////////////////////////////////////////////////////////////
+// small vector kernels
+////////////////////////////////////////////////////////////////////////////////
+// out[0] += (J v).x ; out[1] += |J v|^2. One warp per row
+__global__ void __launch_bounds__(256)
+jv_kernel(const int* __restrict__ rowptr, const int* __restrict__ col, const double* __restrict__ val,
+          const double* __restrict__ v, const double* __restrict__ x, int Nrows, double* __restrict__ out)
+{
+    __shared__ double red0[8], red1[8];
+    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+    const int nwarps = (gridDim.x * blockDim.x) >> 5;
+    double s0 = 0., s1 = 0.;
+    for(int row = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; row < Nrows; row += nwarps)
+    {
+        const int j0 = rowptr[row], j1 = rowptr[row + 1];
+        double acc = 0.;
+        for(int j = j0 + lane; j < j1; j += 32) acc += val[j] * v[col[j]];
+#pragma unroll
+        for(int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+        if(lane == 0) { s0 += acc * x[row]; s1 += acc * acc; }
+    }
+    if(lane == 0) { red0[wib] = s0; red1[wib] = s1; }
+    __syncthreads();
+    if(threadIdx.x == 0)
+    {
+        double a = 0., b = 0.;
+        for(int i = 0; i < (int)(blockDim.x >> 5); i++) { a += red0[i]; b += red1[i]; }
+        atomicAdd(&out[0], a);
+        atomicAdd(&out[1], b);
+    }
+}
+
+// out[0] = a.a, out[1] = b.b, out[2] = a.b  over [i0,i1) (b may be null)
+__global__ void __launch_bounds__(1024)
+dots_kernel(const double* __restrict__ a, const double* __restrict__ b, int i0, int i1, double* __restrict__ out)
+{
+    __shared__ double r[3][32];
+    double s0 = 0., s1 = 0., s2 = 0.;
+    for(int i = i0 + threadIdx.x; i < i1; i += blockDim.x)
+    {
+        const double x = a[i], y = b ? b[i] : 0.;
+        s0 += x * x; s1 += y * y; s2 += x * y;
+    }
+#pragma unroll
+    for(int o = 16; o > 0; o >>= 1)
+    {
+        s0 += __shfl_xor_sync(0xffffffffu, s0, o);
+        s1 += __shfl_xor_sync(0xffffffffu, s1, o);
+        s2 += __shfl_xor_sync(0xffffffffu, s2, o);
+    }
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    if(lane == 0) { r[0][w] = s0; r[1][w] = s1; r[2][w] = s2; }
+    __syncthreads();
+    if(threadIdx.x < 3)
+    {
+        double t = 0.;
+        for(int i = 0; i < (int)(blockDim.x >> 5); i++) t += r[threadIdx.x][i];
+        out[threadIdx.x] = t;
+    }
+}
+
+// step = cg g + cn gn ; p_new = p + step
+__global__ void combine_step_kernel(int n, double cg, const double* __restrict__ g, double cn, const double* __restrict__ gn,
+                                    const double* __restrict__ p, double* __restrict__ step, double* __restrict__ p_new)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if(i >= n) return;
+    const double s = cg * g[i] + (cn != 0. ? cn * gn[i] : 0.);
+    step[i] = s;
+    p_new[i] = p[i] + s;
+}
+
+// rhs = -g' (reduced) ; padding = 0
+__global__ void negate_kernel(int n, int npad, const double* __restrict__ in, double* __restrict__ out)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if(i < npad) out[i] = i < n ? -in[i] : 0.;
+}
+
+// shared part of the full-length GN step, from the reduced solution
+__global__ void scatter_shared_kernel(NormalBuffers N, const double* __restrict__ ds, double* __restrict__ step_full)
+{
+    const int r = blockIdx.x * blockDim.x + threadIdx.x;
+    if(r < N.n_r) step_full[N.state_index(r)] = ds[r];
+}
+
+////////////////////////////////////////////////////////////////////////////////
+// workspace
+////////////////////////////////////////////////////////////////////////////////
+static bool build_workspace(mrcal_b200_problem* P)
+{
+    if(P->ws) return true;
+    const Layout& L = P->L;
+    std::unique_ptr<SolverWorkspace, void (*)(SolverWorkspace*)> ws(new SolverWorkspace(), delete_ws);
+    NormalBuffers& N = ws->N;
+    DeviceArena& A = ws->arena;
+
+    const bool elim = L.sel.do_optimize_frames && (L.i_frame0 >= 0 || L.i_point0 >= 0);
+    N.e0 = elim ? (L.i_frame0 >= 0 ? L.i_frame0 : L.i_point0) : L.Nstate;
+    N.e1 = elim ? N.e0 + (L.i_frame0 >= 0 ? 6 * L.d.Nframes : 0) + (L.i_point0 >= 0 ? 3 * L.Npoints_variable : 0) : L.Nstate;
+    N.n_r = L.Nstate - (N.e1 - N.e0);
+    N.ldS = chol_padded(N.n_r > 0 ? N.n_r : 1);
+    N.cap = L.Nintr_state + 8;
+    N.Nframe_groups = (elim && L.i_frame0 >= 0) ? L.d.Nframes : 0;
+    const int Npoint_groups = (elim && L.i_point0 >= 0) ? L.Npoints_variable : 0;
+    N.Ngroups = N.Nframe_groups + Npoint_groups;
+    const int Nwi = L.d.Nobs_board + L.d.Nobs_point;
+
+    // group -> work items (board observations are sorted by frame; point observations are bucketed)
+    std::vector<int> ptr(N.Ngroups + 1, 0), items;
+    {
+        std::vector<std::vector<int>> buckets(N.Ngroups);
+        if(N.Nframe_groups)
+            for(int w = 0; w < L.d.Nobs_board; w++) buckets[P->h_obs_board[3 * w + 2]].push_back(w);
+        if(Npoint_groups)
+            for(int o = 0; o < L.d.Nobs_point; o++)
+            {
+                const int ip = P->h_obs_point[3 * o + 2];
+                if(ip < L.Npoints_variable) buckets[N.Nframe_groups + ip].push_back(L.d.Nobs_board + o);
+            }
+        for(int g = 0; g < N.Ngroups; g++)
+        {
+            ptr[g] = (int)items.size();
+            items.insert(items.end(), buckets[g].begin(), buckets[g].end());
+        }
+        ptr[N.Ngroups] = (int)items.size();
+    }
+
+    bool ok = A.alloc(&N.S, (size_t)N.ldS * N.ldS) && A.alloc(&N.gs, N.ldS, true) && A.alloc(&N.g_full, L.Nstate, true) &&
+              A.alloc(&N.info, 4, true) &&
+              A.alloc(&N.wi_nsh, Nwi, true) && A.alloc(&N.wi_cols, (size_t)Nwi * N.cap) &&
+              A.alloc(&N.wi_B, (size_t)Nwi * 6 * N.cap) && A.alloc(&N.wi_D, (size_t)Nwi * 36) && A.alloc(&N.wi_gf, (size_t)Nwi * 6) &&
+              A.alloc(&N.grp_ptr, (size_t)N.Ngroups + 1) && A.alloc(&N.grp_items, items.size()) &&
+              A.alloc(&N.grp_Dinv, (size_t)N.Ngroups * 36) && A.alloc(&N.grp_gf, (size_t)N.Ngroups * 6) &&
+              A.alloc(&ws->invL, (size_t)N.ldS * kCholBlock) && A.alloc(&ws->rhs, N.ldS, true) &&
+              A.alloc(&ws->step_gn, L.Nstate, true) && A.alloc(&ws->step, L.Nstate, true) && A.alloc(&ws->scal, 16, true);
+    if(!ok) return false;
+    MB200_CUDA_CHECK(cudaMallocHost(&ws->h_scal, 16 * sizeof(double)));
+    MB200_CUDA_CHECK(cudaMallocHost(&ws->h_info, 4 * sizeof(int)));
+    MB200_CUDA_CHECK(cudaMemcpyAsync(N.grp_ptr, ptr.data(), ptr.size() * sizeof(int), cudaMemcpyHostToDevice, P->stream));
+    if(!items.empty())
+        MB200_CUDA_CHECK(cudaMemcpyAsync(N.grp_items, items.data(), items.size() * sizeof(int), cudaMemcpyHostToDevice, P->stream));
+    MB200_CUDA_CHECK(cudaStreamSynchronize(P->stream));
+    P->ws = std::move(ws);
+    return true;
+}
+
+// Outlier marking on the host, exactly the board part of the reference's
+// markOutliers() (mrcal.c:4105-4357): sigma^2 from the inlier residuals; if any
+// |x| > 5 sigma, every |x| > 4 sigma is marked by negating its weight
+static bool mark_outliers_host(std::vector<double>& pool, const std::vector<double>& x, int Nobs, int WH,
+                               const int* obs /*icam_i,icam_e,iframe*/, int* Noutliers)
+{
+    const double k0 = 4.0, k1 = 5.0;
+    const size_t Nfeat = (size_t)Nobs * WH;
+    *Noutliers = 0;
+    long Ninliers = 0;
+    double var = 0.;
+    for(size_t i = 0; i < Nfeat; i++)
+    {
+        if(pool[3 * i + 2] <= 0.0) { (*Noutliers)++; continue; }
+        var += x[2 * i] * x[2 * i] + x[2 * i + 1] * x[2 * i + 1];
+        Ninliers++;
+    }
+    var /= (double)(Ninliers * 2);
+    bool found = false;
+    for(size_t i = 0; i < Nfeat && !found; i++)
+    {
+        if(pool[3 * i + 2] <= 0.0) continue;
+        const double dx = x[2 * i], dy = x[2 * i + 1];
+        if(dx * dx > k1 * k1 * var || dy * dy > k1 * k1 * var) found = true;
+    }
+    if(!found) return false;
+    for(int o = 0; o < Nobs; o++)
+    {
+        int Nin = 0, Nout = 0;
+        for(int k = 0; k < WH; k++)
+        {
+            const size_t i = (size_t)o * WH + k;
+            if(pool[3 * i + 2] <= 0.0) { Nout++; continue; }
+            Nin++;
+            const double dx = x[2 * i], dy = x[2 * i + 1];
+            if(dx * dx > k0 * k0 * var || dy * dy > k0 * k0 * var)
+            {
+                pool[3 * i + 2] *= -1.0;
+                (*Noutliers)++;
+            }
+        }
+        if(Nin < 3)
+            fprintf(stderr, "mrcal_b200: WARNING: Board observation %d (icam_intrinsics=%d, icam_extrinsics=%d, iframe=%d) had almost "
+                            "all of its points thrown out as outliers: only %d/%d remain. The normal equations are about to "
+                            "become singular. Something is wrong with this observation\n",
+                    o, obs[3 * o], obs[3 * o + 1], obs[3 * o + 2], Nin, Nin + Nout);
+    }
+    return true;
+}
+
+////////////////////////////////////////////////////////////////////////////////
+// one dogleg solve from the current state (the reference's dogleg_optimize2())
+////////////////////////////////////////////////////////////////////////////////
+struct PhaseTimer
+{
+    SolverWorkspace* ws; cudaStream_t s;
+    std::vector<std::pair<int, int>> spans[4];   // evaluate, assemble, factor, solve
+    size_t used = 0;
+    int mark()
+    {
+        if(used == ws->ev.size()) { cudaEvent_t e; cudaEventCreate(&e); ws->ev.push_back(e); }
+        cudaEventRecord(ws->ev[used], s);
+        return (int)used++;
+    }
+    double total(int phase)
+    {
+        double t = 0.;
+        for(auto& sp : spans[phase]) { float ms = 0.f; cudaEventElapsedTime(&ms, ws->ev[sp.first], ws->ev[sp.second]); t += ms; }
+        return t;
+    }
+};
+
+static bool read_scalars(mrcal_b200_problem* P, int n)
+{
+    SolverWorkspace* ws = P->ws.get();
+    MB200_CUDA_CHECK(cudaMemcpyAsync(ws->h_scal, ws->scal, n * sizeof(double), cudaMemcpyDeviceToHost, P->stream));
+    MB200_CUDA_CHECK(cudaStreamSynchronize(P->stream));
+    return true;
+}
+
+static bool dogleg_pass(mrcal_b200_problem* P, const mrcal_b200_solver_parameters_t& par, double* lambda,
+                        mrcal_b200_solve_info_t* info, PhaseTimer* T, double* norm2_final)
+{
+    SolverWorkspace* ws = P->ws.get();
+    NormalBuffers& N = ws->N;
+    const Layout& L = P->L;
+    cudaStream_t s = P->stream;
+    const int Nstate = L.Nstate, Nmeas = L.Nmeas;
+    int* nl = &P->launches;
+    double* const S_NORM2 = nullptr; (void)S_NORM2;
+
+    auto evaluate = [&](int which) -> bool
+    {
+        const int a = T->mark();
+        if(!problem_evaluate(P, which, true, false)) return false;
+        T->spans[0].push_back({a, T->mark()});
+        info->Nevaluations++;
+        return true;
+    };
+    auto assemble = [&](int which) -> bool
+    {
+        const int a = T->mark();
+        if(!normal_assemble(P->dp, N, P->op[which], P->d_rowptr, *lambda, s, nl)) return false;
+        if(comm_active())
+        {
+            // the one collective of the algorithm: reduced system + reduced rhs (+ the shared part of J'x)
+            if(!comm_allreduce_sum(N.S, (size_t)N.ldS * N.ldS, s)) return false;
+            if(!comm_allreduce_sum(N.gs, (size_t)N.ldS, s)) return false;
+        }
+        T->spans[1].push_back({a, T->mark()});
+        return true;
+    };
+
+    if(!evaluate(P->cur)) return false;
+    MB200_CUDA_CHECK(cudaMemcpyAsync(ws->h_scal, P->op[P->cur].norm2, sizeof(double), cudaMemcpyDeviceToHost, s));
+    MB200_CUDA_CHECK(cudaStreamSynchronize(s));
+    double norm2_x = ws->h_scal[0];
+    if(info->Nevaluations == 1) info->norm2_x_initial = norm2_x;
+
+    double trustregion = par.trustregion0;
+    bool have_system = false, have_cauchy = false, have_gn = false;
+    double g2 = 0., Jg2 = 0., kc = 0., cauchy_lensq = 0., gn_lensq = 0., g_dot_gn = 0.;
+    int stepCount = 0;
+    bool done = false;
+
+    while(!done && stepCount < par.max_iterations)
+    {
+        while(true)
+        {
+            const EvalBuffers& cur = P->op[P->cur];
+            const EvalBuffers& nxt = P->op[1 - P->cur];
+            if(!have_system)
+            {
+                if(!assemble(P->cur)) return false;
+                have_system = true;
+                have_cauchy = have_gn = false;
+            }
+            // ---- Cauchy step: -k g, k = |g|^2 / |J g|^2
+            if(!have_cauchy)
+            {
+                MB200_CUDA_CHECK(cudaMemsetAsync(ws->scal, 0, 16 * sizeof(double), s));
+                dots_kernel<<<1, 1024, 0, s>>>(N.g_full, nullptr, 0, Nstate, ws->scal + 0);
+                jv_kernel<<<592, 256, 0, s>>>(P->d_rowptr, cur.Jcol, cur.Jval, N.g_full, cur.x, Nmeas, ws->scal + 4);
+                *nl += 2;
+                if(!read_scalars(P, 8)) return false;
+                g2 = ws->h_scal[0];
+                Jg2 = ws->h_scal[5];
+                if(!(g2 > 0.) || !(Jg2 > 0.))
+                {
+                    // zero gradient: nothing to do (libdogleg's Jt_x_threshold test)
+                    done = true;
+                    break;
+                }
+                kc = g2 / Jg2;
+                cauchy_lensq = kc * kc * g2;
+                have_cauchy = true;
+            }
+            double cg, cn, update_lensq;
+            bool edge;
+            if(cauchy_lensq >= trustregion * trustregion)
+            {
+                // scaled Cauchy step to the edge of the trust region
+                cg = -kc * trustregion / sqrt(cauchy_lensq);
+                cn = 0.;
+                update_lensq = trustregion * trustregion;
+                edge = true;
+            }
+            else
+            {
+                if(!have_gn)
+                {
+                    // ---- Gauss-Newton step: factor the reduced system (diagonal loading on failure), solve, back-substitute
+                    while(true)
+                    {
+                        const int a = T->mark();
+                        if(!chol_factor(N.S, N.ldS, N.n_r, ws->invL, N.info + 1, s, nl)) return false;
+                        MB200_CUDA_CHECK(cudaMemcpyAsync(ws->h_info, N.info, 2 * sizeof(int), cudaMemcpyDeviceToHost, s));
+                        MB200_CUDA_CHECK(cudaStreamSynchronize(s));
+                        T->spans[2].push_back({a, T->mark()});
+                        info->Nfactorizations++;
+                        if(ws->h_info[0] == 0 && ws->h_info[1] == 0) break;
+                        // singular JtJ: add lambda I "from now on", as libdogleg does (1e-10, then x10)
+                        *lambda = (*lambda == 0.) ? 1e-10 : *lambda * 10.;
+                        if(!std::isfinite(*lambda) || *lambda > 1e30) { set_error("the normal equations stay singular even with lambda=%g", *lambda); return false; }
+                        fprintf(stderr, "mrcal_b200: singular JtJ (codes %d,%d). Adding %g I from now on\n", ws->h_info[0], ws->h_info[1], *lambda);
+                        if(!assemble(P->cur)) return false;
+                    }
+                    const int a = T->mark();
+                    negate_kernel<<<(N.ldS + 255) / 256, 256, 0, s>>>(N.n_r, N.ldS, N.gs, ws->rhs);
+                    (*nl)++;
+                    if(N.n_r > 0 && !chol_solve(N.S, N.ldS, ws->invL, ws->rhs, N.ldS, 1, s, nl)) return false;
+                    if(N.n_r > 0) { scatter_shared_kernel<<<(N.n_r + 255) / 256, 256, 0, s>>>(N, ws->rhs, ws->step_gn); (*nl)++; }
+                    if(!normal_backsubstitute(N, ws->rhs, ws->step_gn, N.e0, s, nl)) return false;
+                    dots_kernel<<<1, 1024, 0, s>>>(ws->step_gn, N.g_full, 0, Nstate, ws->scal + 8);
+                    (*nl)++;
+                    T->spans[3].push_back({a, T->mark()});
+                    MB200_CUDA_CHECK(cudaMemcpyAsync(ws->h_scal + 8, ws->scal + 8, 3 * sizeof(double), cudaMemcpyDeviceToHost, s));
+                    MB200_CUDA_CHECK(cudaStreamSynchronize(s));
+                    gn_lensq = ws->h_scal[8];
+                    g_dot_gn = ws->h_scal[10];
+                    have_gn = true;
+                }
+                if(gn_lensq <= trustregion * trustregion)
+                {
+                    cg = 0.; cn = 1.;
+                    update_lensq = gn_lensq;
+                    edge = false;
+                }
+                else
+                {
+                    // dogleg: a + k (b-a) on the trust-region boundary; a = Cauchy = -kc g, b = GN
+                    const double a2 = cauchy_lensq;
+                    const double ab = -kc * g_dot_gn;                 // a.b
+                    const double l2 = a2 - 2. * ab + gn_lensq;        // |b-a|^2
+                    const double c = ab - a2;                         // a.(b-a)
+                    const double disc = c * c - l2 * (a2 - trustregion * trustregion);
+                    const double k = (-c + sqrt(disc > 0. ? disc : 0.)) / l2;
+                    cg = -kc * (1. - k);
+                    cn = k;
+                    update_lensq = trustregion * trustregion;
+                    edge = true;
+                }
+            }
+            // ---- take the step
+            combine_step_kernel<<<(Nstate + 255) / 256, 256, 0, s>>>(Nstate, cg, N.g_full, cn, ws->step_gn, cur.p, ws->step, nxt.p);
+            (*nl)++;
+            if(update_lensq < par.update_threshold)
+            {
+                // libdogleg compares the SQUARED step length with update_threshold
+                done = true;
+                break;
+            }
+            MB200_CUDA_CHECK(cudaMemsetAsync(ws->scal + 12, 0, 2 * sizeof(double), s));
+            jv_kernel<<<592, 256, 0, s>>>(P->d_rowptr, cur.Jcol, cur.Jval, ws->step, cur.x, Nmeas, ws->scal + 12);
+            (*nl)++;
+            if(!evaluate(1 - P->cur)) return false;
+            MB200_CUDA_CHECK(cudaMemcpyAsync(ws->h_scal + 12, ws->scal + 12, 2 * sizeof(double), cudaMemcpyDeviceToHost, s));
+            MB200_CUDA_CHECK(cudaMemcpyAsync(ws->h_scal + 14, nxt.norm2, sizeof(double), cudaMemcpyDeviceToHost, s));
+            MB200_CUDA_CHECK(cudaStreamSynchronize(s));
+            // |x|^2 - |x + J step|^2
+            const double expected = -ws->h_scal[13] - 2. * ws->h_scal[12];
+            const double norm2_new = ws->h_scal[14];
+            const double observed = norm2_x - norm2_new;
+            const double rho = observed / expected;
+            if(rho < par.trustregion_decrease_threshold)               trustregion *= par.trustregion_decrease_factor;
+            else if(rho > par.trustregion_increase_threshold && edge)  trustregion *= par.trustregion_increase_factor;
+            if(rho > 0.0)
+            {
+                P->cur = 1 - P->cur;
+                norm2_x = norm2_new;
+                have_system = false;
+                break;
+            }
+            // rejected: same operating point, smaller trust region
+            if(trustregion < par.trustregion_threshold) { done = true; break; }
+        }
+        if(done) break;
+        stepCount++;
+        info->Niterations++;
+    }
+    *norm2_final = norm2_x;
+    return true;
+}
+
+bool solver_run(mrcal_b200_problem* P, const mrcal_b200_solver_parameters_t* params,
+                mrcal_stats_t* stats, mrcal_b200_solve_info_t* info_out)
+{
+    mrcal_b200_solver_parameters_t par;
+    if(params) par = *params; else mrcal_b200_default_solver_parameters(&par);
+    mrcal_b200_solve_info_t info = {};
+    if(!build_workspace(P)) return false;
+    SolverWorkspace* ws = P->ws.get();
+    const Layout& L = P->L;
+    cudaStream_t s = P->stream;
+    const int launches0 = P->launches;
+    info.Nreduced = ws->N.n_r;
+
+    // the CSR row pointers are analytic; jv_kernel and the regularization assembly read them
+    if(!problem_evaluate(P, P->cur, false, true)) return false;
+
+    PhaseTimer T{ws, s};
+    const int t0 = T.mark();
+    const size_t Nfeat = (size_t)L.d.Nobs_board * L.d.W * L.d.H;
+    std::vector<double> h_pool, h_x;
+    int Noutliers = 0;
+    if(Nfeat)
+    {
+        h_pool.resize(3 * Nfeat);
+        MB200_CUDA_CHECK(cudaMemcpyAsync(h_pool.data(), P->d_pool_board, 3 * Nfeat * sizeof(double), cudaMemcpyDeviceToHost, s));
+        MB200_CUDA_CHECK(cudaStreamSynchronize(s));
+        for(size_t i = 0; i < Nfeat; i++) if(h_pool[3 * i + 2] < 0.0) Noutliers++;   // mrcal.c:6420-6425
+    }
+    double lambda = 0., norm2 = -1.;
+    while(true)
+    {
+        info.Nouter++;
+        if(!dogleg_pass(P, par, &lambda, &info, &T, &norm2)) return false;
+        if(!(L.sel.do_apply_outlier_rejection && Nfeat)) break;
+        h_x.resize(L.Nmeas_board);
+        MB200_CUDA_CHECK(cudaMemcpyAsync(h_x.data(), P->op[P->cur].x, (size_t)L.Nmeas_board * sizeof(double), cudaMemcpyDeviceToHost, s));
+        MB200_CUDA_CHECK(cudaMemcpyAsync(h_pool.data(), P->d_pool_board, 3 * Nfeat * sizeof(double), cudaMemcpyDeviceToHost, s));
+        MB200_CUDA_CHECK(cudaStreamSynchronize(s));
+        if(!mark_outliers_host(h_pool, h_x, L.d.Nobs_board, L.d.W * L.d.H, P->h_obs_board.data(), &Noutliers)) break;
+        MB200_CUDA_CHECK(cudaMemcpyAsync(P->d_pool_board, h_pool.data(), 3 * Nfeat * sizeof(double), cudaMemcpyHostToDevice, s));
+        fprintf(stderr, "mrcal_b200: Threw out some outliers. New count = %d/%d (%.1f%%). Going again\n",
+                Noutliers, L.Nmeas_board, (double)(Noutliers * 100) / (double)L.Nmeas_board);
+    }
+    const int t1 = T.mark();
+    MB200_CUDA_CHECK(cudaStreamSynchronize(s));
+    float ms = 0.f;
+    cudaEventElapsedTime(&ms, ws->ev[t0], ws->ev[t1]);
+    info.ms_total = ms;
+    info.ms_evaluate = T.total(0);
+    info.ms_assemble = T.total(1);
+    info.ms_factor = T.total(2);
+    info.ms_solve = T.total(3);
+    info.norm2_x_final = norm2;
+    info.lambda_final = lambda;
+    info.Nkernel_launches = P->launches - launches0;
+    if(stats)
+    {
+        // mrcal.c:6607-6612
+        stats->rms_reproj_error__pixels = sqrt(norm2 / (double)L.Nmeas);
+        stats->Noutliers_board = Noutliers;
+        stats->Noutliers_triangulated_point = 0;
+    }
+    if(info_out) *info_out = info;
+    return true;
+}
+
+}  // namespace mb200
+using namespace mb200;
+
+extern "C" void mrcal_b200_default_solver_parameters(mrcal_b200_solver_parameters_t* p)
+{
+    // libdogleg's defaults with mrcal's overrides (mrcal.c:6289-6299)
+    p->max_iterations = 300;
+    p->trustregion0 = 1e3;
+    p->trustregion_decrease_factor = 0.1;
+    p->trustregion_decrease_threshold = 0.25;
+    p->trustregion_increase_factor = 2.0;
+    p->trustregion_increase_threshold = 0.75;
+    p->Jt_x_threshold = 0.;
+    p->update_threshold = 1e-7;
+    p->trustregion_threshold = 0.;
+}
+
+extern "C" bool mrcal_b200_problem_reduced_system(mrcal_b200_problem_t* P, double lambda, int* n_reduced,
+                                                  double* S_out, double* g_reduced, double* g_full)
+{
+    if(!build_workspace(P)) return false;
+    NormalBuffers& N = P->ws->N;
+    if(n_reduced) *n_reduced = N.n_r;
+    if(S_out == nullptr && g_reduced == nullptr && g_full == nullptr) return true;
+    if(!problem_evaluate(P, P->cur, true, true)) return false;
+    if(!normal_assemble(P->dp, N, P->op[P->cur], P->d_rowptr, lambda, P->stream, &P->launches)) return false;
+    if(S_out && N.n_r > 0)
+        MB200_CUDA_CHECK(cudaMemcpy2DAsync(S_out, (size_t)N.n_r * sizeof(double), N.S, (size_t)N.ldS * sizeof(double),
+                                           (size_t)N.n_r * sizeof(double), N.n_r, cudaMemcpyDeviceToHost, P->stream));
+    if(g_reduced && N.n_r > 0)
+        MB200_CUDA_CHECK(cudaMemcpyAsync(g_reduced, N.gs, (size_t)N.n_r * sizeof(double), cudaMemcpyDeviceToHost, P->stream));
+    if(g_full)
+        MB200_CUDA_CHECK(cudaMemcpyAsync(g_full, N.g_full, (size_t)P->L.Nstate * sizeof(double), cudaMemcpyDeviceToHost, P->stream));
+    MB200_CUDA_CHECK(cudaStreamSynchronize(P->stream));
+    return true;
+}
+
+extern "C" bool mrcal_b200_problem_optimize(mrcal_b200_problem_t* P, const mrcal_b200_solver_parameters_t* parameters,
+                                            mrcal_stats_t* stats, mrcal_b200_solve_info_t* info)
+{
+    return solver_run(P, parameters, stats, info);
+}
