@@ -1,0 +1,327 @@
+#!/usr/bin/env python3
+"""Benchmark of the calibration solve (BASELINE.json metric): trust-region
+iterations per second on the 4-camera x 400-frame
+LENSMODEL_SPLINED_STEREOGRAPHIC_order=3_Nx=30_Ny=20_fov_x_deg=170 synthetic
+calibration (BASELINE config 3).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--config 3]
+
+A "step" is one complete solve of the problem from the same seed. Prints ONE JSON
+line (rank 0). See DESIGN.md "Measurement" for what every field means.
+
+  value   iterations/s with the problem resident in HBM: Problem.reset() + Problem.optimize(),
+          timed on the device with CUDA events inside the library (info.ms_total)
+  e2e     the same metric through the reference-facing call mrcal_b200.optimize(**inputs)
+          (C-ABI mrcal_optimize) with HOST buffers: H2D of every input and D2H of every
+          output inside the timed region
+  --impl reference   the CPU path on this box's host cores: the compiled reference's own
+          optimizer_callback (oracle/_ref) driven by the restated libdogleg loop with a CPU
+          sparse factorization (oracle/dogleg_np.py); libdogleg/CHOLMOD are not in the image
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "trust-region (LM/dogleg) iterations per second, 4cam x 400frame splined calibration"
+UNIT = "iterations/s"
+
+
+class ClockSampler:
+    """nvidia-smi clocks + throttle reasons during the timed region (B200_PROFILING.md)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, device_index=0):
+        self.rows = []
+        self.proc = None
+        self.device_index = device_index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-lms", "100", "-i", str(self.device_index)],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if self.proc is None:
+            return dict(sm_mhz=None, sm_max_mhz=None, reasons=["nvidia-smi unavailable"])
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        for r in self.rows:
+            try:
+                sm.append(float(r[1])); mx.append(float(r[2]))
+                for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[4:8]):
+                    if v.lower().startswith("active"):
+                        reasons.add(name)
+            except Exception:
+                pass
+        return dict(sm_mhz=float(np.median(sm)) if sm else None, sm_max_mhz=max(mx) if mx else None,
+                    reasons=sorted(reasons), samples=len(sm))
+
+
+def problem_inputs(config):
+    from mrcal_b200 import synthetic
+    kw, truth = synthetic.baseline_config(config, pixel_noise=0.3)
+    return kw
+
+
+def describe(config, kw):
+    return dict(workload=f"BASELINE config {config}: {kw['intrinsics'].shape[0]} cameras, "
+                         f"{kw['rt_ref_frame'].shape[0]} frames, {kw['observations_board'].shape[2]}x"
+                         f"{kw['observations_board'].shape[1]} board, {kw['lensmodel']}",
+                lensmodel=kw["lensmodel"], Ncameras=int(kw["intrinsics"].shape[0]),
+                Nframes=int(kw["rt_ref_frame"].shape[0]),
+                Nobservations_board=int(kw["observations_board"].shape[0]),
+                pixel_noise=0.3, seed="truth perturbed (mrcal_b200/synthetic.py, default_rng(0))",
+                l2="working set per iteration (Jacobian strips 146 MB x2 + normal-equation blocks) exceeds the "
+                   "126 MB L2; additionally a 256 MB buffer is written between timed steps")
+
+
+def cpu_reference_run(kw, iterations, verbose=False):
+    """`iterations` trust-region iterations of the CPU path from the seed; returns (iterations done, seconds, split)."""
+    from oracle import dogleg_np, ref
+    if not ref.available():
+        return None
+    t_cb = [0.0]
+    t_fac = [0.0]
+    fac0 = dogleg_np.factor_solve
+
+    def timed_factor(A, rhs):
+        t = time.perf_counter()
+        out = fac0(A, rhs)
+        t_fac[0] += time.perf_counter() - t
+        return out
+
+    kw2 = {k: (v.copy() if isinstance(v, np.ndarray) else v) for k, v in kw.items()}
+    t0 = time.perf_counter()
+    r = dogleg_np.optimize(kw2, factor=timed_factor, max_iterations=iterations)
+    dt = time.perf_counter() - t0
+    return r["iterations"], dt, dict(factor_solve_s=t_fac[0], evaluations=r["evaluations"],
+                                     factorizations=r["factorizations"])
+
+
+def measure_fp64_peak():
+    """cuBLAS DGEMM throughput, the denominator for the fp64-tensor roofline (not in MEASURED_PEAKS.json)."""
+    import torch
+    n = 8192
+    a = torch.randn(n, n, device="cuda", dtype=torch.float64)
+    b = torch.randn(n, n, device="cuda", dtype=torch.float64)
+    torch.matmul(a, b)
+    torch.cuda.synchronize()
+    best = 1e9
+    for _ in range(3):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        torch.matmul(a, b)
+        e1.record()
+        torch.cuda.synchronize()
+        best = min(best, e0.elapsed_time(e1))
+    del a, b
+    torch.cuda.empty_cache()
+    return 2.0 * n ** 3 / (best * 1e-3) / 1e12
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=("ours", "reference"))
+    ap.add_argument("--config", type=int, default=3)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+
+    kw = problem_inputs(args.config)
+    config = describe(args.config, kw)
+
+    ###################################################################################### reference arm
+    if args.impl == "reference":
+        if rank != 0:
+            return 0
+        # a step = a bounded sample of the workload: the first 2 trust-region iterations from the seed
+        iters_per_step = 2
+        ncores = os.cpu_count()
+        for _ in range(min(args.warmup, 1)):
+            cpu_reference_run(kw, 1)
+        tot_it, tot_s, split = 0, 0.0, None
+        for _ in range(args.steps):
+            r = cpu_reference_run(kw, iters_per_step)
+            if r is None:
+                print(json.dumps({"impl": "reference", "unavailable": "oracle/_ref/libmrcal_ref.so is missing"}))
+                return 0
+            tot_it += r[0]; tot_s += r[1]; split = r[2]
+        v = tot_it / tot_s
+        sample = (f"first {iters_per_step} trust-region iterations from the seed per step: compiled reference "
+                  "optimizer_callback (oracle/_ref) + restated libdogleg loop + scipy SuperLU symmetric-mode "
+                  "factorization of JtJ (libdogleg/CHOLMOD absent from the image); single-threaded like the reference")
+        print(json.dumps({"impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus,
+                          "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * tot_s / args.steps,
+                          "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64",
+                          "data": "synthetic", "config": config,
+                          "cpu_baseline": {"value": v, "unit": UNIT, "cores": 1, "kind": "port", "sample": sample,
+                                           "host_cores_available": ncores, "split": split},
+                          "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}))
+        return 0
+
+    ###################################################################################### our arm
+    import torch
+    import mrcal_b200
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+        from mrcal_b200 import distributed
+        kw_local, shard = distributed.shard_inputs(kw, rank, world)
+        distributed.init_comm(rank, world, local_rank)
+    else:
+        kw_local, shard = kw, None
+
+    P = mrcal_b200.Problem(**kw_local)
+    if shard is not None:
+        from mrcal_b200 import distributed
+        distributed.attach(P, shard)
+    flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device="cuda")
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            torch.distributed.barrier()
+            torch.cuda.synchronize()
+
+    def one_step():
+        flush.zero_()
+        torch.cuda.synchronize()
+        P.reset()
+        return P.optimize()
+
+    for _ in range(args.warmup):
+        one_step()
+    barrier()
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    infos = []
+    for _ in range(args.steps):
+        infos.append(one_step())
+    barrier()
+    clocks = sampler.stop() if rank == 0 else None
+
+    ms = np.array([i["ms_total"] for i in infos])
+    its = np.array([i["Niterations"] for i in infos])
+    dev_ms = float(ms.sum())
+    if world > 1:
+        t = torch.tensor([dev_ms], device="cuda", dtype=torch.float64)
+        torch.distributed.all_reduce(t, op=torch.distributed.ReduceOp.MAX)
+        dev_ms = float(t.item())
+    value = float(its.sum()) / (dev_ms * 1e-3)
+
+    ###### e2e: the reference-facing call with host buffers, H2D + D2H inside the timed region
+    e2e = None
+    if world == 1:
+        names = ("intrinsics", "rt_cam_ref", "rt_ref_frame", "calobject_warp", "observations_board")
+        pinned = {n: torch.from_numpy(kw[n].copy()).pin_memory() for n in names}
+        kw_e2e = dict(kw)
+        for n in names:
+            kw_e2e[n] = pinned[n].numpy()
+        h2d = sum(v.nbytes for v in kw_e2e.values() if isinstance(v, np.ndarray))
+        e_it, e_s, d2h = 0, 0.0, 0
+        for i in range(args.warmup + args.steps):
+            for n in names:
+                np.copyto(kw_e2e[n], kw[n])
+            flush.zero_()
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            out = mrcal_b200.optimize(**kw_e2e)
+            dt = time.perf_counter() - t0
+            if i >= args.warmup:
+                e_s += dt
+                # the C-ABI returns no iteration count: the device-resident runs of the same problem give it
+                e_it += int(round(its.mean()))
+                d2h = out["b_packed"].nbytes + out["x"].nbytes + sum(kw_e2e[n].nbytes for n in names)
+        e2e = {"value": e_it / e_s, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
+               "ms_per_step": 1e3 * e_s / args.steps,
+               "call": "mrcal_b200.optimize(**optimization_inputs) -> C-ABI mrcal_optimize(), host numpy buffers"}
+
+    if rank != 0:
+        return 0
+
+    ###### roofline of the dominant kernel family
+    last = infos[-1]
+    n_c = last["Nreduced"]
+    roofline = None
+    try:
+        peak = measure_fp64_peak()
+        per_fact_s = 1e-3 * sum(i["ms_factor"] for i in infos) / max(1, sum(i["Nfactorizations"] for i in infos))
+        flops = n_c ** 3 / 3.0
+        achieved = flops / per_fact_s / 1e12
+        roofline = {"bound": "tensor", "kernel": "reduced-system Cholesky (potrf_diag + trsm + syrk_dmma, chol.cu)",
+                    "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak, "traffic": None,
+                    "flops_per_launch": flops, "n_reduced": n_c,
+                    "peak_source": "cuBLAS DGEMM 8192^3 (torch.matmul fp64) measured in this run: MEASURED_PEAKS.json has no fp64 entry"}
+    except Exception as e:   # pragma: no cover
+        roofline = {"error": str(e)}
+    # the Jacobian fill against HBM (bytes_cb = 24 Ncorners + 8 Nstate + 8 Nmeas + 12 nnz + 4 (Nmeas+1))
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        hbm = peaks["hbm_gbs"]; hbm_src = "MEASURED_PEAKS.json hbm_gbs (of measured)"
+    except Exception:
+        hbm = 6650.0; hbm_src = "fallback 6.65 TB/s (of fallback)"
+    ms_cb = P.time_callback(20, True)
+    ncorners = kw_local["observations_board"].shape[0] * kw_local["observations_board"].shape[1] * kw_local["observations_board"].shape[2]
+    bytes_cb = 24 * ncorners + 8 * P.Nstate + 8 * P.Nmeasurements + 12 * P.N_j_nonzero + 4 * (P.Nmeasurements + 1)
+    fill = {"bound": "hbm", "kernel": "eval_boards_kernel (residual + Jacobian fill)", "achieved": bytes_cb / (ms_cb * 1e-3) / 1e9,
+            "peak": hbm, "unit": "GB/s", "frac": bytes_cb / (ms_cb * 1e-3) / 1e9 / hbm, "bytes_per_launch": bytes_cb,
+            "ms_per_launch": ms_cb, "peak_source": hbm_src, "traffic": None}
+
+    ###### CPU baseline on this box's host cores: a bounded sample
+    cpu = None
+    if world == 1 and not args.no_cpu_baseline:
+        r = cpu_reference_run(kw, 2)
+        if r is not None:
+            cpu = {"value": r[0] / r[1], "unit": UNIT, "cores": 1, "kind": "port",
+                   "sample": "first 2 trust-region iterations of the same problem from the same seed: compiled reference "
+                             "optimizer_callback (oracle/_ref) + restated libdogleg loop + scipy SuperLU symmetric-mode "
+                             "factorization (libdogleg/CHOLMOD absent from the image)",
+                   "host_cores_available": os.cpu_count(), "split": r[2], "seconds": r[1]}
+
+    out = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+           "ms_per_step": dev_ms / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+           "dtype": "f64", "data": "synthetic", "config": config,
+           "iterations_per_step": float(its.mean()), "rms_reproj_error__pixels": last["rms_reproj_error__pixels"],
+           "gpu_launches": int(sum(i["Nkernel_launches"] for i in infos)),
+           "phase_ms_per_iteration": {k: float(sum(i[k] for i in infos) / its.sum())
+                                      for k in ("ms_evaluate", "ms_assemble", "ms_factor", "ms_solve")},
+           "clocks": clocks, "e2e": e2e, "roofline": roofline, "roofline_jacobian_fill": fill, "cpu_baseline": cpu}
+    print(json.dumps(out))
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())

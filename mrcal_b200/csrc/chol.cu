@@ -31,76 +31,104 @@ constexpr int NB = 64;     // inner block
 constexpr int NBO = 256;   // outer panel
 
 ////////////////////////////////////////////////////////////////////////////////
-// diagonal block: Cholesky + inverse of the factor, one CTA of 256 threads
+// diagonal block: Cholesky + inverse of the factor. One CTA of 64 threads; thread i
+// keeps ROW i of the block in registers (all loops fully unrolled, so the row is a
+// register array), finished columns are published through shared memory.
+//   factor:  left-looking. column j: s_i = a_ij - sum_{k<j} l_ik l_jk ; l_jj = sqrt(s_j) ;
+//            l_ij = s_i / l_jj.  Two barriers per column, 2016 DFMA per thread.
+//   inverse: thread c computes column c of X = inv(L) by forward substitution; all
+//            threads run the same instruction stream (x_k = 0 for k < c), so the reads
+//            of L from shared memory are broadcasts.
 ////////////////////////////////////////////////////////////////////////////////
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(NB)
 potrf_diag_kernel(double* __restrict__ A, int ld, int k0, double* __restrict__ invL, int* __restrict__ info, int nreal)
 {
-    extern __shared__ __align__(16) double dsm[];
-    double (*s)[NB + 1] = reinterpret_cast<double (*)[NB + 1]>(dsm);
-    double (*x)[NB + 1] = reinterpret_cast<double (*)[NB + 1]>(dsm + NB * (NB + 1));
-    __shared__ int bad;
-    const int tid = threadIdx.x;
-    if(tid == 0) bad = 0;
-    for(int e = tid; e < NB * NB; e += 256)
+    __shared__ double sL[NB][NB + 1];
+    __shared__ double s_rinv[NB];
+    const int i = threadIdx.x;
+    for(int e = i; e < NB * NB; e += NB)
     {
-        const int i = e / NB, j = e % NB;
-        s[i][j] = j <= i ? A[(size_t)(k0 + i) * ld + k0 + j] : 0.;
+        const int r = e / NB, c = e % NB;
+        sL[r][c] = c <= r ? A[(size_t)(k0 + r) * ld + k0 + c] : 0.;
     }
     __syncthreads();
+    double row[NB];
+#pragma unroll
+    for(int k = 0; k < NB; k++) row[k] = sL[i][k];
+    __syncthreads();
+
+#pragma unroll
     for(int j = 0; j < NB; j++)
     {
-        if(tid == 0)
+        double s0 = row[j], s1 = 0., s2 = 0., s3 = 0.;
+#pragma unroll
+        for(int k = 0; k < j; k++)
         {
-            const double d = s[j][j];
+            const double l = sL[j][k];
+            if((k & 3) == 0) s0 -= row[k] * l;
+            else if((k & 3) == 1) s1 -= row[k] * l;
+            else if((k & 3) == 2) s2 -= row[k] * l;
+            else s3 -= row[k] * l;
+        }
+        const double sj = (s0 + s1) + (s2 + s3);
+        if(i == j)
+        {
+            double d = sj;
             if(!(d > 0.))
             {
-                // not positive definite. Remember the first failing pivot; keep
-                // going with a harmless value so the kernel chain terminates
-                if(k0 + j < nreal && bad == 0) { bad = 1; atomicCAS(info, 0, k0 + j + 1); }
-                s[j][j] = 1.;
+                // not positive definite. Remember the first failing pivot; carry on with a
+                // harmless value so the chain of kernels still terminates
+                if(k0 + j < nreal) atomicCAS(info, 0, k0 + j + 1);
+                d = 1.;
             }
-            else
-                s[j][j] = sqrt(d);
+            const double l = sqrt(d);
+            row[j] = l;
+            sL[j][j] = l;
+            s_rinv[j] = 1. / l;
         }
         __syncthreads();
-        const double djj = s[j][j];
-        if(tid > j && tid < NB) s[tid][j] /= djj;
-        __syncthreads();
-        // trailing update of the block: s[i][k] -= s[i][j] s[k][j], j < k <= i
-        const int m = NB - 1 - j;
-        for(int e = tid; e < m * m; e += 256)
+        if(i > j)
         {
-            const int i = j + 1 + e / m, k = j + 1 + e % m;
-            if(k <= i) s[i][k] -= s[i][j] * s[k][j];
+            row[j] = sj * s_rinv[j];
+            sL[i][j] = row[j];
         }
         __syncthreads();
     }
-    for(int e = tid; e < NB * NB; e += 256)
+    // L back to global (lower triangle), coalesced
+    for(int e = i; e < NB * NB; e += NB)
     {
-        const int i = e / NB, j = e % NB;
-        if(j <= i) A[(size_t)(k0 + i) * ld + k0 + j] = s[i][j];
+        const int r = e / NB, c = e % NB;
+        if(c <= r) A[(size_t)(k0 + r) * ld + k0 + c] = sL[r][c];
     }
-    // X = inv(L): 4 threads per column c share each dot product
+    // column i of inv(L)
+    double xc[NB];
+#pragma unroll
+    for(int r = 0; r < NB; r++)
     {
-        const int c = tid >> 2, part = tid & 3;
-        for(int i = 0; i < NB; i++)
+        double a0 = 0., a1 = 0., a2 = 0., a3 = 0.;
+#pragma unroll
+        for(int k = 0; k < r; k++)
         {
-            double acc = 0.;
-            if(i > c)
-                for(int k = c + part; k < i; k += 4) acc += s[i][k] * x[k][c];
-            acc += __shfl_xor_sync(0xffffffffu, acc, 1);
-            acc += __shfl_xor_sync(0xffffffffu, acc, 2);
-            if(part == 0) x[i][c] = i < c ? 0. : (i == c ? 1. / s[i][i] : -acc / s[i][i]);
-            __syncwarp();
+            const double l = sL[r][k];
+            if((k & 3) == 0) a0 += l * xc[k];
+            else if((k & 3) == 1) a1 += l * xc[k];
+            else if((k & 3) == 2) a2 += l * xc[k];
+            else a3 += l * xc[k];
         }
+        const double acc = (a0 + a1) + (a2 + a3);
+        xc[r] = ((r == i ? 1. : 0.) - acc) * s_rinv[r];
     }
     __syncthreads();
-    for(int e = tid; e < NB * NB; e += 256) invL[e] = x[e / NB][e % NB];
+#pragma unroll
+    for(int r = 0; r < NB; r++) sL[r][i] = xc[r];
+    __syncthreads();
+    for(int e = i; e < NB * NB; e += NB) invL[e] = sL[e / NB][e % NB];
 }
 
 ////////////////////////////////////////////////////////////////////////////////
-// panel: X[i][c] = sum_m A[i][k0+m] invL[c][m], rows i >= k0+64, in place
+// panel: X[i][c] = sum_m A[i][k0+m] invL[c][m], rows i >= k0+64, in place.
+// 64x64 tile per CTA, 4x4 outputs per thread; a thread's 4 columns are 16 apart so
+// that a warp's shared-memory reads of invL rows fall in distinct banks
 ////////////////////////////////////////////////////////////////////////////////
 __global__ void __launch_bounds__(256)
 trsm_kernel(double* __restrict__ A, int ld, int k0, const double* __restrict__ invL, int n)
@@ -117,14 +145,14 @@ trsm_kernel(double* __restrict__ A, int ld, int k0, const double* __restrict__ i
         sl[i][j] = invL[e];
     }
     __syncthreads();
-    // each thread: a 4x4 block of outputs
-    const int ti = (tid / 16) * 4, tc = (tid % 16) * 4;
+    const int ti = (tid / 16) * 4, tc = tid % 16;
     double acc[4][4] = {};
+#pragma unroll 8
     for(int m = 0; m < NB; m++)
     {
         double a[4], l[4];
 #pragma unroll
-        for(int r = 0; r < 4; r++) { a[r] = sa[ti + r][m]; l[r] = sl[tc + r][m]; }
+        for(int r = 0; r < 4; r++) { a[r] = sa[ti + r][m]; l[r] = sl[tc + 16 * r][m]; }
 #pragma unroll
         for(int r = 0; r < 4; r++)
 #pragma unroll
@@ -133,7 +161,7 @@ trsm_kernel(double* __restrict__ A, int ld, int k0, const double* __restrict__ i
 #pragma unroll
     for(int r = 0; r < 4; r++)
 #pragma unroll
-        for(int c = 0; c < 4; c++) A[(size_t)(row0 + ti + r) * ld + k0 + tc + c] = acc[r][c];
+        for(int c = 0; c < 4; c++) A[(size_t)(row0 + ti + r) * ld + k0 + tc + 16 * c] = acc[r][c];
     (void)n;
 }
 
@@ -260,7 +288,6 @@ static bool configure_kernels()
     static bool configured = false;
     if(configured) return true;
     MB200_CUDA_CHECK(cudaFuncSetAttribute(syrk_dmma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSyrkSmem));
-    MB200_CUDA_CHECK(cudaFuncSetAttribute(potrf_diag_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kBlockSmem));
     MB200_CUDA_CHECK(cudaFuncSetAttribute(trsm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kBlockSmem));
     configured = true;
     return true;
@@ -284,7 +311,7 @@ bool chol_factor(double* A, int npad, int nreal, double* invL, int* d_info, cuda
         const int K1 = K0 + NBO < npad ? K0 + NBO : npad;
         for(int k0 = K0; k0 < K1; k0 += NB)
         {
-            potrf_diag_kernel<<<1, 256, kBlockSmem, s>>>(A, npad, k0, invL + (size_t)(k0 / NB) * NB * NB, d_info, nreal);
+            potrf_diag_kernel<<<1, NB, 0, s>>>(A, npad, k0, invL + (size_t)(k0 / NB) * NB * NB, d_info, nreal);
             if(nlaunch) (*nlaunch)++;
             const int nrows_below = npad - (k0 + NB);
             if(nrows_below > 0)

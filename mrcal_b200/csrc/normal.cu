@@ -17,9 +17,17 @@
 // knot columns are data-dependent (mrcal.c:2171-2185), so each CTA discovers
 // its own local column set every time.
 #include "normal.h"
+#include "chol.h"
 
 namespace mb200 {
 
+// COMPACTION. Only the shared unknowns that some observation row touches are coupled to anything.
+// For the wide splined models most knots are never hit by a board corner and appear only in their
+// own 2x2 regularization block (at BASELINE config 3: 1266 of 4820 shared unknowns are coupled), so
+// each assembly first marks the touched ("active") shared unknowns, numbers them compactly, and S is
+// built and factored over those alone; the untouched ones are solved from their regularization rows
+// directly (inactive_step_kernel). The reference gets the same saving from CHOLMOD's sparse
+// factorization.
 constexpr int kMaxRowNnz = 40;     // widest row: 16 intrinsics + 6 + 6 + 2 (any model here <= 30)
 constexpr int kGramMax   = 216;    // largest local column count whose Gram matrix lives in shared memory
 
@@ -73,14 +81,104 @@ __device__ __forceinline__ ItemDesc describe_item(const DevProblem& P, int w, in
 
 __device__ __forceinline__ int tri(int a, int b) { return a * (a + 1) / 2 + b; }   // a >= b
 
-// One CTA per work item (board observation or point observation)
+// Pass 1, one CTA per work item: which shared columns does the item touch? Writes the item's column
+// list (reduced numbering, increasing) and marks those unknowns active.
 __global__ void __launch_bounds__(256)
-assemble_items_kernel(DevProblem P, NormalBuffers N, const double* __restrict__ x,
+item_columns_kernel(DevProblem P, NormalBuffers N, const int* __restrict__ Jcol)
+{
+    extern __shared__ __align__(16) double dsm[];
+    __shared__ int s_scan[256];
+    const int w = blockIdx.x, tid = threadIdx.x;
+    const ItemDesc d = describe_item(P, w, N.Nframe_groups);
+    const int ncam = d.cam0 >= 0 ? 6 : 0, nwarp = d.warp0 >= 0 ? 2 : 0;
+    short* lmap = reinterpret_cast<short*>(dsm);   // [clen]
+    for(int i = tid; i < d.clen; i += 256) lmap[i] = 0;
+    __syncthreads();
+    if(d.nI > 0)
+        for(int e = tid; e < d.rows * d.nI; e += 256)
+        {
+            const int r = e / d.nI, k = e - r * d.nI;
+            const int c = Jcol[(size_t)d.j0 + (size_t)r * d.nnz_row + k] - d.cbase;
+            lmap[c] = 1;
+            // the two surfaces of a spline knot stay together: their regularization rows couple them
+            if(N.splined && c >= P.Ncore_state) lmap[P.Ncore_state + ((c - P.Ncore_state) ^ 1)] = 1;
+        }
+    __syncthreads();
+    // exclusive scan over clen flags, 256 threads each owning a contiguous chunk
+    const int per = (d.clen + 255) / 256;
+    const int lo = tid * per, hi = min(lo + per, d.clen);
+    int cnt = 0;
+    for(int i = lo; i < hi; i++) cnt += lmap[i];
+    s_scan[tid] = cnt;
+    __syncthreads();
+    for(int o = 1; o < 256; o <<= 1)
+    {
+        const int v = tid >= o ? s_scan[tid - o] : 0;
+        __syncthreads();
+        s_scan[tid] += v;
+        __syncthreads();
+    }
+    int base = s_scan[tid] - cnt;
+    int* cols = N.wi_cols + (size_t)w * N.cap;
+    for(int i = lo; i < hi; i++)
+        if(lmap[i])
+        {
+            const int r = N.reduced_index(d.cbase + i);
+            cols[base++] = r;
+            N.active[r] = 1;
+        }
+    const int nloc = s_scan[255];
+    if(tid < ncam)  { const int r = N.reduced_index(d.cam0 + tid);  cols[nloc + tid] = r;        N.active[r] = 1; }
+    if(tid < nwarp) { const int r = N.reduced_index(d.warp0 + tid); cols[nloc + ncam + tid] = r; N.active[r] = 1; }
+    if(tid == 0)
+    {
+        const int nsh = nloc + ncam + nwarp;
+        N.wi_nsh[w] = nsh;
+        atomicMax(&N.stat[1], nsh + d.nelim);
+    }
+}
+
+// unknowns named by a regularization row that is not a per-unknown (or per-knot) block must be in the
+// coupled system: today that is the unity_cam01 row (3 columns)
+__global__ void mark_reg_active_kernel(DevProblem P, NormalBuffers N)
+{
+    if(P.reg_unity && threadIdx.x < 3) N.active[N.reduced_index(P.i_extr0 + 3 + threadIdx.x)] = 1;
+}
+
+// compact numbering of the active shared unknowns: one CTA
+__global__ void __launch_bounds__(1024)
+compact_scan_kernel(NormalBuffers N)
+{
+    __shared__ int s_scan[1024];
+    const int tid = threadIdx.x;
+    const int per = (N.n_r + 1023) / 1024;
+    const int lo = tid * per, hi = min(lo + per, N.n_r);
+    int cnt = 0;
+    for(int i = lo; i < hi; i++) cnt += N.active[i] ? 1 : 0;
+    s_scan[tid] = cnt;
+    __syncthreads();
+    for(int o = 1; o < 1024; o <<= 1)
+    {
+        const int v = tid >= o ? s_scan[tid - o] : 0;
+        __syncthreads();
+        s_scan[tid] += v;
+        __syncthreads();
+    }
+    int base = s_scan[tid] - cnt;
+    for(int i = lo; i < hi; i++)
+    {
+        if(N.active[i]) { N.cidx[i] = base; N.cinv[base] = i; base++; }
+        else            N.cidx[i] = -1;
+    }
+    if(tid == 1023) N.stat[0] = s_scan[1023];
+}
+
+// Pass 2, one CTA per work item: the Gram matrix of the item's rows over its local columns
+__global__ void __launch_bounds__(256)
+assemble_items_kernel(DevProblem P, NormalBuffers N, int gram_cap, const double* __restrict__ x,
                       const double* __restrict__ Jval, const int* __restrict__ Jcol)
 {
     extern __shared__ __align__(16) double dsm[];
-    __shared__ int   s_scan[256];
-    __shared__ int   s_nloc;
     __shared__ short s_lidx[2][kMaxRowNnz];
     __shared__ double s_val[2][kMaxRowNnz];
     __shared__ double s_xr[2];
@@ -89,12 +187,20 @@ assemble_items_kernel(DevProblem P, NormalBuffers N, const double* __restrict__ 
     const int w = blockIdx.x, tid = threadIdx.x;
     const ItemDesc d = describe_item(P, w, N.Nframe_groups);
     const int ncam = d.cam0 >= 0 ? 6 : 0, nwarp = d.warp0 >= 0 ? 2 : 0;
+    const int nsh = N.wi_nsh[w], nloc = nsh - ncam - nwarp, ntot = nsh + d.nelim;
+    const bool big = ntot > gram_cap;   // Gram matrix does not fit: shared x shared goes straight to global
 
-    // ---- 1. local numbering of the touched intrinsics columns
-    short* lmap = reinterpret_cast<short*>(dsm);                       // [clen]
+    // shared-memory carve-up: lmap [clen] shorts | ccol [nsh] ints | gram | gvec [ntot]
+    short* lmap = reinterpret_cast<short*>(dsm);
     const int lmap_doubles = (d.clen * (int)sizeof(short) + 7) / 8;
-    double* gram = dsm + lmap_doubles;
-    for(int i = tid; i < d.clen; i += 256) lmap[i] = 0;
+    int* ccol = reinterpret_cast<int*>(dsm + lmap_doubles);               // compact index of each local column
+    const int ccol_doubles = (N.cap * (int)sizeof(int) + 7) / 8;
+    double* gram = dsm + lmap_doubles + ccol_doubles;
+    const int ngram = big ? d.nelim * ntot : ntot * (ntot + 1) / 2;
+    double* gvec = gram + ngram;   // [ntot] J'x of this item
+
+    const int* cols = N.wi_cols + (size_t)w * N.cap;
+    for(int i = tid; i < d.clen; i += 256) lmap[i] = -1;
     for(int e = tid; e < kMaxRowNnz * (kMaxRowNnz + 1) / 2; e += 256)
     {
         // decode pair index e -> (a >= b)
@@ -104,50 +210,14 @@ assemble_items_kernel(DevProblem P, NormalBuffers N, const double* __restrict__ 
         s_pa[e] = (unsigned char)a;
         s_pb[e] = (unsigned char)(e - a * (a + 1) / 2);
     }
-    __syncthreads();
-    if(d.nI > 0)
-        for(int e = tid; e < d.rows * d.nI; e += 256)
-        {
-            const int r = e / d.nI, k = e - r * d.nI;
-            lmap[Jcol[(size_t)d.j0 + (size_t)r * d.nnz_row + k] - d.cbase] = 1;
-        }
-    __syncthreads();
-    // exclusive scan over clen flags, 256 threads each owning a contiguous chunk
-    {
-        const int per = (d.clen + 255) / 256;
-        const int lo = tid * per, hi = min(lo + per, d.clen);
-        int cnt = 0;
-        for(int i = lo; i < hi; i++) cnt += lmap[i];
-        s_scan[tid] = cnt;
-        __syncthreads();
-        for(int o = 1; o < 256; o <<= 1)
-        {
-            const int v = tid >= o ? s_scan[tid - o] : 0;
-            __syncthreads();
-            s_scan[tid] += v;
-            __syncthreads();
-        }
-        int base = s_scan[tid] - cnt;
-        for(int i = lo; i < hi; i++) { const int f = lmap[i]; lmap[i] = f ? (short)base : (short)-1; base += f; }
-        if(tid == 255) s_nloc = s_scan[255];
-        __syncthreads();
-    }
-    const int nloc = s_nloc;
-    const int nsh = nloc + ncam + nwarp, ntot = nsh + d.nelim;
-    const bool big = ntot > kGramMax;   // Gram matrix does not fit: shared x shared goes straight to global
-
-    // the item's shared columns, in reduced numbering (increasing)
-    int* cols = N.wi_cols + (size_t)w * N.cap;
-    for(int i = tid; i < d.clen; i += 256)
-        if(lmap[i] >= 0) cols[lmap[i]] = N.reduced_index(d.cbase + i);
-    if(tid < ncam)  cols[nloc + tid] = N.reduced_index(d.cam0 + tid);
-    if(tid < nwarp) cols[nloc + ncam + tid] = N.reduced_index(d.warp0 + tid);
-    if(tid == 0) N.wi_nsh[w] = nsh;
-
-    // ---- 2. accumulate. gram: lower-packed ntot x ntot, or (big) the nelim x ntot strip
-    const int ngram = big ? d.nelim * ntot : ntot * (ntot + 1) / 2;
-    double* gvec = gram + ngram;   // [ntot] J'x of this item
     for(int i = tid; i < ngram + ntot; i += 256) gram[i] = 0.;
+    __syncthreads();
+    for(int l = tid; l < nsh; l += 256)
+    {
+        const int r = cols[l];
+        ccol[l] = N.cidx[r];
+        if(l < nloc) lmap[r - d.cbase] = (short)l;   // intrinsics columns sit before the eliminated range: reduced == state index
+    }
     __syncthreads();
 
     const int npairs = d.nnz_row * (d.nnz_row + 1) / 2;
@@ -176,8 +246,8 @@ assemble_items_kernel(DevProblem P, NormalBuffers N, const double* __restrict__ 
             int la = s_lidx[buf][a], lb = s_lidx[buf][b];
             if(la < lb) { const int t = la; la = lb; lb = t; }
             if(!big) gram[tri(la, lb)] += v;
-            else if(la >= nsh) gram[(la - nsh) * ntot + lb] += v;          // eliminated x anything
-            else atomicAdd(&N.S[(size_t)cols[la] * N.ldS + cols[lb]], v);    // shared x shared
+            else if(la >= nsh) gram[(la - nsh) * ntot + lb] += v;            // eliminated x anything
+            else atomicAdd(&N.S[(size_t)ccol[la] * N.ldS + ccol[lb]], v);      // shared x shared
         }
         if(tid >= 64 && tid < 64 + d.nnz_row)
         {
@@ -190,8 +260,8 @@ assemble_items_kernel(DevProblem P, NormalBuffers N, const double* __restrict__ 
     }
     __syncthreads();
 
-    // ---- 3. write out
-    // shared x shared -> S (lower triangle, reduced numbering)
+    // ---- write out
+    // shared x shared -> S (lower triangle, compact numbering; local order == global order)
     if(!big)
         for(int e = tid; e < nsh * (nsh + 1) / 2; e += 256)
         {
@@ -200,13 +270,13 @@ assemble_items_kernel(DevProblem P, NormalBuffers N, const double* __restrict__ 
             while((a + 1) * (a + 2) / 2 <= e) a++;
             const int b = e - a * (a + 1) / 2;
             const double v = gram[e];
-            if(v != 0.) atomicAdd(&N.S[(size_t)cols[a] * N.ldS + cols[b]], v);
+            if(v != 0.) atomicAdd(&N.S[(size_t)ccol[a] * N.ldS + ccol[b]], v);
         }
     // gradient of the shared unknowns: into g' (completed by the Schur kernel) and into the full J'x
     for(int l = tid; l < nsh; l += 256)
         if(gvec[l] != 0.)
         {
-            atomicAdd(&N.gs[cols[l]], gvec[l]);
+            atomicAdd(&N.gs[ccol[l]], gvec[l]);
             atomicAdd(&N.g_full[N.state_index(cols[l])], gvec[l]);
         }
     // eliminated block of this item: B (nelim x nsh), D (nelim x nelim), gf (nelim)
@@ -233,7 +303,8 @@ assemble_items_kernel(DevProblem P, NormalBuffers N, const double* __restrict__ 
     }
 }
 
-// Regularization rows touch shared unknowns only: one thread per row
+// Regularization rows touch shared unknowns only: one thread per row. A row whose unknowns are
+// inactive (touched by no observation) stays out of S: inactive_step_kernel deals with it
 __global__ void assemble_reg_kernel(DevProblem P, NormalBuffers N, const double* __restrict__ x,
                                     const double* __restrict__ Jval, const int* __restrict__ Jcol,
                                     const int* __restrict__ rowptr)
@@ -242,19 +313,77 @@ __global__ void assemble_reg_kernel(DevProblem P, NormalBuffers N, const double*
     if(m >= P.Nmeas) return;
     const int j0 = rowptr[m], j1 = rowptr[m + 1];
     const double xm = x[m];
+    bool all_active = true;
     for(int a = j0; a < j1; a++)
     {
-        const int ca = N.reduced_index(Jcol[a]);
+        atomicAdd(&N.g_full[Jcol[a]], Jval[a] * xm);
+        if(N.cidx[N.reduced_index(Jcol[a])] < 0) all_active = false;
+    }
+    if(!all_active) return;
+    for(int a = j0; a < j1; a++)
+    {
+        const int ca = N.cidx[N.reduced_index(Jcol[a])];
         const double va = Jval[a];
         atomicAdd(&N.gs[ca], va * xm);
-        atomicAdd(&N.g_full[Jcol[a]], va * xm);
         for(int b = j0; b <= a; b++)
         {
-            const int cb = N.reduced_index(Jcol[b]);
+            const int cb = N.cidx[N.reduced_index(Jcol[b])];
             const int hi = ca > cb ? ca : cb, lo = ca > cb ? cb : ca;
             atomicAdd(&N.S[(size_t)hi * N.ldS + lo], va * Jval[b] * ((ca == cb && a != b) ? 2. : 1.));
         }
     }
+}
+
+// Gauss-Newton step of the INACTIVE shared unknowns: each is coupled only to its regularization
+// block (a spline knot's two surfaces: 2x2; anything else: 1x1), solved here in closed form.
+// One thread per shared unknown
+__global__ void inactive_step_kernel(DevProblem P, NormalBuffers N, double lambda, const double* __restrict__ x,
+                                     const double* __restrict__ Jval, double* __restrict__ step_full)
+{
+    const int r = blockIdx.x * blockDim.x + threadIdx.x;
+    if(r >= N.n_r || N.cidx[r] >= 0) return;
+    const int c = N.state_index(r);
+    double step = 0.;
+    const int n_intr = P.Ncam_i * P.Nintr_state;
+    if(P.reg && c < n_intr)
+    {
+        const int cam = c / P.Nintr_state, k = c - cam * P.Nintr_state;
+        const int Ndist_rows = P.opt_dist ? P.Ncam_i * (P.Nintr - 4) : 0;
+        if(k >= P.Ncore_state)
+        {
+            const int j = k - P.Ncore_state;
+            if(N.splined)
+            {
+                // rows (radial, tangential) of this knot; entries [d/dx, d/dy] each (eval.cu)
+                const int knot = j >> 1, which = j & 1;
+                const int t0 = cam * (P.Nintr - 4) + 2 * knot;
+                const double* e0 = &Jval[(size_t)P.reg_j0 + 2 * (size_t)t0];
+                const double* e1 = e0 + 2;
+                const double x0 = x[P.m_reg0 + t0], x1 = x[P.m_reg0 + t0 + 1];
+                const double Hxx = e0[0] * e0[0] + e1[0] * e1[0] + lambda;
+                const double Hyy = e0[1] * e0[1] + e1[1] * e1[1] + lambda;
+                const double Hxy = e0[0] * e0[1] + e1[0] * e1[1];
+                const double gx = e0[0] * x0 + e1[0] * x1, gy = e0[1] * x0 + e1[1] * x1;
+                const double det = Hxx * Hyy - Hxy * Hxy;
+                if(det > 0.) step = which == 0 ? -(Hyy * gx - Hxy * gy) / det : -(Hxx * gy - Hxy * gx) / det;
+            }
+            else
+            {
+                const int t = cam * (P.Nintr - 4) + j;
+                const double e = Jval[(size_t)P.reg_j0 + t];
+                const double H = e * e + lambda;
+                if(H > 0.) step = -e * x[P.m_reg0 + t] / H;
+            }
+        }
+        else if(k >= 2)
+        {
+            const int t = Ndist_rows + 2 * cam + (k - 2);
+            const double e = Jval[(size_t)P.reg_j0 + (size_t)(N.splined ? 2 : 1) * Ndist_rows + 2 * cam + (k - 2)];
+            const double H = e * e + lambda;
+            if(H > 0.) step = -e * x[P.m_reg0 + t] / H;
+        }
+    }
+    step_full[c] = step;
 }
 
 // 6x6 (or 3x3) SPD inverse by Cholesky, in registers of one thread. Returns false if not PD
@@ -364,7 +493,7 @@ schur_groups_kernel(NormalBuffers N, double lambda)
         {
             double t = 0.;
             for(int p = 0; p < nelim; p++) t += B1[(size_t)p * N.cap + l] * s_h[p];
-            if(t != 0.) atomicAdd(&N.gs[c1[l]], -t);
+            if(t != 0.) atomicAdd(&N.gs[N.cidx[c1[l]]], -t);
         }
         for(int a2 = i0; a2 <= a1; a2++)
         {
@@ -380,7 +509,7 @@ schur_groups_kernel(NormalBuffers N, double lambda)
                 double v = 0.;
                 for(int p = 0; p < nelim; p++) v += C1[p * N.cap + a] * B2[(size_t)p * N.cap + b];
                 if(v == 0.) continue;
-                const int r = c1[a], c = c2[b];
+                const int r = N.cidx[c1[a]], c = N.cidx[c2[b]];
                 if(r > c)       atomicAdd(&N.S[(size_t)r * N.ldS + c], -v);
                 else if(r < c)  atomicAdd(&N.S[(size_t)c * N.ldS + r], -v);
                 else            atomicAdd(&N.S[(size_t)r * N.ldS + r], same ? -v : -2. * v);
@@ -426,37 +555,52 @@ __global__ void set_diagonal_kernel(double* S, int ld, int i0, int i1, double v,
     if(i < i1) { if(add) S[(size_t)i * ld + i] += v; else S[(size_t)i * ld + i] = v; }
 }
 
-bool normal_assemble(const DevProblem& dp, const NormalBuffers& N, const EvalBuffers& op, const int* d_rowptr,
+bool normal_assemble(const DevProblem& dp, NormalBuffers& N, const EvalBuffers& op, const int* d_rowptr,
                      double lambda, cudaStream_t s, int* nlaunch)
 {
     static bool configured = false;
-    // Gram matrix (+J'x) of the widest item that can occur, capped at kGramMax; wider items keep
-    // only their eliminated strip in shared memory
-    const int ntot_max = N.cap + 6;
-    const int ng = ntot_max < kGramMax ? ntot_max : kGramMax;
-    size_t gram_doubles = (size_t)ng * (ng + 1) / 2 + ng;
-    if(ntot_max > kGramMax && (size_t)7 * ntot_max > gram_doubles) gram_doubles = (size_t)7 * ntot_max;
-    const size_t smem_items = ((size_t)(dp.Nintr_state * sizeof(short) + 7) / 8 + gram_doubles + 16) * sizeof(double);
-    const size_t smem_schur = (size_t)6 * N.cap * sizeof(double);
     if(!configured)
     {
         MB200_CUDA_CHECK(cudaFuncSetAttribute(assemble_items_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
         MB200_CUDA_CHECK(cudaFuncSetAttribute(schur_groups_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
         configured = true;
     }
-    if(smem_items > 220 * 1024 || smem_schur > 100 * 1024)
+    const size_t lmap_bytes = ((size_t)dp.Nintr_state * sizeof(short) + 7) / 8 * 8;
+    const size_t ccol_bytes = ((size_t)N.cap * sizeof(int) + 7) / 8 * 8;
+    const size_t smem_schur = (size_t)6 * N.cap * sizeof(double);
+    if(lmap_bytes + ccol_bytes + (size_t)7 * (N.cap + 6) * sizeof(double) > 200 * 1024 || smem_schur > 100 * 1024)
     {
         set_error("lens model with %d intrinsics per camera is too large for the assembly kernels", dp.Nintr_state);
         return false;
     }
+    const int Nwi = dp.Nobs_board + dp.Nobs_point;
+
+    // ---- pass 1: who touches what; compact numbering of the coupled shared unknowns
+    MB200_CUDA_CHECK(cudaMemsetAsync(N.active, 0, (size_t)(N.n_r > 0 ? N.n_r : 1) * sizeof(int), s));
+    MB200_CUDA_CHECK(cudaMemsetAsync(N.stat, 0, 4 * sizeof(int), s));
+    if(Nwi > 0) { item_columns_kernel<<<Nwi, 256, lmap_bytes, s>>>(dp, N, op.Jcol); (*nlaunch)++; }
+    if(dp.reg_unity) { mark_reg_active_kernel<<<1, 32, 0, s>>>(dp, N); (*nlaunch)++; }
+    compact_scan_kernel<<<1, 1024, 0, s>>>(N);
+    (*nlaunch)++;
+    MB200_CUDA_CHECK(cudaMemcpyAsync(N.h_stat, N.stat, 2 * sizeof(int), cudaMemcpyDeviceToHost, s));
+    MB200_CUDA_CHECK(cudaStreamSynchronize(s));
+    N.n_c = N.h_stat[0];
+    N.ldS = chol_padded(N.n_c > 0 ? N.n_c : 1);
+    const int max_ntot = N.h_stat[1];
+
+    // ---- pass 2: Gram matrices -> S, g', B, D
+    const int gram_cap = max_ntot < kGramMax ? (max_ntot > 8 ? max_ntot : 8) : kGramMax;
+    size_t gram_doubles = (size_t)gram_cap * (gram_cap + 1) / 2 + gram_cap;
+    if(max_ntot > kGramMax && (size_t)7 * max_ntot > gram_doubles) gram_doubles = (size_t)7 * max_ntot;
+    const size_t smem_items = lmap_bytes + ccol_bytes + (gram_doubles + 2) * sizeof(double);
+
     MB200_CUDA_CHECK(cudaMemsetAsync(N.S, 0, (size_t)N.ldS * N.ldS * sizeof(double), s));
-    MB200_CUDA_CHECK(cudaMemsetAsync(N.gs, 0, (size_t)N.ldS * sizeof(double), s));
+    MB200_CUDA_CHECK(cudaMemsetAsync(N.gs, 0, (size_t)N.ldS_max * sizeof(double), s));
     MB200_CUDA_CHECK(cudaMemsetAsync(N.g_full, 0, (size_t)dp.Nstate * sizeof(double), s));
     MB200_CUDA_CHECK(cudaMemsetAsync(N.info, 0, sizeof(int), s));
-    const int Nwi = dp.Nobs_board + dp.Nobs_point;
     if(Nwi > 0)
     {
-        assemble_items_kernel<<<Nwi, 256, smem_items, s>>>(dp, N, op.x, op.Jval, op.Jcol);
+        assemble_items_kernel<<<Nwi, 256, smem_items, s>>>(dp, N, gram_cap, op.x, op.Jval, op.Jcol);
         (*nlaunch)++;
     }
     const int Nreg = dp.Nmeas - dp.m_reg0;
@@ -470,26 +614,61 @@ bool normal_assemble(const DevProblem& dp, const NormalBuffers& N, const EvalBuf
         schur_groups_kernel<<<N.Ngroups, 256, smem_schur, s>>>(N, lambda);
         (*nlaunch)++;
     }
-    // padding rows of the factorization; diagonal loading of the shared block
-    if(N.ldS > N.n_r)
+    // padding rows of the factorization; diagonal loading of the coupled block
+    if(N.ldS > N.n_c)
     {
-        set_diagonal_kernel<<<(N.ldS - N.n_r + 255) / 256, 256, 0, s>>>(N.S, N.ldS, N.n_r, N.ldS, 1., false);
+        set_diagonal_kernel<<<(N.ldS - N.n_c + 255) / 256, 256, 0, s>>>(N.S, N.ldS, N.n_c, N.ldS, 1., false);
         (*nlaunch)++;
     }
-    if(lambda > 0. && N.n_r > 0)
+    if(lambda > 0. && N.n_c > 0)
     {
-        set_diagonal_kernel<<<(N.n_r + 255) / 256, 256, 0, s>>>(N.S, N.ldS, 0, N.n_r, lambda, true);
+        set_diagonal_kernel<<<(N.n_c + 255) / 256, 256, 0, s>>>(N.S, N.ldS, 0, N.n_c, lambda, true);
         (*nlaunch)++;
     }
     MB200_CUDA_CHECK(cudaGetLastError());
     return true;
 }
 
-bool normal_backsubstitute(const NormalBuffers& N, const double* ds, double* step_full, int e0, cudaStream_t s, int* nlaunch)
+// rhs[c] = -g'[c] for the compact system; padding 0
+__global__ void compact_rhs_kernel(NormalBuffers N, double* __restrict__ rhs)
 {
-    if(N.Ngroups <= 0) return true;
-    backsub_groups_kernel<<<(N.Ngroups * 32 + 255) / 256, 256, 0, s>>>(N, ds, step_full, e0);
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if(c < N.ldS) rhs[c] = c < N.n_c ? -N.gs[c] : 0.;
+}
+// compact solution -> reduced-length vector (for the back-substitution) and the full-length step
+__global__ void scatter_compact_kernel(NormalBuffers N, const double* __restrict__ sol, double* __restrict__ ds_r,
+                                       double* __restrict__ step_full)
+{
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if(c >= N.n_c) return;
+    const int r = N.cinv[c];
+    ds_r[r] = sol[c];
+    step_full[N.state_index(r)] = sol[c];
+}
+
+bool normal_rhs(const NormalBuffers& N, double* rhs, cudaStream_t s, int* nlaunch)
+{
+    compact_rhs_kernel<<<(N.ldS + 255) / 256, 256, 0, s>>>(N, rhs);
     (*nlaunch)++;
+    MB200_CUDA_CHECK(cudaGetLastError());
+    return true;
+}
+
+// the full-length Gauss-Newton step from the compact solution `sol`
+bool normal_expand_step(const DevProblem& dp, const NormalBuffers& N, const EvalBuffers& op, double lambda,
+                        const double* sol, double* ds_r, double* step_full, cudaStream_t s, int* nlaunch)
+{
+    if(N.n_c > 0) { scatter_compact_kernel<<<(N.n_c + 255) / 256, 256, 0, s>>>(N, sol, ds_r, step_full); (*nlaunch)++; }
+    if(N.n_r > N.n_c)
+    {
+        inactive_step_kernel<<<(N.n_r + 255) / 256, 256, 0, s>>>(dp, N, lambda, op.x, op.Jval, step_full);
+        (*nlaunch)++;
+    }
+    if(N.Ngroups > 0)
+    {
+        backsub_groups_kernel<<<(N.Ngroups * 32 + 255) / 256, 256, 0, s>>>(N, ds_r, step_full, N.e0);
+        (*nlaunch)++;
+    }
     MB200_CUDA_CHECK(cudaGetLastError());
     return true;
 }

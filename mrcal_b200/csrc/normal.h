@@ -9,10 +9,19 @@ namespace mb200 {
 // non-fixed point: 3 unknowns) with the work items that see it.
 struct NormalBuffers
 {
-    double* S;        // [ldS][ldS] row-major, lower: reduced normal matrix (then its Cholesky factor)
-    int     ldS;      // n_r padded to a multiple of 64
+    double* S;        // [ldS][ldS] row-major, lower: reduced normal matrix over the ACTIVE shared unknowns
+                      // (compact numbering), then its Cholesky factor
+    int     ldS;      // n_c padded to a multiple of 64 (changes per assembly)
+    int     ldS_max;  // n_r padded: the allocation
     int     n_r;      // number of shared (non-eliminated) unknowns
-    double* gs;       // [ldS] reduced gradient g' (reduced numbering)
+    int     n_c;      // ... of which touched by some observation: the coupled ("active") ones
+    double* gs;       // [ldS_max] reduced gradient g' (compact numbering)
+    int*    active;   // [n_r] flag
+    int*    cidx;     // [n_r] reduced -> compact index, -1 if inactive
+    int*    cinv;     // [ldS_max] compact -> reduced index
+    int*    stat;     // device: [0] n_c, [1] widest item (local columns)
+    int*    h_stat;   // pinned host mirror of stat
+    bool    splined;
     double* g_full;   // [Nstate] J'x, state numbering
     int*    info;     // 0, or a code for the first non-PD block found
     int     e0, e1;   // eliminated state range [e0,e1)
@@ -34,10 +43,16 @@ struct NormalBuffers
     __host__ __device__ int state_index(int r) const { return r < e0 ? r : r + (e1 - e0); }
 };
 
-// S, g', g_full at the operating point `op` (needs its x and Jacobian). lambda: diagonal loading
-bool normal_assemble(const DevProblem& dp, const NormalBuffers& N, const EvalBuffers& op, const int* d_rowptr,
+// S, g', g_full at the operating point `op` (needs its x and Jacobian). lambda: diagonal loading.
+// Updates N.n_c / N.ldS (one small device->host read)
+bool normal_assemble(const DevProblem& dp, NormalBuffers& N, const EvalBuffers& op, const int* d_rowptr,
                      double lambda, cudaStream_t s, int* nlaunch);
-// eliminated part of the step from the reduced solution ds (reduced numbering)
-bool normal_backsubstitute(const NormalBuffers& N, const double* ds, double* step_full, int e0, cudaStream_t s, int* nlaunch);
+// rhs <- -g' (compact numbering, ldS entries)
+bool normal_rhs(const NormalBuffers& N, double* rhs, cudaStream_t s, int* nlaunch);
+// full-length Gauss-Newton step from the compact solution: active shared unknowns, inactive shared
+// unknowns (from their regularization blocks), eliminated unknowns (back-substitution).
+// ds_r: scratch, n_r doubles
+bool normal_expand_step(const DevProblem& dp, const NormalBuffers& N, const EvalBuffers& op, double lambda,
+                        const double* sol, double* ds_r, double* step_full, cudaStream_t s, int* nlaunch);
 
 }  // namespace mb200

@@ -27,7 +27,8 @@ struct SolverWorkspace
     DeviceArena arena;
     NormalBuffers N{};
     double* invL = nullptr;
-    double* rhs = nullptr;        // [ldS] reduced solution
+    double* rhs = nullptr;        // [ldS] compact solution
+    double* ds_r = nullptr;       // [n_r] the same in reduced numbering
     double* step_gn = nullptr;    // [Nstate]
     double* step = nullptr;       // [Nstate]
     double* scal = nullptr;       // [16] device scalars
@@ -144,7 +145,10 @@ static bool build_workspace(mrcal_b200_problem* P)
     N.e0 = elim ? (L.i_frame0 >= 0 ? L.i_frame0 : L.i_point0) : L.Nstate;
     N.e1 = elim ? N.e0 + (L.i_frame0 >= 0 ? 6 * L.d.Nframes : 0) + (L.i_point0 >= 0 ? 3 * L.Npoints_variable : 0) : L.Nstate;
     N.n_r = L.Nstate - (N.e1 - N.e0);
-    N.ldS = chol_padded(N.n_r > 0 ? N.n_r : 1);
+    N.ldS_max = chol_padded(N.n_r > 0 ? N.n_r : 1);
+    N.ldS = N.ldS_max;
+    N.n_c = N.n_r;
+    N.splined = L.splined;
     N.cap = L.Nintr_state + 8;
     N.Nframe_groups = (elim && L.i_frame0 >= 0) ? L.d.Nframes : 0;
     const int Npoint_groups = (elim && L.i_point0 >= 0) ? L.Npoints_variable : 0;
@@ -171,17 +175,19 @@ static bool build_workspace(mrcal_b200_problem* P)
         ptr[N.Ngroups] = (int)items.size();
     }
 
-    bool ok = A.alloc(&N.S, (size_t)N.ldS * N.ldS) && A.alloc(&N.gs, N.ldS, true) && A.alloc(&N.g_full, L.Nstate, true) &&
-              A.alloc(&N.info, 4, true) &&
+    bool ok = A.alloc(&N.S, (size_t)N.ldS_max * N.ldS_max) && A.alloc(&N.gs, N.ldS_max, true) && A.alloc(&N.g_full, L.Nstate, true) &&
+              A.alloc(&N.info, 4, true) && A.alloc(&N.active, N.n_r, true) && A.alloc(&N.cidx, N.n_r, true) &&
+              A.alloc(&N.cinv, N.ldS_max, true) && A.alloc(&N.stat, 4, true) && A.alloc(&ws->ds_r, N.n_r, true) &&
               A.alloc(&N.wi_nsh, Nwi, true) && A.alloc(&N.wi_cols, (size_t)Nwi * N.cap) &&
               A.alloc(&N.wi_B, (size_t)Nwi * 6 * N.cap) && A.alloc(&N.wi_D, (size_t)Nwi * 36) && A.alloc(&N.wi_gf, (size_t)Nwi * 6) &&
               A.alloc(&N.grp_ptr, (size_t)N.Ngroups + 1) && A.alloc(&N.grp_items, items.size()) &&
               A.alloc(&N.grp_Dinv, (size_t)N.Ngroups * 36) && A.alloc(&N.grp_gf, (size_t)N.Ngroups * 6) &&
-              A.alloc(&ws->invL, (size_t)N.ldS * kCholBlock) && A.alloc(&ws->rhs, N.ldS, true) &&
+              A.alloc(&ws->invL, (size_t)N.ldS_max * kCholBlock) && A.alloc(&ws->rhs, N.ldS_max, true) &&
               A.alloc(&ws->step_gn, L.Nstate, true) && A.alloc(&ws->step, L.Nstate, true) && A.alloc(&ws->scal, 16, true);
     if(!ok) return false;
     MB200_CUDA_CHECK(cudaMallocHost(&ws->h_scal, 16 * sizeof(double)));
-    MB200_CUDA_CHECK(cudaMallocHost(&ws->h_info, 4 * sizeof(int)));
+    MB200_CUDA_CHECK(cudaMallocHost(&ws->h_info, 8 * sizeof(int)));
+    N.h_stat = ws->h_info + 4;
     MB200_CUDA_CHECK(cudaMemcpyAsync(N.grp_ptr, ptr.data(), ptr.size() * sizeof(int), cudaMemcpyHostToDevice, P->stream));
     if(!items.empty())
         MB200_CUDA_CHECK(cudaMemcpyAsync(N.grp_items, items.data(), items.size() * sizeof(int), cudaMemcpyHostToDevice, P->stream));
@@ -297,7 +303,7 @@ static bool dogleg_pass(mrcal_b200_problem* P, const mrcal_b200_solver_parameter
         {
             // the one collective of the algorithm: reduced system + reduced rhs (+ the shared part of J'x)
             if(!comm_allreduce_sum(N.S, (size_t)N.ldS * N.ldS, s)) return false;
-            if(!comm_allreduce_sum(N.gs, (size_t)N.ldS, s)) return false;
+            if(!comm_allreduce_sum(N.gs, (size_t)N.ldS, s)) return false;   // TODO: the active set must be the union over ranks
         }
         T->spans[1].push_back({a, T->mark()});
         return true;
@@ -365,7 +371,7 @@ static bool dogleg_pass(mrcal_b200_problem* P, const mrcal_b200_solver_parameter
                     while(true)
                     {
                         const int a = T->mark();
-                        if(!chol_factor(N.S, N.ldS, N.n_r, ws->invL, N.info + 1, s, nl)) return false;
+                        if(!chol_factor(N.S, N.ldS, N.n_c, ws->invL, N.info + 1, s, nl)) return false;
                         MB200_CUDA_CHECK(cudaMemcpyAsync(ws->h_info, N.info, 2 * sizeof(int), cudaMemcpyDeviceToHost, s));
                         MB200_CUDA_CHECK(cudaStreamSynchronize(s));
                         T->spans[2].push_back({a, T->mark()});
@@ -378,11 +384,9 @@ static bool dogleg_pass(mrcal_b200_problem* P, const mrcal_b200_solver_parameter
                         if(!assemble(P->cur)) return false;
                     }
                     const int a = T->mark();
-                    negate_kernel<<<(N.ldS + 255) / 256, 256, 0, s>>>(N.n_r, N.ldS, N.gs, ws->rhs);
-                    (*nl)++;
-                    if(N.n_r > 0 && !chol_solve(N.S, N.ldS, ws->invL, ws->rhs, N.ldS, 1, s, nl)) return false;
-                    if(N.n_r > 0) { scatter_shared_kernel<<<(N.n_r + 255) / 256, 256, 0, s>>>(N, ws->rhs, ws->step_gn); (*nl)++; }
-                    if(!normal_backsubstitute(N, ws->rhs, ws->step_gn, N.e0, s, nl)) return false;
+                    if(!normal_rhs(N, ws->rhs, s, nl)) return false;
+                    if(N.n_c > 0 && !chol_solve(N.S, N.ldS, ws->invL, ws->rhs, N.ldS, 1, s, nl)) return false;
+                    if(!normal_expand_step(P->dp, N, P->op[P->cur], *lambda, ws->rhs, ws->ds_r, ws->step_gn, s, nl)) return false;
                     dots_kernel<<<1, 1024, 0, s>>>(ws->step_gn, N.g_full, 0, Nstate, ws->scal + 8);
                     (*nl)++;
                     T->spans[3].push_back({a, T->mark()});
@@ -465,7 +469,6 @@ bool solver_run(mrcal_b200_problem* P, const mrcal_b200_solver_parameters_t* par
     const Layout& L = P->L;
     cudaStream_t s = P->stream;
     const int launches0 = P->launches;
-    info.Nreduced = ws->N.n_r;
 
     // the CSR row pointers are analytic; jv_kernel and the regularization assembly read them
     if(!problem_evaluate(P, P->cur, false, true)) return false;
@@ -506,6 +509,7 @@ bool solver_run(mrcal_b200_problem* P, const mrcal_b200_solver_parameters_t* par
     info.ms_assemble = T.total(1);
     info.ms_factor = T.total(2);
     info.ms_solve = T.total(3);
+    info.Nreduced = ws->N.n_c;
     info.norm2_x_final = norm2;
     info.lambda_final = lambda;
     info.Nkernel_launches = P->launches - launches0;
@@ -546,14 +550,27 @@ extern "C" bool mrcal_b200_problem_reduced_system(mrcal_b200_problem_t* P, doubl
     if(S_out == nullptr && g_reduced == nullptr && g_full == nullptr) return true;
     if(!problem_evaluate(P, P->cur, true, true)) return false;
     if(!normal_assemble(P->dp, N, P->op[P->cur], P->d_rowptr, lambda, P->stream, &P->launches)) return false;
-    if(S_out && N.n_r > 0)
-        MB200_CUDA_CHECK(cudaMemcpy2DAsync(S_out, (size_t)N.n_r * sizeof(double), N.S, (size_t)N.ldS * sizeof(double),
-                                           (size_t)N.n_r * sizeof(double), N.n_r, cudaMemcpyDeviceToHost, P->stream));
-    if(g_reduced && N.n_r > 0)
-        MB200_CUDA_CHECK(cudaMemcpyAsync(g_reduced, N.gs, (size_t)N.n_r * sizeof(double), cudaMemcpyDeviceToHost, P->stream));
+    // the device holds the system over the active unknowns only; expand to reduced numbering here
+    // (inactive rows/columns come out as zero: they are not part of the coupled system)
+    std::vector<double> Sc((size_t)N.n_c * N.n_c), gc(N.n_c);
+    std::vector<int> cinv(N.n_c);
+    if(N.n_c > 0)
+    {
+        MB200_CUDA_CHECK(cudaMemcpy2DAsync(Sc.data(), (size_t)N.n_c * sizeof(double), N.S, (size_t)N.ldS * sizeof(double),
+                                           (size_t)N.n_c * sizeof(double), N.n_c, cudaMemcpyDeviceToHost, P->stream));
+        MB200_CUDA_CHECK(cudaMemcpyAsync(gc.data(), N.gs, (size_t)N.n_c * sizeof(double), cudaMemcpyDeviceToHost, P->stream));
+        MB200_CUDA_CHECK(cudaMemcpyAsync(cinv.data(), N.cinv, (size_t)N.n_c * sizeof(int), cudaMemcpyDeviceToHost, P->stream));
+    }
     if(g_full)
         MB200_CUDA_CHECK(cudaMemcpyAsync(g_full, N.g_full, (size_t)P->L.Nstate * sizeof(double), cudaMemcpyDeviceToHost, P->stream));
     MB200_CUDA_CHECK(cudaStreamSynchronize(P->stream));
+    if(S_out) memset(S_out, 0, (size_t)N.n_r * N.n_r * sizeof(double));
+    if(g_reduced) memset(g_reduced, 0, (size_t)N.n_r * sizeof(double));
+    for(int a = 0; a < N.n_c; a++)
+    {
+        if(g_reduced) g_reduced[cinv[a]] = gc[a];
+        if(S_out) for(int b = 0; b <= a; b++) S_out[(size_t)cinv[a] * N.n_r + cinv[b]] = Sc[(size_t)a * N.n_c + b];
+    }
     return true;
 }
 
