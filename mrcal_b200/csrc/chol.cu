@@ -21,6 +21,7 @@
 // mma.sync.m8n8k4.row.col.f64 wants for both operands of  C -= P P'.
 #include <cuda_runtime.h>
 #include <cstdint>
+#include <vector>
 
 #include "chol.h"
 #include "problem.h"
@@ -31,49 +32,41 @@ constexpr int NB = 64;     // inner block
 constexpr int NBO = 256;   // outer panel
 
 ////////////////////////////////////////////////////////////////////////////////
-// diagonal block: Cholesky + inverse of the factor. One CTA of 64 threads; thread i
-// keeps ROW i of the block in registers (all loops fully unrolled, so the row is a
-// register array), finished columns are published through shared memory.
-//   factor:  left-looking. column j: s_i = a_ij - sum_{k<j} l_ik l_jk ; l_jj = sqrt(s_j) ;
-//            l_ij = s_i / l_jj.  Two barriers per column, 2016 DFMA per thread.
-//   inverse: thread c computes column c of X = inv(L) by forward substitution; all
-//            threads run the same instruction stream (x_k = 0 for k < c), so the reads
-//            of L from shared memory are broadcasts.
+// diagonal block: Cholesky + inverse of the factor. One CTA of 256 threads = 64 rows x
+// 4 threads; the block lives in shared memory.
+//   factor:  left-looking. column j: s_i = a_ij - sum_{k<j} l_ik l_jk, the sum split over
+//            the row's 4 threads (k = part mod 4) and combined with two shuffles;
+//            l_jj = sqrt(s_j) ; l_ij = s_i / l_jj.  Two barriers per column.
+//   inverse: column c of X = inv(L) by forward substitution, again 4 threads per column.
+// Loops are NOT unrolled: the instruction stream of a fully unrolled 64x64 factorization
+// does not fit the instruction cache and runs slower than the arithmetic.
 ////////////////////////////////////////////////////////////////////////////////
-__global__ void __launch_bounds__(NB)
+__global__ void __launch_bounds__(256)
 potrf_diag_kernel(double* __restrict__ A, int ld, int k0, double* __restrict__ invL, int* __restrict__ info, int nreal)
 {
-    __shared__ double sL[NB][NB + 1];
+    extern __shared__ __align__(16) double dsm[];
+    double (*sL)[NB + 1] = reinterpret_cast<double (*)[NB + 1]>(dsm);
+    double (*sX)[NB + 1] = reinterpret_cast<double (*)[NB + 1]>(dsm + NB * (NB + 1));
     __shared__ double s_rinv[NB];
-    const int i = threadIdx.x;
-    for(int e = i; e < NB * NB; e += NB)
+    const int tid = threadIdx.x;
+    const int i = tid >> 2, part = tid & 3;
+    for(int e = tid; e < NB * NB; e += 256)
     {
         const int r = e / NB, c = e % NB;
         sL[r][c] = c <= r ? A[(size_t)(k0 + r) * ld + k0 + c] : 0.;
     }
     __syncthreads();
-    double row[NB];
-#pragma unroll
-    for(int k = 0; k < NB; k++) row[k] = sL[i][k];
-    __syncthreads();
-
-#pragma unroll
     for(int j = 0; j < NB; j++)
     {
-        double s0 = row[j], s1 = 0., s2 = 0., s3 = 0.;
-#pragma unroll
-        for(int k = 0; k < j; k++)
+        double s = 0.;
+#pragma unroll 4
+        for(int k = part; k < j; k += 4) s += sL[i][k] * sL[j][k];
+        s += __shfl_xor_sync(0xffffffffu, s, 1);
+        s += __shfl_xor_sync(0xffffffffu, s, 2);
+        const double sij = sL[i][j] - s;
+        if(i == j && part == 0)
         {
-            const double l = sL[j][k];
-            if((k & 3) == 0) s0 -= row[k] * l;
-            else if((k & 3) == 1) s1 -= row[k] * l;
-            else if((k & 3) == 2) s2 -= row[k] * l;
-            else s3 -= row[k] * l;
-        }
-        const double sj = (s0 + s1) + (s2 + s3);
-        if(i == j)
-        {
-            double d = sj;
+            double d = sij;
             if(!(d > 0.))
             {
                 // not positive definite. Remember the first failing pivot; carry on with a
@@ -82,47 +75,34 @@ potrf_diag_kernel(double* __restrict__ A, int ld, int k0, double* __restrict__ i
                 d = 1.;
             }
             const double l = sqrt(d);
-            row[j] = l;
             sL[j][j] = l;
             s_rinv[j] = 1. / l;
         }
         __syncthreads();
-        if(i > j)
-        {
-            row[j] = sj * s_rinv[j];
-            sL[i][j] = row[j];
-        }
+        if(i > j && part == 0) sL[i][j] = sij * s_rinv[j];
         __syncthreads();
     }
-    // L back to global (lower triangle), coalesced
-    for(int e = i; e < NB * NB; e += NB)
+    for(int e = tid; e < NB * NB; e += 256)
     {
         const int r = e / NB, c = e % NB;
         if(c <= r) A[(size_t)(k0 + r) * ld + k0 + c] = sL[r][c];
     }
-    // column i of inv(L)
-    double xc[NB];
-#pragma unroll
-    for(int r = 0; r < NB; r++)
+    // column c = i of inv(L); its 4 threads sit in one warp
     {
-        double a0 = 0., a1 = 0., a2 = 0., a3 = 0.;
-#pragma unroll
-        for(int k = 0; k < r; k++)
+        const int c = i;
+        for(int r = 0; r < NB; r++)
         {
-            const double l = sL[r][k];
-            if((k & 3) == 0) a0 += l * xc[k];
-            else if((k & 3) == 1) a1 += l * xc[k];
-            else if((k & 3) == 2) a2 += l * xc[k];
-            else a3 += l * xc[k];
+            double acc = 0.;
+#pragma unroll 4
+            for(int k = c + part; k < r; k += 4) acc += sL[r][k] * sX[k][c];
+            acc += __shfl_xor_sync(0xffffffffu, acc, 1);
+            acc += __shfl_xor_sync(0xffffffffu, acc, 2);
+            if(part == 0) sX[r][c] = r < c ? 0. : ((r == c ? 1. : 0.) - acc) * s_rinv[r];
+            __syncwarp();
         }
-        const double acc = (a0 + a1) + (a2 + a3);
-        xc[r] = ((r == i ? 1. : 0.) - acc) * s_rinv[r];
     }
     __syncthreads();
-#pragma unroll
-    for(int r = 0; r < NB; r++) sL[r][i] = xc[r];
-    __syncthreads();
-    for(int e = i; e < NB * NB; e += NB) invL[e] = sL[e / NB][e % NB];
+    for(int e = tid; e < NB * NB; e += 256) invL[e] = sX[e / NB][e % NB];
 }
 
 ////////////////////////////////////////////////////////////////////////////////
@@ -289,6 +269,7 @@ static bool configure_kernels()
     if(configured) return true;
     MB200_CUDA_CHECK(cudaFuncSetAttribute(syrk_dmma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSyrkSmem));
     MB200_CUDA_CHECK(cudaFuncSetAttribute(trsm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kBlockSmem));
+    MB200_CUDA_CHECK(cudaFuncSetAttribute(potrf_diag_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kBlockSmem));
     configured = true;
     return true;
 }
@@ -302,7 +283,77 @@ static bool syrk_update(double* A, int ld, int n, int c0, int c1, int k0, int k1
     return true;
 }
 
+static bool chol_factor_enqueue(double* A, int npad, int nreal, double* invL, int* d_info, cudaStream_t s, int* nlaunch, int kinds = 7);
+static bool chol_solve_enqueue(const double* L, int npad, const double* invL, double* B, int ldb, int nrhs, cudaStream_t s, int* nlaunch);
+
+// The factorization is ~3 short kernels per 64-column block, all with launch-time-constant
+// arguments: replaying a captured CUDA graph takes the host out of the loop (the host would
+// otherwise bound the rate at which the chain of tiny kernels is issued).
+struct GraphKey { const void* a; const void* b; int npad, nreal, kind; };
+struct GraphEntry { GraphKey key; cudaGraphExec_t exec; int launches; unsigned long stamp; };
+static std::vector<GraphEntry> g_graphs;
+static unsigned long g_stamp = 0;
+
+template <typename F>
+static bool run_graphed(const GraphKey& key, cudaStream_t s, int* nlaunch, F enqueue)
+{
+    for(auto& e : g_graphs)
+        if(e.key.a == key.a && e.key.b == key.b && e.key.npad == key.npad && e.key.nreal == key.nreal && e.key.kind == key.kind)
+        {
+            e.stamp = ++g_stamp;
+            MB200_CUDA_CHECK(cudaGraphLaunch(e.exec, s));
+            if(nlaunch) *nlaunch += e.launches;
+            return true;
+        }
+    int n = 0;
+    cudaGraph_t graph = nullptr;
+    MB200_CUDA_CHECK(cudaStreamBeginCapture(s, cudaStreamCaptureModeThreadLocal));
+    const bool ok = enqueue(&n);
+    cudaError_t e1 = cudaStreamEndCapture(s, &graph);
+    if(!ok || e1 != cudaSuccess || graph == nullptr)
+    {
+        if(graph) cudaGraphDestroy(graph);
+        set_error("CUDA graph capture of the factorization failed: %s", cudaGetErrorString(e1));
+        return false;
+    }
+    GraphEntry ent{key, nullptr, n, ++g_stamp};
+    MB200_CUDA_CHECK(cudaGraphInstantiate(&ent.exec, graph, 0));
+    cudaGraphDestroy(graph);
+    if(g_graphs.size() >= 16)
+    {
+        size_t old = 0;
+        for(size_t i = 1; i < g_graphs.size(); i++) if(g_graphs[i].stamp < g_graphs[old].stamp) old = i;
+        cudaGraphExecDestroy(g_graphs[old].exec);
+        g_graphs.erase(g_graphs.begin() + old);
+    }
+    g_graphs.push_back(ent);
+    MB200_CUDA_CHECK(cudaGraphLaunch(ent.exec, s));
+    if(nlaunch) *nlaunch += n;
+    return true;
+}
+
+void chol_forget_graphs(const void* A)
+{
+    for(size_t i = 0; i < g_graphs.size();)
+        if(g_graphs[i].key.a == A || g_graphs[i].key.b == A) { cudaGraphExecDestroy(g_graphs[i].exec); g_graphs.erase(g_graphs.begin() + i); }
+        else i++;
+}
+
 bool chol_factor(double* A, int npad, int nreal, double* invL, int* d_info, cudaStream_t s, int* nlaunch)
+{
+    if(!configure_kernels()) return false;
+    return run_graphed(GraphKey{A, d_info, npad, nreal, 0}, s, nlaunch,
+                       [&](int* n) { return chol_factor_enqueue(A, npad, nreal, invL, d_info, s, n); });
+}
+
+bool chol_solve(const double* L, int npad, const double* invL, double* B, int ldb, int nrhs, cudaStream_t s, int* nlaunch)
+{
+    if(nrhs != 1) return chol_solve_enqueue(L, npad, invL, B, ldb, nrhs, s, nlaunch);
+    return run_graphed(GraphKey{L, B, npad, ldb, 1}, s, nlaunch,
+                       [&](int* n) { return chol_solve_enqueue(L, npad, invL, B, ldb, 1, s, n); });
+}
+
+static bool chol_factor_enqueue(double* A, int npad, int nreal, double* invL, int* d_info, cudaStream_t s, int* nlaunch, int kinds)
 {
     if(!configure_kernels()) return false;
     MB200_CUDA_CHECK(cudaMemsetAsync(d_info, 0, sizeof(int), s));
@@ -311,19 +362,25 @@ bool chol_factor(double* A, int npad, int nreal, double* invL, int* d_info, cuda
         const int K1 = K0 + NBO < npad ? K0 + NBO : npad;
         for(int k0 = K0; k0 < K1; k0 += NB)
         {
-            potrf_diag_kernel<<<1, NB, 0, s>>>(A, npad, k0, invL + (size_t)(k0 / NB) * NB * NB, d_info, nreal);
-            if(nlaunch) (*nlaunch)++;
+            if(kinds & 1)
+            {
+                potrf_diag_kernel<<<1, 256, kBlockSmem, s>>>(A, npad, k0, invL + (size_t)(k0 / NB) * NB * NB, d_info, nreal);
+                if(nlaunch) (*nlaunch)++;
+            }
             const int nrows_below = npad - (k0 + NB);
             if(nrows_below > 0)
             {
-                trsm_kernel<<<nrows_below / NB, 256, kBlockSmem, s>>>(A, npad, k0, invL + (size_t)(k0 / NB) * NB * NB, npad);
-                if(nlaunch) (*nlaunch)++;
+                if(kinds & 2)
+                {
+                    trsm_kernel<<<nrows_below / NB, 256, kBlockSmem, s>>>(A, npad, k0, invL + (size_t)(k0 / NB) * NB * NB, npad);
+                    if(nlaunch) (*nlaunch)++;
+                }
                 // rest of this outer panel only
-                if(!syrk_update(A, npad, npad, k0 + NB, K1, k0, k0 + NB, s, nlaunch)) return false;
+                if((kinds & 4) && !syrk_update(A, npad, npad, k0 + NB, K1, k0, k0 + NB, s, nlaunch)) return false;
             }
         }
         // the whole trailing matrix, K = width of the panel
-        if(!syrk_update(A, npad, npad, K1, npad, K0, K1, s, nlaunch)) return false;
+        if((kinds & 8 || kinds == 7) && !syrk_update(A, npad, npad, K1, npad, K0, K1, s, nlaunch)) return false;
     }
     MB200_CUDA_CHECK(cudaGetLastError());
     return true;
@@ -386,7 +443,7 @@ solve_update_bwd_kernel(const double* __restrict__ L, int ld, double* __restrict
     }
 }
 
-bool chol_solve(const double* L, int npad, const double* invL, double* B, int ldb, int nrhs, cudaStream_t s, int* nlaunch)
+static bool chol_solve_enqueue(const double* L, int npad, const double* invL, double* B, int ldb, int nrhs, cudaStream_t s, int* nlaunch)
 {
     const int nblk = npad / NB;
     for(int k = 0; k < nblk; k++)
@@ -414,6 +471,54 @@ bool chol_solve(const double* L, int npad, const double* invL, double* B, int ld
     }
     MB200_CUDA_CHECK(cudaGetLastError());
     return true;
+}
+
+__global__ void debug_fill_spd_kernel(double* A, int n)
+{
+    const size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if(e >= (size_t)n * n) return;
+    const int i = (int)(e / n), j = (int)(e % n);
+    A[e] = i == j ? (double)n : 1. / (1. + (double)((i * 31 + j * 17) % 97));
+}
+
+// Timing aid (not on any product path): device time of `reps` factorizations of an n x n matrix,
+// restricted to the kernel kinds in the mask (1 potrf_diag, 2 trsm, 4 panel syrk, 8 trailing syrk;
+// 15 = everything), launched directly (graph=0) or as a captured graph (graph=1)
+double chol_debug_time(int n, int reps, int kinds, int graph)
+{
+    const int npad = chol_padded(n);
+    double *A, *invL; int* info;
+    if(cudaMalloc(&A, (size_t)npad * npad * sizeof(double)) != cudaSuccess) return -1.;
+    cudaMalloc(&invL, (size_t)npad * NB * sizeof(double));
+    cudaMalloc(&info, sizeof(int));
+    cudaStream_t s; cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking);
+    configure_kernels();
+    debug_fill_spd_kernel<<<(unsigned)(((size_t)npad * npad + 255) / 256), 256, 0, s>>>(A, npad);
+    cudaGraphExec_t exec = nullptr;
+    if(graph)
+    {
+        cudaGraph_t g;
+        cudaStreamBeginCapture(s, cudaStreamCaptureModeThreadLocal);
+        chol_factor_enqueue(A, npad, n, invL, info, s, nullptr, kinds == 15 ? 7 : kinds);
+        cudaStreamEndCapture(s, &g);
+        cudaGraphInstantiate(&exec, g, 0);
+        cudaGraphDestroy(g);
+    }
+    cudaEvent_t e0, e1; cudaEventCreate(&e0); cudaEventCreate(&e1);
+    for(int r = -1; r < reps; r++)
+    {
+        if(r == 0) cudaEventRecord(e0, s);
+        if(graph) cudaGraphLaunch(exec, s);
+        else      chol_factor_enqueue(A, npad, n, invL, info, s, nullptr, kinds == 15 ? 7 : kinds);
+    }
+    cudaEventRecord(e1, s);
+    cudaEventSynchronize(e1);
+    float ms = 0.f; cudaEventElapsedTime(&ms, e0, e1);
+    if(exec) cudaGraphExecDestroy(exec);
+    cudaEventDestroy(e0); cudaEventDestroy(e1);
+    cudaStreamDestroy(s);
+    cudaFree(A); cudaFree(invL); cudaFree(info);
+    return ms / reps;
 }
 
 // min/max of the diagonal of L (for rcond)

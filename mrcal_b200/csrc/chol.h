@@ -16,6 +16,11 @@ bool chol_factor(double* A, int npad, int nreal, double* invL, int* d_info, cuda
 // Solve L L' X = B in place for nrhs right-hand sides stored as rows B[r][0..npad)
 bool chol_solve(const double* L, int npad, const double* invL, double* B, int ldb, int nrhs, cudaStream_t s, int* nlaunch);
 
+// drop cached CUDA graphs that reference this buffer (call before freeing it)
+void chol_forget_graphs(const void* A);
+
+double chol_debug_time(int n, int reps, int kinds, int graph);
+
 // d_out2[0] = min, d_out2[1] = max of diag(L)[0..nreal)
 bool chol_diag_minmax(const double* L, int npad, int nreal, double* d_out2, cudaStream_t s);
 

@@ -102,6 +102,7 @@ extern "C" void mrcal_b200_factorization_destroy(mrcal_b200_factorization_t* F)
 {
     if(F == nullptr) return;
     if(F->stream) { cudaStreamSynchronize(F->stream); }
+    chol_forget_graphs(F->H);
     F->arena.release();
     if(F->stream) cudaStreamDestroy(F->stream);
     delete F;
@@ -134,4 +135,10 @@ extern "C" double mrcal_b200_factorization_rcond(mrcal_b200_factorization_t* F)
     if(!(mm[1] > 0.)) return 0.;
     const double r = mm[0] / mm[1];
     return r * r;
+}
+
+// Timing aid for kernel development (scripts/time_cholesky.py); not declared in the public header
+extern "C" double mrcal_b200_debug_time_cholesky(int n, int reps, int kinds, int graph)
+{
+    return chol_debug_time(n, reps, kinds, graph);
 }

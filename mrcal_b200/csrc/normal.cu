@@ -29,7 +29,8 @@ namespace mb200 {
 // directly (inactive_step_kernel). The reference gets the same saving from CHOLMOD's sparse
 // factorization.
 constexpr int kMaxRowNnz = 40;     // widest row: 16 intrinsics + 6 + 6 + 2 (any model here <= 30)
-constexpr int kGramMax   = 216;    // largest local column count whose Gram matrix lives in shared memory
+constexpr int kGramMax   = 200;
+constexpr int RCH        = 16;     // rows staged per chunk in assemble_items_kernel (RCH*kMaxRowNnz <= 3*256)    // largest local column count whose Gram matrix lives in shared memory
 
 struct ItemDesc
 {
@@ -179,9 +180,9 @@ assemble_items_kernel(DevProblem P, NormalBuffers N, int gram_cap, const double*
                       const double* __restrict__ Jval, const int* __restrict__ Jcol)
 {
     extern __shared__ __align__(16) double dsm[];
-    __shared__ short s_lidx[2][kMaxRowNnz];
-    __shared__ double s_val[2][kMaxRowNnz];
-    __shared__ double s_xr[2];
+    __shared__ short s_lidx[2][RCH][kMaxRowNnz];
+    __shared__ double s_val[2][RCH][kMaxRowNnz];
+    __shared__ double s_xr[2][RCH];
     __shared__ unsigned char s_pa[kMaxRowNnz * (kMaxRowNnz + 1) / 2], s_pb[kMaxRowNnz * (kMaxRowNnz + 1) / 2];
 
     const int w = blockIdx.x, tid = threadIdx.x;
@@ -220,45 +221,78 @@ assemble_items_kernel(DevProblem P, NormalBuffers N, int gram_cap, const double*
     }
     __syncthreads();
 
+    // Rows are consumed in chunks of RCH: while one chunk is being accumulated, the (column, value)
+    // pairs of the next are already in flight from global memory into registers, so the per-row
+    // critical path has no global-memory latency in it
     const int npairs = d.nnz_row * (d.nnz_row + 1) / 2;
-    for(int r = 0; r < d.rows; r++)
+    const int per_chunk = RCH * d.nnz_row;
+    const int nchunks = (d.rows + RCH - 1) / RCH;
+    int    pf_col[3];
+    double pf_val[3];
+    auto prefetch = [&](int chunk)
     {
-        const int buf = r & 1;
-        if(tid < d.nnz_row)
+#pragma unroll
+        for(int q = 0; q < 3; q++)
         {
-            const size_t j = (size_t)d.j0 + (size_t)r * d.nnz_row + tid;
-            const int k = tid;
+            const int e = tid + q * 256;
+            const int rr = e / d.nnz_row, k = e - rr * d.nnz_row;
+            const int r = chunk * RCH + rr;
+            pf_col[q] = 0; pf_val[q] = 0.;
+            if(e < per_chunk && r < d.rows)
+            {
+                const size_t j = (size_t)d.j0 + (size_t)r * d.nnz_row + k;
+                if(k < d.nI) pf_col[q] = Jcol[j];
+                pf_val[q] = Jval[j];
+            }
+        }
+    };
+    auto commit = [&](int chunk, int buf)
+    {
+#pragma unroll
+        for(int q = 0; q < 3; q++)
+        {
+            const int e = tid + q * 256;
+            if(e >= per_chunk) continue;
+            const int rr = e / d.nnz_row, k = e - rr * d.nnz_row;
             int l;
-            if(k < d.nI)                          l = lmap[Jcol[j] - d.cbase];
+            if(k < d.nI)                          l = chunk * RCH + rr < d.rows ? lmap[pf_col[q] - d.cbase] : 0;
             else if(k < d.nI + ncam)              l = nloc + (k - d.nI);
             else if(k < d.nI + ncam + d.nelim)    l = nsh + (k - d.nI - ncam);
             else                                  l = nloc + ncam + (k - d.nI - ncam - d.nelim);
-            s_lidx[buf][k] = (short)l;
-            s_val[buf][k] = Jval[j];
+            s_lidx[buf][rr][k] = (short)l;
+            s_val[buf][rr][k] = pf_val[q];
         }
-        if(tid == 32) s_xr[buf] = x[d.m0 + r];
-        __syncthreads();   // the only barrier per row: the staging buffers alternate
-        for(int e = tid; e < npairs; e += 256)
+        if(tid < RCH) s_xr[buf][tid] = chunk * RCH + tid < d.rows ? x[d.m0 + chunk * RCH + tid] : 0.;
+    };
+    prefetch(0);
+    for(int c = 0; c < nchunks; c++)
+    {
+        const int buf = c & 1;
+        commit(c, buf);
+        __syncthreads();
+        if(c + 1 < nchunks) prefetch(c + 1);
+        const int nrows_here = min(RCH, d.rows - c * RCH);
+        for(int rr = 0; rr < nrows_here; rr++)
         {
-            const int a = s_pa[e], b = s_pb[e];
-            const double v = s_val[buf][a] * s_val[buf][b];
-            if(v == 0.) continue;
-            int la = s_lidx[buf][a], lb = s_lidx[buf][b];
-            if(la < lb) { const int t = la; la = lb; lb = t; }
-            if(!big) gram[tri(la, lb)] += v;
-            else if(la >= nsh) gram[(la - nsh) * ntot + lb] += v;            // eliminated x anything
-            else atomicAdd(&N.S[(size_t)ccol[la] * N.ldS + ccol[lb]], v);      // shared x shared
+            const short*  lidx = s_lidx[buf][rr];
+            const double* val  = s_val[buf][rr];
+            for(int e = tid; e < npairs; e += 256)
+            {
+                const int a = s_pa[e], b = s_pb[e];
+                const double v = val[a] * val[b];
+                if(v == 0.) continue;
+                int la = lidx[a], lb = lidx[b];
+                if(la < lb) { const int t = la; la = lb; lb = t; }
+                if(!big) gram[tri(la, lb)] += v;
+                else if(la >= nsh) gram[(la - nsh) * ntot + lb] += v;            // eliminated x anything
+                else atomicAdd(&N.S[(size_t)ccol[la] * N.ldS + ccol[lb]], v);      // shared x shared
+            }
+            if(tid >= 224 && tid < 224 + d.nnz_row) gvec[lidx[tid - 224]] += val[tid - 224] * s_xr[buf][rr];
+            // two different rows can hit the same Gram entry from different threads: one barrier per row.
+            // (Within a row, distinct (a,b) hit distinct entries.)
+            __syncthreads();
         }
-        if(tid >= 64 && tid < 64 + d.nnz_row)
-        {
-            const int k = tid - 64;
-            gvec[s_lidx[buf][k]] += s_val[buf][k] * s_xr[buf];
-        }
-        // No second barrier: the next row stages into the OTHER buffer, and nobody can pass that
-        // row's barrier (hence touch gram again, or restage this buffer) before everybody has
-        // finished this row. Within one row, distinct (a,b) hit distinct gram entries.
     }
-    __syncthreads();
 
     // ---- write out
     // shared x shared -> S (lower triangle, compact numbering; local order == global order)
@@ -561,7 +595,7 @@ bool normal_assemble(const DevProblem& dp, NormalBuffers& N, const EvalBuffers& 
     static bool configured = false;
     if(!configured)
     {
-        MB200_CUDA_CHECK(cudaFuncSetAttribute(assemble_items_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
+        MB200_CUDA_CHECK(cudaFuncSetAttribute(assemble_items_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
         MB200_CUDA_CHECK(cudaFuncSetAttribute(schur_groups_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
         configured = true;
     }

@@ -37,6 +37,7 @@ struct SolverWorkspace
     std::vector<cudaEvent_t> ev;
     ~SolverWorkspace()
     {
+        chol_forget_graphs(N.S);
         if(h_scal) cudaFreeHost(h_scal);
         if(h_info) cudaFreeHost(h_info);
         for(auto e : ev) cudaEventDestroy(e);
@@ -338,7 +339,7 @@ static bool dogleg_pass(mrcal_b200_problem* P, const mrcal_b200_solver_parameter
             {
                 MB200_CUDA_CHECK(cudaMemsetAsync(ws->scal, 0, 16 * sizeof(double), s));
                 dots_kernel<<<1, 1024, 0, s>>>(N.g_full, nullptr, 0, Nstate, ws->scal + 0);
-                jv_kernel<<<592, 256, 0, s>>>(P->d_rowptr, cur.Jcol, cur.Jval, N.g_full, cur.x, Nmeas, ws->scal + 4);
+                jv_kernel<<<148 * 16, 256, 0, s>>>(P->d_rowptr, cur.Jcol, cur.Jval, N.g_full, cur.x, Nmeas, ws->scal + 4);
                 *nl += 2;
                 if(!read_scalars(P, 8)) return false;
                 g2 = ws->h_scal[0];
@@ -427,7 +428,7 @@ static bool dogleg_pass(mrcal_b200_problem* P, const mrcal_b200_solver_parameter
                 break;
             }
             MB200_CUDA_CHECK(cudaMemsetAsync(ws->scal + 12, 0, 2 * sizeof(double), s));
-            jv_kernel<<<592, 256, 0, s>>>(P->d_rowptr, cur.Jcol, cur.Jval, ws->step, cur.x, Nmeas, ws->scal + 12);
+            jv_kernel<<<148 * 16, 256, 0, s>>>(P->d_rowptr, cur.Jcol, cur.Jval, ws->step, cur.x, Nmeas, ws->scal + 12);
             (*nl)++;
             if(!evaluate(1 - P->cur)) return false;
             MB200_CUDA_CHECK(cudaMemcpyAsync(ws->h_scal + 12, ws->scal + 12, 2 * sizeof(double), cudaMemcpyDeviceToHost, s));
