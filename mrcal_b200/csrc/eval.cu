@@ -531,7 +531,7 @@ eval_regularization_kernel(DevProblem P, bool splined, double* __restrict__ x, d
         }
     }
     const double s = block_sum(err * err, red);
-    if(threadIdx.x == 0 && s != 0.) atomicAdd(norm2, s);
+    if(threadIdx.x == 0 && s != 0. && P.reg_owner) atomicAdd(norm2, s);
 }
 
 // CSR row pointers. Analytic: every row of an observation has the same width

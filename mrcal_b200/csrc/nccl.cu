@@ -75,6 +75,18 @@ bool comm_allreduce_sum(double* d_buf, size_t count, cudaStream_t s)
     return true;
 }
 
+bool comm_allreduce_max_int(int* d_buf, size_t count, cudaStream_t s)
+{
+    if(!comm_active()) return true;
+    const int rc = g_nccl.AllReduce(d_buf, d_buf, count, /*ncclInt32*/ 2, /*ncclMax*/ 2, g_nccl.comm, s);
+    if(rc != 0)
+    {
+        set_error("ncclAllReduce(max) failed: %s", g_nccl.GetErrorString ? g_nccl.GetErrorString(rc) : "?");
+        return false;
+    }
+    return true;
+}
+
 }  // namespace mb200
 using namespace mb200;
 
@@ -118,6 +130,7 @@ extern "C" bool mrcal_b200_problem_set_sharding(mrcal_b200_problem_t* P, int fra
                                                 int point_offset, int Npoints_global)
 {
     P->sharded = true;
+    P->dp.reg_owner = comm_rank() == 0;
     P->frame_offset = frame_offset; P->Nframes_global = Nframes_global;
     P->point_offset = point_offset; P->Npoints_global = Npoints_global;
     return true;

@@ -21,6 +21,10 @@
 
 namespace mb200 {
 
+bool comm_active();
+bool comm_allreduce_sum(double* d_buf, size_t count, cudaStream_t s);
+bool comm_allreduce_max_int(int* d_buf, size_t count, cudaStream_t s);
+
 // COMPACTION. Only the shared unknowns that some observation row touches are coupled to anything.
 // For the wide splined models most knots are never hit by a board corner and appear only in their
 // own 2x2 regularization block (at BASELINE config 3: 1266 of 4820 shared unknowns are coupled), so
@@ -344,7 +348,7 @@ __global__ void assemble_reg_kernel(DevProblem P, NormalBuffers N, const double*
                                     const int* __restrict__ rowptr)
 {
     const int m = P.m_reg0 + blockIdx.x * blockDim.x + threadIdx.x;
-    if(m >= P.Nmeas) return;
+    if(m >= P.Nmeas || !P.reg_owner) return;
     const int j0 = rowptr[m], j1 = rowptr[m + 1];
     const double xm = x[m];
     bool all_active = true;
@@ -589,6 +593,18 @@ __global__ void set_diagonal_kernel(double* S, int ld, int i0, int i1, double v,
     if(i < i1) { if(add) S[(size_t)i * ld + i] += v; else S[(size_t)i * ld + i] = v; }
 }
 
+// shared part of J'x <-> a contiguous buffer in reduced numbering (for the cross-rank reduction)
+__global__ void gather_shared_kernel(NormalBuffers N, double* __restrict__ buf)
+{
+    const int r = blockIdx.x * blockDim.x + threadIdx.x;
+    if(r < N.n_r) buf[r] = N.g_full[N.state_index(r)];
+}
+__global__ void scatter_shared_kernel(NormalBuffers N, const double* __restrict__ buf)
+{
+    const int r = blockIdx.x * blockDim.x + threadIdx.x;
+    if(r < N.n_r) N.g_full[N.state_index(r)] = buf[r];
+}
+
 bool normal_assemble(const DevProblem& dp, NormalBuffers& N, const EvalBuffers& op, const int* d_rowptr,
                      double lambda, cudaStream_t s, int* nlaunch)
 {
@@ -614,6 +630,8 @@ bool normal_assemble(const DevProblem& dp, NormalBuffers& N, const EvalBuffers& 
     MB200_CUDA_CHECK(cudaMemsetAsync(N.stat, 0, 4 * sizeof(int), s));
     if(Nwi > 0) { item_columns_kernel<<<Nwi, 256, lmap_bytes, s>>>(dp, N, op.Jcol); (*nlaunch)++; }
     if(dp.reg_unity) { mark_reg_active_kernel<<<1, 32, 0, s>>>(dp, N); (*nlaunch)++; }
+    // sharded solve: every rank must number the union of the active sets identically
+    if(comm_active() && N.n_r > 0 && !comm_allreduce_max_int(N.active, (size_t)N.n_r, s)) return false;
     compact_scan_kernel<<<1, 1024, 0, s>>>(N);
     (*nlaunch)++;
     MB200_CUDA_CHECK(cudaMemcpyAsync(N.h_stat, N.stat, 2 * sizeof(int), cudaMemcpyDeviceToHost, s));
@@ -646,6 +664,17 @@ bool normal_assemble(const DevProblem& dp, NormalBuffers& N, const EvalBuffers& 
     if(N.Ngroups > 0)
     {
         schur_groups_kernel<<<N.Ngroups, 256, smem_schur, s>>>(N, lambda);
+        (*nlaunch)++;
+    }
+    if(comm_active())
+    {
+        // THE collective of the algorithm: the reduced normal equations, summed over the frame shards.
+        // g' and the shared part of J'x ride along (gather -> reduce -> scatter)
+        gather_shared_kernel<<<(N.n_r + 255) / 256, 256, 0, s>>>(N, N.gsh);
+        (*nlaunch)++;
+        if(!comm_allreduce_sum(N.S, (size_t)N.ldS * N.ldS, s)) return false;
+        if(!comm_allreduce_sum(N.gs, (size_t)2 * N.ldS_max, s)) return false;   // gs and gsh are contiguous
+        scatter_shared_kernel<<<(N.n_r + 255) / 256, 256, 0, s>>>(N, N.gsh);
         (*nlaunch)++;
     }
     // padding rows of the factorization; diagonal loading of the coupled block

@@ -16,6 +16,7 @@ struct NormalBuffers
     int     n_r;      // number of shared (non-eliminated) unknowns
     int     n_c;      // ... of which touched by some observation: the coupled ("active") ones
     double* gs;       // [ldS_max] reduced gradient g' (compact numbering)
+    double* gsh;      // [ldS_max] staging for the shared part of J'x (reduced numbering); follows gs in memory
     int*    active;   // [n_r] flag
     int*    cidx;     // [n_r] reduced -> compact index, -1 if inactive
     int*    cinv;     // [ldS_max] compact -> reduced index

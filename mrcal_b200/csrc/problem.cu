@@ -236,7 +236,7 @@ mrcal_b200_problem_create(const double* intrinsics, const mrcal_pose_t* rt_cam_r
     dp.opt_core = L.sel.do_optimize_intrinsics_core; dp.opt_dist = L.sel.do_optimize_intrinsics_distortions;
     dp.opt_extr = L.i_extr0 >= 0; dp.opt_frames = L.sel.do_optimize_frames; dp.opt_warp = L.i_warp0 >= 0;
     dp.have_warp = calobject_warp != nullptr;
-    dp.reg = L.sel.do_apply_regularization; dp.reg_unity = L.Nreg_unity > 0;
+    dp.reg = L.sel.do_apply_regularization; dp.reg_unity = L.Nreg_unity > 0; dp.reg_owner = true;
     dp.opencv8plus = lensmodel->type == MRCAL_LENSMODEL_OPENCV8 || lensmodel->type == MRCAL_LENSMODEL_OPENCV12;
     dp.nnz_row_intr = L.nnz_row_intr; dp.nnz_row_board_geom = L.nnz_row_board_geom;
     dp.in_intrinsics = P->d_seed_intr; dp.in_rt_cam = P->d_seed_rtcam; dp.in_rt_frame = P->d_seed_rtframe;

@@ -33,6 +33,7 @@ struct DevProblem
     bool opt_core, opt_dist, opt_extr, opt_frames, opt_warp;
     bool have_warp;            // a calobject_warp was given (optimised or not)
     bool reg, reg_unity;
+    bool reg_owner;            // this rank adds the (replicated) regularization rows to cross-rank sums
     int  opencv8plus;          // regularisation of the rational denominators (mrcal.c:5806-5834)
     int  nnz_row_intr;         // per board/point row
     int  nnz_row_board_geom;   // frames + warp

@@ -77,11 +77,16 @@ jv_kernel(const int* __restrict__ rowptr, const int* __restrict__ col, const dou
     }
 }
 
-// out[0] = a.a, out[1] = b.b, out[2] = a.b  over [i0,i1) (b may be null)
+// Block k in {0,1,2} reduces range k of the state vector: [0,e0) shared head, [e0,e1) eliminated
+// (the only part that differs between ranks when the frames are sharded), [e1,n) shared tail.
+// out[3k+0] = a.a, out[3k+1] = b.b, out[3k+2] = a.b  (b may be null)
 __global__ void __launch_bounds__(1024)
-dots_kernel(const double* __restrict__ a, const double* __restrict__ b, int i0, int i1, double* __restrict__ out)
+dots_kernel(const double* __restrict__ a, const double* __restrict__ b, int e0, int e1, int n, double* __restrict__ out)
 {
     __shared__ double r[3][32];
+    const int i0 = blockIdx.x == 0 ? 0 : (blockIdx.x == 1 ? e0 : e1);
+    const int i1 = blockIdx.x == 0 ? e0 : (blockIdx.x == 1 ? e1 : n);
+    out += 3 * blockIdx.x;
     double s0 = 0., s1 = 0., s2 = 0.;
     for(int i = i0 + threadIdx.x; i < i1; i += blockDim.x)
     {
@@ -150,6 +155,7 @@ static bool build_workspace(mrcal_b200_problem* P)
     N.ldS = N.ldS_max;
     N.n_c = N.n_r;
     N.splined = L.splined;
+    // gs | gsh contiguous (one reduction)
     N.cap = L.Nintr_state + 8;
     N.Nframe_groups = (elim && L.i_frame0 >= 0) ? L.d.Nframes : 0;
     const int Npoint_groups = (elim && L.i_point0 >= 0) ? L.Npoints_variable : 0;
@@ -176,7 +182,7 @@ static bool build_workspace(mrcal_b200_problem* P)
         ptr[N.Ngroups] = (int)items.size();
     }
 
-    bool ok = A.alloc(&N.S, (size_t)N.ldS_max * N.ldS_max) && A.alloc(&N.gs, N.ldS_max, true) && A.alloc(&N.g_full, L.Nstate, true) &&
+    bool ok = A.alloc(&N.S, (size_t)N.ldS_max * N.ldS_max) && A.alloc(&N.gs, 2 * (size_t)N.ldS_max, true) && A.alloc(&N.g_full, L.Nstate, true) &&
               A.alloc(&N.info, 4, true) && A.alloc(&N.active, N.n_r, true) && A.alloc(&N.cidx, N.n_r, true) &&
               A.alloc(&N.cinv, N.ldS_max, true) && A.alloc(&N.stat, 4, true) && A.alloc(&ws->ds_r, N.n_r, true) &&
               A.alloc(&N.wi_nsh, Nwi, true) && A.alloc(&N.wi_cols, (size_t)Nwi * N.cap) &&
@@ -184,9 +190,10 @@ static bool build_workspace(mrcal_b200_problem* P)
               A.alloc(&N.grp_ptr, (size_t)N.Ngroups + 1) && A.alloc(&N.grp_items, items.size()) &&
               A.alloc(&N.grp_Dinv, (size_t)N.Ngroups * 36) && A.alloc(&N.grp_gf, (size_t)N.Ngroups * 6) &&
               A.alloc(&ws->invL, (size_t)N.ldS_max * kCholBlock) && A.alloc(&ws->rhs, N.ldS_max, true) &&
-              A.alloc(&ws->step_gn, L.Nstate, true) && A.alloc(&ws->step, L.Nstate, true) && A.alloc(&ws->scal, 16, true);
+              A.alloc(&ws->step_gn, L.Nstate, true) && A.alloc(&ws->step, L.Nstate, true) && A.alloc(&ws->scal, 32, true);
     if(!ok) return false;
-    MB200_CUDA_CHECK(cudaMallocHost(&ws->h_scal, 16 * sizeof(double)));
+    N.gsh = N.gs + N.ldS_max;
+    MB200_CUDA_CHECK(cudaMallocHost(&ws->h_scal, 32 * sizeof(double)));
     MB200_CUDA_CHECK(cudaMallocHost(&ws->h_info, 8 * sizeof(int)));
     N.h_stat = ws->h_info + 4;
     MB200_CUDA_CHECK(cudaMemcpyAsync(N.grp_ptr, ptr.data(), ptr.size() * sizeof(int), cudaMemcpyHostToDevice, P->stream));
@@ -300,17 +307,18 @@ static bool dogleg_pass(mrcal_b200_problem* P, const mrcal_b200_solver_parameter
     {
         const int a = T->mark();
         if(!normal_assemble(P->dp, N, P->op[which], P->d_rowptr, *lambda, s, nl)) return false;
-        if(comm_active())
-        {
-            // the one collective of the algorithm: reduced system + reduced rhs (+ the shared part of J'x)
-            if(!comm_allreduce_sum(N.S, (size_t)N.ldS * N.ldS, s)) return false;
-            if(!comm_allreduce_sum(N.gs, (size_t)N.ldS, s)) return false;   // TODO: the active set must be the union over ranks
-        }
         T->spans[1].push_back({a, T->mark()});
         return true;
     };
 
+    // rows whose sums this rank contributes to cross-rank reductions: the regularization rows are
+    // replicated on every rank but counted once
+    const int Nrows_mine = P->dp.reg_owner ? Nmeas : P->dp.m_reg0;
+    const int e0 = N.e0, e1 = N.e1;
+    auto sum3 = [&](const double* h, int k) { return h[k] + h[3 + k] + h[6 + k]; };
+
     if(!evaluate(P->cur)) return false;
+    if(comm_active() && !comm_allreduce_sum(P->op[P->cur].norm2, 1, s)) return false;
     MB200_CUDA_CHECK(cudaMemcpyAsync(ws->h_scal, P->op[P->cur].norm2, sizeof(double), cudaMemcpyDeviceToHost, s));
     MB200_CUDA_CHECK(cudaStreamSynchronize(s));
     double norm2_x = ws->h_scal[0];
@@ -337,13 +345,18 @@ static bool dogleg_pass(mrcal_b200_problem* P, const mrcal_b200_solver_parameter
             // ---- Cauchy step: -k g, k = |g|^2 / |J g|^2
             if(!have_cauchy)
             {
-                MB200_CUDA_CHECK(cudaMemsetAsync(ws->scal, 0, 16 * sizeof(double), s));
-                dots_kernel<<<1, 1024, 0, s>>>(N.g_full, nullptr, 0, Nstate, ws->scal + 0);
-                jv_kernel<<<148 * 16, 256, 0, s>>>(P->d_rowptr, cur.Jcol, cur.Jval, N.g_full, cur.x, Nmeas, ws->scal + 4);
+                MB200_CUDA_CHECK(cudaMemsetAsync(ws->scal, 0, 32 * sizeof(double), s));
+                dots_kernel<<<3, 1024, 0, s>>>(N.g_full, nullptr, e0, e1, Nstate, ws->scal + 0);
+                jv_kernel<<<148 * 16, 256, 0, s>>>(P->d_rowptr, cur.Jcol, cur.Jval, N.g_full, cur.x, Nrows_mine, ws->scal + 9);
                 *nl += 2;
-                if(!read_scalars(P, 8)) return false;
-                g2 = ws->h_scal[0];
-                Jg2 = ws->h_scal[5];
+                if(comm_active())
+                {
+                    // eliminated-range dots and the row sums are per-rank partial sums: slots [3..5] and [9..10]
+                    if(!comm_allreduce_sum(ws->scal + 3, 3, s) || !comm_allreduce_sum(ws->scal + 9, 2, s)) return false;
+                }
+                if(!read_scalars(P, 11)) return false;
+                g2 = sum3(ws->h_scal, 0);
+                Jg2 = ws->h_scal[10];
                 if(!(g2 > 0.) || !(Jg2 > 0.))
                 {
                     // zero gradient: nothing to do (libdogleg's Jt_x_threshold test)
@@ -377,6 +390,16 @@ static bool dogleg_pass(mrcal_b200_problem* P, const mrcal_b200_solver_parameter
                         MB200_CUDA_CHECK(cudaStreamSynchronize(s));
                         T->spans[2].push_back({a, T->mark()});
                         info->Nfactorizations++;
+                        if(comm_active())
+                        {
+                            // a frame block that is singular on ONE rank must send every rank down the same path
+                            ws->h_scal[30] = (double)(ws->h_info[0] != 0 || ws->h_info[1] != 0);
+                            MB200_CUDA_CHECK(cudaMemcpyAsync(ws->scal + 30, ws->h_scal + 30, sizeof(double), cudaMemcpyHostToDevice, s));
+                            if(!comm_allreduce_sum(ws->scal + 30, 1, s)) return false;
+                            MB200_CUDA_CHECK(cudaMemcpyAsync(ws->h_scal + 30, ws->scal + 30, sizeof(double), cudaMemcpyDeviceToHost, s));
+                            MB200_CUDA_CHECK(cudaStreamSynchronize(s));
+                            if(ws->h_scal[30] != 0. && ws->h_info[0] == 0 && ws->h_info[1] == 0) ws->h_info[0] = -1;
+                        }
                         if(ws->h_info[0] == 0 && ws->h_info[1] == 0) break;
                         // singular JtJ: add lambda I "from now on", as libdogleg does (1e-10, then x10)
                         *lambda = (*lambda == 0.) ? 1e-10 : *lambda * 10.;
@@ -388,13 +411,14 @@ static bool dogleg_pass(mrcal_b200_problem* P, const mrcal_b200_solver_parameter
                     if(!normal_rhs(N, ws->rhs, s, nl)) return false;
                     if(N.n_c > 0 && !chol_solve(N.S, N.ldS, ws->invL, ws->rhs, N.ldS, 1, s, nl)) return false;
                     if(!normal_expand_step(P->dp, N, P->op[P->cur], *lambda, ws->rhs, ws->ds_r, ws->step_gn, s, nl)) return false;
-                    dots_kernel<<<1, 1024, 0, s>>>(ws->step_gn, N.g_full, 0, Nstate, ws->scal + 8);
+                    dots_kernel<<<3, 1024, 0, s>>>(ws->step_gn, N.g_full, e0, e1, Nstate, ws->scal + 11);
                     (*nl)++;
+                    if(comm_active() && !comm_allreduce_sum(ws->scal + 14, 3, s)) return false;
                     T->spans[3].push_back({a, T->mark()});
-                    MB200_CUDA_CHECK(cudaMemcpyAsync(ws->h_scal + 8, ws->scal + 8, 3 * sizeof(double), cudaMemcpyDeviceToHost, s));
+                    MB200_CUDA_CHECK(cudaMemcpyAsync(ws->h_scal + 11, ws->scal + 11, 9 * sizeof(double), cudaMemcpyDeviceToHost, s));
                     MB200_CUDA_CHECK(cudaStreamSynchronize(s));
-                    gn_lensq = ws->h_scal[8];
-                    g_dot_gn = ws->h_scal[10];
+                    gn_lensq = sum3(ws->h_scal + 11, 0);
+                    g_dot_gn = sum3(ws->h_scal + 11, 2);
                     have_gn = true;
                 }
                 if(gn_lensq <= trustregion * trustregion)
@@ -427,16 +451,17 @@ static bool dogleg_pass(mrcal_b200_problem* P, const mrcal_b200_solver_parameter
                 done = true;
                 break;
             }
-            MB200_CUDA_CHECK(cudaMemsetAsync(ws->scal + 12, 0, 2 * sizeof(double), s));
-            jv_kernel<<<148 * 16, 256, 0, s>>>(P->d_rowptr, cur.Jcol, cur.Jval, ws->step, cur.x, Nmeas, ws->scal + 12);
+            MB200_CUDA_CHECK(cudaMemsetAsync(ws->scal + 20, 0, 2 * sizeof(double), s));
+            jv_kernel<<<148 * 16, 256, 0, s>>>(P->d_rowptr, cur.Jcol, cur.Jval, ws->step, cur.x, Nrows_mine, ws->scal + 20);
             (*nl)++;
             if(!evaluate(1 - P->cur)) return false;
-            MB200_CUDA_CHECK(cudaMemcpyAsync(ws->h_scal + 12, ws->scal + 12, 2 * sizeof(double), cudaMemcpyDeviceToHost, s));
-            MB200_CUDA_CHECK(cudaMemcpyAsync(ws->h_scal + 14, nxt.norm2, sizeof(double), cudaMemcpyDeviceToHost, s));
+            MB200_CUDA_CHECK(cudaMemcpyAsync(ws->scal + 22, nxt.norm2, sizeof(double), cudaMemcpyDeviceToDevice, s));
+            if(comm_active() && !comm_allreduce_sum(ws->scal + 20, 3, s)) return false;
+            MB200_CUDA_CHECK(cudaMemcpyAsync(ws->h_scal + 20, ws->scal + 20, 3 * sizeof(double), cudaMemcpyDeviceToHost, s));
             MB200_CUDA_CHECK(cudaStreamSynchronize(s));
             // |x|^2 - |x + J step|^2
-            const double expected = -ws->h_scal[13] - 2. * ws->h_scal[12];
-            const double norm2_new = ws->h_scal[14];
+            const double expected = -ws->h_scal[21] - 2. * ws->h_scal[20];
+            const double norm2_new = ws->h_scal[22];
             const double observed = norm2_x - norm2_new;
             const double rho = observed / expected;
             if(rho < par.trustregion_decrease_threshold)               trustregion *= par.trustregion_decrease_factor;
@@ -492,6 +517,7 @@ bool solver_run(mrcal_b200_problem* P, const mrcal_b200_solver_parameters_t* par
         info.Nouter++;
         if(!dogleg_pass(P, par, &lambda, &info, &T, &norm2)) return false;
         if(!(L.sel.do_apply_outlier_rejection && Nfeat)) break;
+        if(comm_active()) { set_error("outlier rejection is not implemented for sharded (multi-GPU) solves yet: pass do_apply_outlier_rejection=False"); return false; }
         h_x.resize(L.Nmeas_board);
         MB200_CUDA_CHECK(cudaMemcpyAsync(h_x.data(), P->op[P->cur].x, (size_t)L.Nmeas_board * sizeof(double), cudaMemcpyDeviceToHost, s));
         MB200_CUDA_CHECK(cudaMemcpyAsync(h_pool.data(), P->d_pool_board, 3 * Nfeat * sizeof(double), cudaMemcpyDeviceToHost, s));

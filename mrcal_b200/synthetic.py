@@ -262,7 +262,12 @@ def make_problem(lensmodel="LENSMODEL_OPENCV8", Ncameras=2, Nframes=20, W=10, H=
                 if pc[2] > 0.1 and 0 <= qq[0] <= imagersize[0] - 1 and 0 <= qq[1] <= imagersize[1] - 1:
                     io.append((ip, icam, icam - 1))
                     oo.append((qq[0], qq[1], 1.0))
-        # keep the reference's rule: point indices appear in order and cover all points
+        # a point seen by a single camera has a rank-2 (singular) 3x3 block: keep those seen at least twice.
+        # And keep the reference's rule: point indices appear in order and cover all points
+        nviews = np.bincount([i[0] for i in io], minlength=Npoints)
+        keep = [k for k, i in enumerate(io) if nviews[i[0]] >= 2]
+        io = [io[k] for k in keep]
+        oo = [oo[k] for k in keep]
         seen = sorted(set(i[0] for i in io))
         remap = {old: new for new, old in enumerate(seen)}
         pts = pts[seen]
