@@ -32,76 +32,144 @@ constexpr int NB = 64;     // inner block
 constexpr int NBO = 256;   // outer panel
 
 ////////////////////////////////////////////////////////////////////////////////
-// diagonal block: Cholesky + inverse of the factor. One CTA of 256 threads = 64 rows x
-// 4 threads; the block lives in shared memory.
-//   factor:  left-looking. column j: s_i = a_ij - sum_{k<j} l_ik l_jk, the sum split over
-//            the row's 4 threads (k = part mod 4) and combined with two shuffles;
-//            l_jj = sqrt(s_j) ; l_ij = s_i / l_jj.  Two barriers per column.
-//   inverse: column c of X = inv(L) by forward substitution, again 4 threads per column.
-// Loops are NOT unrolled: the instruction stream of a fully unrolled 64x64 factorization
-// does not fit the instruction cache and runs slower than the arithmetic.
+// diagonal block: Cholesky + inverse of the factor, one CTA of 256 threads, block in
+// shared memory. The 64 pivots are an inherently serial chain (rsqrt + a dependent
+// update each); everything is arranged to keep that chain short:
+//   4 panels of 16 columns. Per panel
+//     (a) ONE WARP factors the 16x16 diagonal sub-block with a row per lane in registers,
+//         columns exchanged by shuffles (no barriers), and inverts it the same way
+//     (b) all threads: the 16 columns below it  X = A inv(D)'          (48..0 rows)
+//     (c) all threads: trailing update of the block  A -= X X'
+//   then the off-diagonal blocks of inv(L) row-block by row-block:
+//         inv(L)_ij = -inv(L)_ii sum_{j<=k<i} L_ik inv(L)_kj
 ////////////////////////////////////////////////////////////////////////////////
+constexpr int SB = 16;   // sub-block
+
 __global__ void __launch_bounds__(256)
 potrf_diag_kernel(double* __restrict__ A, int ld, int k0, double* __restrict__ invL, int* __restrict__ info, int nreal)
 {
     extern __shared__ __align__(16) double dsm[];
     double (*sL)[NB + 1] = reinterpret_cast<double (*)[NB + 1]>(dsm);
     double (*sX)[NB + 1] = reinterpret_cast<double (*)[NB + 1]>(dsm + NB * (NB + 1));
-    __shared__ double s_rinv[NB];
-    const int tid = threadIdx.x;
-    const int i = tid >> 2, part = tid & 3;
+    __shared__ double sT[NB - SB][SB + 1];   // panel scratch
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int ty = tid >> 4, tx = tid & 15;
+
     for(int e = tid; e < NB * NB; e += 256)
     {
         const int r = e / NB, c = e % NB;
         sL[r][c] = c <= r ? A[(size_t)(k0 + r) * ld + k0 + c] : 0.;
+        sX[r][c] = 0.;
     }
     __syncthreads();
-    for(int j = 0; j < NB; j++)
+
+    for(int p = 0; p < NB / SB; p++)
     {
-        double s = 0.;
-#pragma unroll 4
-        for(int k = part; k < j; k += 4) s += sL[i][k] * sL[j][k];
-        s += __shfl_xor_sync(0xffffffffu, s, 1);
-        s += __shfl_xor_sync(0xffffffffu, s, 2);
-        const double sij = sL[i][j] - s;
-        if(i == j && part == 0)
+        const int c0 = p * SB;
+        if(warp == 0)
         {
-            double d = sij;
-            if(!(d > 0.))
+            // (a) lanes 0..15 own rows c0..c0+15 of the diagonal sub-block (lanes 16..31 shadow them)
+            const int li = lane & 15;
+            double a[SB], xinv[SB], rinv[SB];
+#pragma unroll
+            for(int k = 0; k < SB; k++) a[k] = sL[c0 + li][c0 + k];
+#pragma unroll
+            for(int j = 0; j < SB; j++)
             {
-                // not positive definite. Remember the first failing pivot; carry on with a
-                // harmless value so the chain of kernels still terminates
-                if(k0 + j < nreal) atomicCAS(info, 0, k0 + j + 1);
-                d = 1.;
+                double d = __shfl_sync(0xffffffffu, a[j], j);
+                if(!(d > 0.))
+                {
+                    // not positive definite: remember the first failing pivot, carry on with a harmless value
+                    if(lane == 0 && k0 + c0 + j < nreal) atomicCAS(info, 0, k0 + c0 + j + 1);
+                    d = 1.;
+                }
+                const double r = rsqrt(d);
+                rinv[j] = r;
+                a[j] = (li == j) ? d * r : a[j] * r;
+#pragma unroll
+                for(int k = j + 1; k < SB; k++)
+                {
+                    const double lkj = __shfl_sync(0xffffffffu, a[j], k);
+                    a[k] -= a[j] * lkj;
+                }
             }
-            const double l = sqrt(d);
-            sL[j][j] = l;
-            s_rinv[j] = 1. / l;
+            // column li of inv(D): x_i = ((i==li) - sum_{k<i} L_ik x_k) / L_ii ; x_k = 0 for k < li
+#pragma unroll
+            for(int i = 0; i < SB; i++)
+            {
+                double acc = (i == li) ? 1. : 0.;
+#pragma unroll
+                for(int k = 0; k < i; k++)
+                {
+                    const double lik = __shfl_sync(0xffffffffu, a[k], i);
+                    acc -= lik * xinv[k];
+                }
+                xinv[i] = i < li ? 0. : acc * rinv[i];
+            }
+            if(lane < SB)
+            {
+#pragma unroll
+                for(int k = 0; k < SB; k++)
+                {
+                    if(k <= li) sL[c0 + li][c0 + k] = a[k];
+                    sX[c0 + k][c0 + li] = xinv[k];
+                }
+            }
         }
         __syncthreads();
-        if(i > j && part == 0) sL[i][j] = sij * s_rinv[j];
-        __syncthreads();
+        const int m = NB - SB - c0;   // rows below this panel
+        if(m > 0)
+        {
+            // (b) X[r][j] = sum_{k<=j} A[c0+16+r][c0+k] inv(D)[j][k]
+            for(int r = ty; r < m; r += 16)
+            {
+                double acc = 0.;
+#pragma unroll
+                for(int k = 0; k < SB; k++) acc += sL[c0 + SB + r][c0 + k] * sX[c0 + tx][c0 + k];
+                sT[r][tx] = acc;
+            }
+            __syncthreads();
+            for(int r = ty; r < m; r += 16) sL[c0 + SB + r][c0 + tx] = sT[r][tx];
+            // (c) A[r][c] -= sum_k X[r][k] X[c][k], lower triangle of the trailing m x m
+            for(int r = ty; r < m; r += 16)
+                for(int c = tx; c <= r; c += 16)
+                {
+                    double acc = 0.;
+#pragma unroll
+                    for(int k = 0; k < SB; k++) acc += sT[r][k] * sT[c][k];
+                    sL[c0 + SB + r][c0 + SB + c] -= acc;
+                }
+            __syncthreads();
+        }
     }
+    // L back to global (lower triangle), coalesced
     for(int e = tid; e < NB * NB; e += 256)
     {
         const int r = e / NB, c = e % NB;
         if(c <= r) A[(size_t)(k0 + r) * ld + k0 + c] = sL[r][c];
     }
-    // column c = i of inv(L); its 4 threads sit in one warp
+    // off-diagonal blocks of inv(L), one row-block at a time
+    for(int ib = 1; ib < NB / SB; ib++)
     {
-        const int c = i;
-        for(int r = 0; r < NB; r++)
+        const int r0 = ib * SB, w = r0;   // columns 0..w-1
+        // T[r][c] = sum_{k=c..w-1} L[r0+r][k] X[k][c]   (X lower triangular: X[k][c] = 0 for k < c)
+        for(int c = ty; c < w; c += 16)
         {
             double acc = 0.;
-#pragma unroll 4
-            for(int k = c + part; k < r; k += 4) acc += sL[r][k] * sX[k][c];
-            acc += __shfl_xor_sync(0xffffffffu, acc, 1);
-            acc += __shfl_xor_sync(0xffffffffu, acc, 2);
-            if(part == 0) sX[r][c] = r < c ? 0. : ((r == c ? 1. : 0.) - acc) * s_rinv[r];
-            __syncwarp();
+            for(int k = c; k < w; k++) acc += sL[r0 + tx][k] * sX[k][c];
+            sT[c][tx] = acc;   // stored transposed: T[tx][c]
         }
+        __syncthreads();
+        // X[r0+r][c] = -sum_{q<=r} X_ii[r][q] T[q][c]
+        for(int c = ty; c < w; c += 16)
+        {
+            double acc = 0.;
+#pragma unroll
+            for(int q = 0; q < SB; q++) acc += sX[r0 + tx][r0 + q] * sT[c][q];
+            sX[r0 + tx][c] = -acc;
+        }
+        __syncthreads();
     }
-    __syncthreads();
     for(int e = tid; e < NB * NB; e += 256) invL[e] = sX[e / NB][e % NB];
 }
 

@@ -147,6 +147,10 @@ eval_boards_kernel(DevProblem P, double* __restrict__ x, double* __restrict__ Jv
 {
     __shared__ ObsGeometry G;
     __shared__ double red[32];
+    // Jacobian staging: each thread (corner) deposits its two rows here, then the CTA streams the
+    // block out with fully coalesced stores (the rows of one observation are contiguous in J).
+    // Odd strides keep the per-thread deposits free of bank conflicts
+    extern __shared__ __align__(16) double stage_v[];
 
     const int iobs   = blockIdx.x;
     const int icam_i = P.obs_board[3 * iobs + 0];
@@ -177,9 +181,15 @@ eval_boards_kernel(DevProblem P, double* __restrict__ x, double* __restrict__ Jv
     const int NWH         = P.W * P.H;
     const double wx2 = P.u_warp[0], wy2 = P.u_warp[1];
 
+    const int row2 = 2 * nnz_row, stride = row2 + 1;
+    int* stage_c = reinterpret_cast<int*>(stage_v + (size_t)blockDim.x * stride);
+
     double sumsq = 0.;
-    for(int ipt = threadIdx.x; ipt < NWH; ipt += blockDim.x)
+    for(int ipt0 = 0; ipt0 < NWH; ipt0 += blockDim.x)
     {
+      const int ipt = ipt0 + threadIdx.x;
+      if(ipt < NWH)
+      {
         const int cx = ipt % P.W, cy = ipt / P.W;
         // the board point, with the parabolic warp (mrcal.c:2794-2819)
         double pt[3] = {(double)cx * P.spacing, (double)cy * P.spacing, 0.};
@@ -271,12 +281,11 @@ eval_boards_kernel(DevProblem P, double* __restrict__ x, double* __restrict__ Jv
             for(int k = 0; k < 2; k++) dq_dz[k] = G2[k][0] * G.Rf[2] + G2[k][1] * G.Rf[5] + G2[k][2] * G.Rf[8];
 
             const int ivar0s = ivar0 - (P.opt_core ? 0 : 4);
-            const size_t jbase = (size_t)P.board_j0[iobs] + (size_t)(2 * ipt) * nnz_row;
 #pragma unroll
             for(int i_xy = 0; i_xy < 2; i_xy++)
             {
-                double* jv = Jval + jbase + (size_t)i_xy * nnz_row;
-                int*    jc = Jcol + jbase + (size_t)i_xy * nnz_row;
+                double* jv = stage_v + (size_t)threadIdx.x * stride + i_xy * nnz_row;
+                int*    jc = stage_c + (size_t)threadIdx.x * stride + i_xy * nnz_row;
                 double g_f;
                 if constexpr(LensTraits<KIND>::SPLINED) g_f = upd[i_xy];
                 else                                    g_f = (q[i_xy] - intr[2 + i_xy]) / intr[i_xy];   // mrcal.c:1427-1431
@@ -302,6 +311,21 @@ eval_boards_kernel(DevProblem P, double* __restrict__ x, double* __restrict__ Jv
                 }
             }
         }
+      }
+      if constexpr(WITH_J)
+      {
+        // stream this chunk of corners out: entries [ipt0*row2, (ipt0+nhere)*row2) of the observation's block
+        __syncthreads();
+        const int nhere = min((int)blockDim.x, NWH - ipt0);
+        const size_t gbase = (size_t)P.board_j0[iobs] + (size_t)ipt0 * row2;
+        for(int g = threadIdx.x; g < nhere * row2; g += blockDim.x)
+        {
+            const int t = g / row2, e = g - t * row2;
+            Jval[gbase + g] = stage_v[(size_t)t * stride + e];
+            Jcol[gbase + g] = stage_c[(size_t)t * stride + e];
+        }
+        __syncthreads();
+      }
     }
     const double s = block_sum(sumsq, red);
     if(threadIdx.x == 0 && s != 0.) atomicAdd(norm2, s);
@@ -574,8 +598,22 @@ static bool launch_kind(const DevProblem& dp, const EvalBuffers& out, bool with_
         int threads = ((dp.W * dp.H + 31) / 32) * 32;
         if(threads > 256) threads = 256;
         if(threads < 64) threads = 64;
-        if(with_j) eval_boards_kernel<KIND, true ><<<dp.Nobs_board, threads, 0, stream>>>(dp, out.x, out.Jval, out.Jcol, out.norm2);
-        else       eval_boards_kernel<KIND, false><<<dp.Nobs_board, threads, 0, stream>>>(dp, out.x, out.Jval, out.Jcol, out.norm2);
+        if(with_j)
+        {
+            // widest row: extrinsics present
+            const int row2 = 2 * (dp.nnz_row_intr + (dp.opt_extr ? 6 : 0) + dp.nnz_row_board_geom);
+            const size_t smem = (size_t)threads * (row2 + 1) * (sizeof(double) + sizeof(int)) + 16;
+            static bool configured[LENS_NKINDS] = {};
+            if(!configured[KIND])
+            {
+                MB200_CUDA_CHECK(cudaFuncSetAttribute(eval_boards_kernel<KIND, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+                configured[KIND] = true;
+            }
+            if(smem > 200 * 1024) { set_error("Jacobian rows of %d entries are too wide for the staging buffer", row2 / 2); return false; }
+            eval_boards_kernel<KIND, true ><<<dp.Nobs_board, threads, smem, stream>>>(dp, out.x, out.Jval, out.Jcol, out.norm2);
+        }
+        else
+            eval_boards_kernel<KIND, false><<<dp.Nobs_board, threads, 0, stream>>>(dp, out.x, out.Jval, out.Jcol, out.norm2);
         (*nlaunch)++;
     }
     if(dp.Nobs_point > 0)

@@ -341,6 +341,206 @@ assemble_items_kernel(DevProblem P, NormalBuffers N, int gram_cap, const double*
     }
 }
 
+// Pass 2 on the fp64 tensor pipe. The Gram matrix of one observation is a dense contraction:
+//   G = D' D,   D = [ rows of the item over its ntot local columns | x ]   (200 x ~75, ~40 % dense)
+// so it goes through DMMA.8x8x4. D is built 32 rows at a time in shared memory (scatter of the
+// 30 nonzeros of each row), every warp owns a fixed set of 8x8 tiles of the lower triangle of G
+// and keeps them in registers for the whole item; the x column makes J'x the last row of G.
+// 3 barriers per 32 rows instead of one per row, ~10x fewer shared-memory transactions than
+// the scalar kernel above (which remains the fallback for items with more than kDmmaMaxCols
+// local columns).
+constexpr int kDmmaMaxCols = 160;                       // ntot + 1, padded to 8
+constexpr int DCH = 32;                                 // rows per chunk
+// Three instantiations by item width, so that the common narrow items do not pay the register
+// footprint (hence the occupancy) of the widest: tiles per warp for T = ncols/8 <= 10, 16, 20
+constexpr int kDmmaClassT[3]     = {10, 16, 20};
+constexpr int kDmmaClassTiles[3] = {7, 17, 27};
+
+__device__ __forceinline__ void dmma884(double& c0, double& c1, double a, double b)
+{
+    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n"
+                 : "+d"(c0), "+d"(c1) : "d"(a), "d"(b));
+}
+
+template <int kDmmaMaxTiles, int TMIN, int TMAX>
+__global__ void __launch_bounds__(256)
+assemble_items_dmma_kernel(DevProblem P, NormalBuffers N, int ldD, const double* __restrict__ x,
+                           const double* __restrict__ Jval, const int* __restrict__ Jcol)
+{
+    extern __shared__ __align__(16) double dsm[];
+    __shared__ unsigned char s_ti[kDmmaMaxTiles * 8], s_tj[kDmmaMaxTiles * 8];
+    {
+        // this instantiation handles the items whose tile count T is in (TMIN, TMAX]
+        const int T_ = (N.wi_nsh[blockIdx.x] + describe_item(P, blockIdx.x, N.Nframe_groups).nelim + 1 + 7) >> 3;
+        if(T_ <= TMIN || T_ > TMAX) return;
+    }
+
+    const int w = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int g = lane >> 2, t = lane & 3;
+    const ItemDesc d = describe_item(P, w, N.Nframe_groups);
+    const int ncam = d.cam0 >= 0 ? 6 : 0, nwarp = d.warp0 >= 0 ? 2 : 0;
+    const int nsh = N.wi_nsh[w], nloc = nsh - ncam - nwarp, ntot = nsh + d.nelim;
+    const int ncols = ntot + 1;                         // + the x column
+    const int T = (ncols + 7) >> 3, ntiles = T * (T + 1) / 2;
+
+    // shared-memory carve-up: lmap [clen] shorts | ccol [cap] ints | D [DCH][ldD]
+    short* lmap = reinterpret_cast<short*>(dsm);
+    const int lmap_doubles = (d.clen * (int)sizeof(short) + 7) / 8;
+    int* ccol = reinterpret_cast<int*>(dsm + lmap_doubles);
+    const int ccol_doubles = (N.cap * (int)sizeof(int) + 7) / 8;
+    double* D = dsm + lmap_doubles + ccol_doubles;
+
+    const int* cols = N.wi_cols + (size_t)w * N.cap;
+    for(int i = tid; i < d.clen; i += 256) lmap[i] = -1;
+    for(int i = tid; i < DCH * ldD; i += 256) D[i] = 0.;
+    for(int q = tid; q < ntiles; q += 256)
+    {
+        // tile q -> (ti >= tj); warp q%8 owns it as its (q/8)-th tile
+        int ti = (int)((sqrtf(8.f * q + 1.f) - 1.f) * 0.5f);
+        while(ti * (ti + 1) / 2 > q) ti--;
+        while((ti + 1) * (ti + 2) / 2 <= q) ti++;
+        s_ti[q] = (unsigned char)ti;
+        s_tj[q] = (unsigned char)(q - ti * (ti + 1) / 2);
+    }
+    __syncthreads();
+    for(int l = tid; l < nsh; l += 256)
+    {
+        const int r = cols[l];
+        ccol[l] = N.cidx[r];
+        if(l < nloc) lmap[r - d.cbase] = (short)l;
+    }
+    __syncthreads();
+
+    double acc[kDmmaMaxTiles][2];
+#pragma unroll
+    for(int i = 0; i < kDmmaMaxTiles; i++) acc[i][0] = acc[i][1] = 0.;
+    const int my_ntiles = (ntiles - warp + 7) / 8;      // tiles warp, warp+8, ...
+
+    const int per_chunk = DCH * d.nnz_row;
+    const int nchunks = (d.rows + DCH - 1) / DCH;
+    int    pf_col[4];
+    double pf_val[4];
+    double pf_x = 0.;
+    auto prefetch = [&](int chunk)
+    {
+#pragma unroll
+        for(int q = 0; q < 4; q++)
+        {
+            const int e = tid + q * 256;
+            const int rr = e / d.nnz_row, k = e - rr * d.nnz_row;
+            const int r = chunk * DCH + rr;
+            pf_col[q] = 0; pf_val[q] = 0.;
+            if(e < per_chunk && r < d.rows)
+            {
+                const size_t j = (size_t)d.j0 + (size_t)r * d.nnz_row + k;
+                if(k < d.nI) pf_col[q] = Jcol[j];
+                pf_val[q] = Jval[j];
+            }
+        }
+        if(tid < DCH) pf_x = chunk * DCH + tid < d.rows ? x[d.m0 + chunk * DCH + tid] : 0.;
+    };
+    // where entry q of this thread lands in D (or -1)
+    auto slot = [&](int chunk, int q) -> int
+    {
+        const int e = tid + q * 256;
+        if(e >= per_chunk) return -1;
+        const int rr = e / d.nnz_row, k = e - rr * d.nnz_row;
+        if(chunk * DCH + rr >= d.rows) return -1;
+        int l;
+        if(k < d.nI)                          l = lmap[pf_col[q] - d.cbase];
+        else if(k < d.nI + ncam)              l = nloc + (k - d.nI);
+        else if(k < d.nI + ncam + d.nelim)    l = nsh + (k - d.nI - ncam);
+        else                                  l = nloc + ncam + (k - d.nI - ncam - d.nelim);
+        return rr * ldD + l;
+    };
+    prefetch(0);
+    for(int c = 0; c < nchunks; c++)
+    {
+        int where[4];
+#pragma unroll
+        for(int q = 0; q < 4; q++)
+        {
+            where[q] = slot(c, q);
+            if(where[q] >= 0) D[where[q]] = pf_val[q];
+        }
+        if(tid < DCH) D[tid * ldD + ntot] = pf_x;
+        __syncthreads();
+        if(c + 1 < nchunks) prefetch(c + 1);
+#pragma unroll
+        for(int i = 0; i < kDmmaMaxTiles; i++)
+        {
+            if(i < my_ntiles)   // warp-uniform; compile-time i keeps acc[] in registers
+            {
+                const int q = warp + 8 * i;
+                const double* Da = D + 8 * s_ti[q] + g;     // A operand: element (row g of the tile, k = t) = D[k][8 ti + g]
+                const double* Db = D + 8 * s_tj[q] + g;     // B operand: element (k = t, col g)            = D[k][8 tj + g]
+#pragma unroll
+                for(int ks = 0; ks < DCH / 4; ks++)
+                    dmma884(acc[i][0], acc[i][1], Da[(ks * 4 + t) * ldD], Db[(ks * 4 + t) * ldD]);
+            }
+        }
+        __syncthreads();
+        // un-scatter: cheaper than clearing the whole chunk
+#pragma unroll
+        for(int q = 0; q < 4; q++) if(where[q] >= 0) D[where[q]] = 0.;
+        if(tid < DCH) D[tid * ldD + ntot] = 0.;
+        // (the next chunk's scatter touches other or the same entries of D only after the barrier below,
+        //  which is the one at the top of the next iteration's MMA; a thread zeroes only what it wrote)
+        __syncthreads();
+    }
+
+    // ---- write out from the accumulators. Lane holds G[8 ti + g][8 tj + 2t + {0,1}]
+    double* B = N.wi_B + (size_t)w * 6 * N.cap;
+#pragma unroll
+    for(int i = 0; i < kDmmaMaxTiles; i++)
+    {
+        if(i >= my_ntiles) continue;
+        const int q = warp + 8 * i;
+        const int row = 8 * s_ti[q] + g;
+#pragma unroll
+        for(int h = 0; h < 2; h++)
+        {
+            const int col = 8 * s_tj[q] + 2 * t + h;
+            const double v = acc[i][h];
+            // lower triangle (incl. diagonal) of the (ntot+1)^2 Gram matrix; the (x,x) corner is |x|^2: unused
+            if(row > ntot || col > row || col >= ntot) continue;
+            if(row < nsh)
+            {
+                if(v != 0.) atomicAdd(&N.S[(size_t)ccol[row] * N.ldS + ccol[col]], v);        // shared x shared
+            }
+            else if(row < ntot)
+            {
+                const int p = row - nsh;
+                if(col < nsh) B[(size_t)p * N.cap + col] = v;                                  // eliminated x shared
+                else
+                {
+                    const int qq = col - nsh;                                                   // eliminated x eliminated
+                    N.wi_D[(size_t)w * 36 + p * 6 + qq] = v;
+                    N.wi_D[(size_t)w * 36 + qq * 6 + p] = v;
+                }
+            }
+            else   // row == ntot: the x row = J'x
+            {
+                if(col < nsh)
+                {
+                    if(v != 0.)
+                    {
+                        atomicAdd(&N.gs[ccol[col]], v);
+                        atomicAdd(&N.g_full[N.state_index(cols[col])], v);
+                    }
+                }
+                else N.wi_gf[(size_t)w * 6 + (col - nsh)] = v;
+            }
+        }
+    }
+    // unused corners of the 6x6 / 6-vector for 3-unknown (point) groups and for no elimination at all
+    if(d.nelim > 0 && d.nelim < 6)
+    {
+        if(tid < 36) { const int p = tid / 6, qq = tid % 6; if(p >= d.nelim || qq >= d.nelim) N.wi_D[(size_t)w * 36 + tid] = 0.; }
+        if(tid >= 64 && tid < 70 && tid - 64 >= d.nelim) N.wi_gf[(size_t)w * 6 + tid - 64] = 0.;
+    }
+}
+
 // Regularization rows touch shared unknowns only: one thread per row. A row whose unknowns are
 // inactive (touched by no observation) stays out of S: inactive_step_kernel deals with it
 __global__ void assemble_reg_kernel(DevProblem P, NormalBuffers N, const double* __restrict__ x,
@@ -613,6 +813,9 @@ bool normal_assemble(const DevProblem& dp, NormalBuffers& N, const EvalBuffers& 
     {
         MB200_CUDA_CHECK(cudaFuncSetAttribute(assemble_items_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
         MB200_CUDA_CHECK(cudaFuncSetAttribute(schur_groups_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
+        MB200_CUDA_CHECK(cudaFuncSetAttribute((assemble_items_dmma_kernel<kDmmaClassTiles[0], 0, kDmmaClassT[0]>), cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
+        MB200_CUDA_CHECK(cudaFuncSetAttribute((assemble_items_dmma_kernel<kDmmaClassTiles[1], kDmmaClassT[0], kDmmaClassT[1]>), cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
+        MB200_CUDA_CHECK(cudaFuncSetAttribute((assemble_items_dmma_kernel<kDmmaClassTiles[2], kDmmaClassT[1], kDmmaClassT[2]>), cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
         configured = true;
     }
     const size_t lmap_bytes = ((size_t)dp.Nintr_state * sizeof(short) + 7) / 8 * 8;
@@ -652,7 +855,34 @@ bool normal_assemble(const DevProblem& dp, NormalBuffers& N, const EvalBuffers& 
     MB200_CUDA_CHECK(cudaMemsetAsync(N.info, 0, sizeof(int), s));
     if(Nwi > 0)
     {
-        assemble_items_kernel<<<Nwi, 256, smem_items, s>>>(dp, N, gram_cap, op.x, op.Jval, op.Jcol);
+        const int ncols_pad = ((max_ntot + 1 + 7) / 8) * 8;
+        if(ncols_pad <= kDmmaMaxCols)
+        {
+            // the tensor-pipe kernel: D chunk [32][ldD], ldD = 4 (mod 16) for conflict-free fragment loads
+            int ldD = ncols_pad;
+            while(ldD % 16 != 4) ldD++;
+            const int Tmax = ncols_pad / 8;
+            auto ld_for = [](int T) { int ld = 8 * T; while(ld % 16 != 4) ld++; return ld; };
+            auto smem_for = [&](int T) { return lmap_bytes + ccol_bytes + (size_t)DCH * ld_for(T) * sizeof(double); };
+            (void)ldD;
+            {
+                const int T0 = Tmax < kDmmaClassT[0] ? Tmax : kDmmaClassT[0];
+                assemble_items_dmma_kernel<kDmmaClassTiles[0], 0, kDmmaClassT[0]><<<Nwi, 256, smem_for(T0), s>>>(dp, N, ld_for(T0), op.x, op.Jval, op.Jcol);
+            }
+            if(Tmax > kDmmaClassT[0])
+            {
+                const int T1 = Tmax < kDmmaClassT[1] ? Tmax : kDmmaClassT[1];
+                assemble_items_dmma_kernel<kDmmaClassTiles[1], kDmmaClassT[0], kDmmaClassT[1]><<<Nwi, 256, smem_for(T1), s>>>(dp, N, ld_for(T1), op.x, op.Jval, op.Jcol);
+                (*nlaunch)++;
+            }
+            if(Tmax > kDmmaClassT[1])
+            {
+                assemble_items_dmma_kernel<kDmmaClassTiles[2], kDmmaClassT[1], kDmmaClassT[2]><<<Nwi, 256, smem_for(Tmax), s>>>(dp, N, ld_for(Tmax), op.x, op.Jval, op.Jcol);
+                (*nlaunch)++;
+            }
+        }
+        else
+            assemble_items_kernel<<<Nwi, 256, smem_items, s>>>(dp, N, gram_cap, op.x, op.Jval, op.Jcol);
         (*nlaunch)++;
     }
     const int Nreg = dp.Nmeas - dp.m_reg0;
