@@ -152,6 +152,8 @@ def main():
     ap.add_argument("--impl", default="ours", choices=("ours", "reference"))
     ap.add_argument("--config", type=int, default=3)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--max-iterations", type=int, default=300,
+                    help="cap on trust-region iterations per solve (300 = the reference's; smaller only for profiling runs)")
     args = ap.parse_args()
 
     rank = int(os.environ.get("RANK", "0"))
@@ -219,7 +221,7 @@ def main():
         flush.zero_()
         torch.cuda.synchronize()
         P.reset()
-        return P.optimize()
+        return P.optimize(max_iterations=args.max_iterations)
 
     for _ in range(args.warmup):
         one_step()

@@ -421,6 +421,15 @@ bool chol_solve(const double* L, int npad, const double* invL, double* B, int ld
                        [&](int* n) { return chol_solve_enqueue(L, npad, invL, B, ldb, 1, s, n); });
 }
 
+static bool chol_solve_bwd_enqueue(const double* L, int npad, const double* invL, double* B, int ldb, cudaStream_t s, int* nlaunch);
+
+// L' z = y only (the forward half came out of the factorization itself: see normal_assemble's augmented row)
+bool chol_solve_backward(const double* L, int npad, const double* invL, double* B, int ldb, cudaStream_t s, int* nlaunch)
+{
+    return run_graphed(GraphKey{L, B, npad, ldb, 2}, s, nlaunch,
+                       [&](int* n) { return chol_solve_bwd_enqueue(L, npad, invL, B, ldb, s, n); });
+}
+
 static bool chol_factor_enqueue(double* A, int npad, int nreal, double* invL, int* d_info, cudaStream_t s, int* nlaunch, int kinds)
 {
     if(!configure_kernels()) return false;
@@ -587,6 +596,24 @@ double chol_debug_time(int n, int reps, int kinds, int graph)
     cudaStreamDestroy(s);
     cudaFree(A); cudaFree(invL); cudaFree(info);
     return ms / reps;
+}
+
+static bool chol_solve_bwd_enqueue(const double* L, int npad, const double* invL, double* B, int ldb, cudaStream_t s, int* nlaunch)
+{
+    const int nblk = npad / NB;
+    for(int k = nblk - 1; k >= 0; k--)
+    {
+        const int k0 = k * NB;
+        solve_diag_kernel<<<1, NB, 0, s>>>(invL + (size_t)k * NB * NB, B, ldb, k0, true);
+        if(nlaunch) (*nlaunch)++;
+        if(k0 > 0)
+        {
+            solve_update_bwd_kernel<<<(k0 + 255) / 256, 256, 0, s>>>(L, npad, B, ldb, 1, k0);
+            if(nlaunch) (*nlaunch)++;
+        }
+    }
+    MB200_CUDA_CHECK(cudaGetLastError());
+    return true;
 }
 
 // min/max of the diagonal of L (for rcond)

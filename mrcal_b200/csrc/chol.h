@@ -16,6 +16,9 @@ bool chol_factor(double* A, int npad, int nreal, double* invL, int* d_info, cuda
 // Solve L L' X = B in place for nrhs right-hand sides stored as rows B[r][0..npad)
 bool chol_solve(const double* L, int npad, const double* invL, double* B, int ldb, int nrhs, cudaStream_t s, int* nlaunch);
 
+// Only the backward half, L' Z = B in place, one right-hand side
+bool chol_solve_backward(const double* L, int npad, const double* invL, double* B, int ldb, cudaStream_t s, int* nlaunch);
+
 // drop cached CUDA graphs that reference this buffer (call before freeing it)
 void chol_forget_graphs(const void* A);
 

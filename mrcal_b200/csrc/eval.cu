@@ -71,6 +71,15 @@ __global__ void unpack_state_kernel(DevProblem P, const double* __restrict__ b)
     }
 }
 
+// R and dR/dr of every frame and camera pose, one thread each: the board kernel's CTAs then only
+// load 36 doubles instead of one of their threads evaluating sincos and 27 derivatives serially
+__global__ void expand_rotations_kernel(DevProblem P)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if(i < P.Nframes)                  rodrigues(&P.u_rot_frame[36 * i], &P.u_rot_frame[36 * i + 9], &P.u_rtframe[6 * i]);
+    else if(i < P.Nframes + P.Ncam_e)  { const int c = i - P.Nframes; rodrigues(&P.u_rot_cam[36 * c], &P.u_rot_cam[36 * c + 9], &P.u_rtcam[6 * c]); }
+}
+
 __device__ __forceinline__ double block_sum(double v, double* sh /* >= 32 doubles */)
 {
 #pragma unroll
@@ -158,17 +167,21 @@ eval_boards_kernel(DevProblem P, double* __restrict__ x, double* __restrict__ Jv
     const int iframe = P.obs_board[3 * iobs + 2];
     const bool cam_identity = icam_e < 0;
 
-    if(threadIdx.x == 0)
+    if(threadIdx.x < 36)
     {
-        const double* rt = &P.u_rtframe[6 * iframe];
-        rodrigues(G.Rf, G.dRf, rt);
-        G.tf[0] = rt[3]; G.tf[1] = rt[4]; G.tf[2] = rt[5];
+        const double v = P.u_rot_frame[36 * iframe + threadIdx.x];
+        if(threadIdx.x < 9) G.Rf[threadIdx.x] = v; else G.dRf[threadIdx.x - 9] = v;
     }
-    if(threadIdx.x == 32 % blockDim.x && !cam_identity)
+    else if(threadIdx.x < 39) G.tf[threadIdx.x - 36] = P.u_rtframe[6 * iframe + 3 + threadIdx.x - 36];
+    if(!cam_identity)
     {
-        const double* rt = &P.u_rtcam[6 * icam_e];
-        rodrigues(G.Rc, G.dRc, rt);
-        G.tc[0] = rt[3]; G.tc[1] = rt[4]; G.tc[2] = rt[5];
+        if(threadIdx.x >= 64 && threadIdx.x < 100)
+        {
+            const int k = threadIdx.x - 64;
+            const double v = P.u_rot_cam[36 * icam_e + k];
+            if(k < 9) G.Rc[k] = v; else G.dRc[k - 9] = v;
+        }
+        else if(threadIdx.x >= 40 && threadIdx.x < 43) G.tc[threadIdx.x - 40] = P.u_rtcam[6 * icam_e + 3 + threadIdx.x - 40];
     }
     __syncthreads();
 
@@ -597,7 +610,7 @@ static bool launch_kind(const DevProblem& dp, const EvalBuffers& out, bool with_
     {
         int threads = ((dp.W * dp.H + 31) / 32) * 32;
         if(threads > 256) threads = 256;
-        if(threads < 64) threads = 64;
+        if(threads < 128) threads = 128;
         if(with_j)
         {
             // widest row: extrinsics present
@@ -631,6 +644,11 @@ bool launch_unpack_state(const DevProblem& dp, const double* b_packed, cudaStrea
     const int n = dp.Ncam_i * dp.Nintr + dp.Ncam_e * 6 + dp.Nframes * 6 + dp.Npoints * 3 + 2;
     unpack_state_kernel<<<(n + 255) / 256, 256, 0, stream>>>(dp, b_packed);
     if(nlaunch) (*nlaunch)++;
+    if(dp.Nframes + dp.Ncam_e > 0 && dp.Nobs_board > 0)
+    {
+        expand_rotations_kernel<<<(dp.Nframes + dp.Ncam_e + 127) / 128, 128, 0, stream>>>(dp);
+        if(nlaunch) (*nlaunch)++;
+    }
     MB200_CUDA_CHECK(cudaGetLastError());
     return true;
 }

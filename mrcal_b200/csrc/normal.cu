@@ -421,19 +421,31 @@ assemble_items_dmma_kernel(DevProblem P, NormalBuffers N, int ldD, const double*
     int    pf_col[4];
     double pf_val[4];
     double pf_x = 0.;
+    // entry q of this thread is entry (rr, k) of every chunk: the index arithmetic is loop invariant
+    int my_rr[4], my_k[4], my_l[4];
+#pragma unroll
+    for(int q = 0; q < 4; q++)
+    {
+        const int e = tid + q * 256;
+        my_rr[q] = e < per_chunk ? e / d.nnz_row : -1;
+        my_k[q] = e < per_chunk ? e - my_rr[q] * d.nnz_row : 0;
+        const int k = my_k[q];
+        if(k < d.nI)                          my_l[q] = -1;                                   // per-row lookup
+        else if(k < d.nI + ncam)              my_l[q] = nloc + (k - d.nI);
+        else if(k < d.nI + ncam + d.nelim)    my_l[q] = nsh + (k - d.nI - ncam);
+        else                                  my_l[q] = nloc + ncam + (k - d.nI - ncam - d.nelim);
+    }
     auto prefetch = [&](int chunk)
     {
 #pragma unroll
         for(int q = 0; q < 4; q++)
         {
-            const int e = tid + q * 256;
-            const int rr = e / d.nnz_row, k = e - rr * d.nnz_row;
-            const int r = chunk * DCH + rr;
+            const int r = chunk * DCH + my_rr[q];
             pf_col[q] = 0; pf_val[q] = 0.;
-            if(e < per_chunk && r < d.rows)
+            if(my_rr[q] >= 0 && r < d.rows)
             {
-                const size_t j = (size_t)d.j0 + (size_t)r * d.nnz_row + k;
-                if(k < d.nI) pf_col[q] = Jcol[j];
+                const size_t j = (size_t)d.j0 + (size_t)r * d.nnz_row + my_k[q];
+                if(my_k[q] < d.nI) pf_col[q] = Jcol[j];
                 pf_val[q] = Jval[j];
             }
         }
@@ -442,16 +454,9 @@ assemble_items_dmma_kernel(DevProblem P, NormalBuffers N, int ldD, const double*
     // where entry q of this thread lands in D (or -1)
     auto slot = [&](int chunk, int q) -> int
     {
-        const int e = tid + q * 256;
-        if(e >= per_chunk) return -1;
-        const int rr = e / d.nnz_row, k = e - rr * d.nnz_row;
-        if(chunk * DCH + rr >= d.rows) return -1;
-        int l;
-        if(k < d.nI)                          l = lmap[pf_col[q] - d.cbase];
-        else if(k < d.nI + ncam)              l = nloc + (k - d.nI);
-        else if(k < d.nI + ncam + d.nelim)    l = nsh + (k - d.nI - ncam);
-        else                                  l = nloc + ncam + (k - d.nI - ncam - d.nelim);
-        return rr * ldD + l;
+        if(my_rr[q] < 0 || chunk * DCH + my_rr[q] >= d.rows) return -1;
+        const int l = my_l[q] >= 0 ? my_l[q] : (int)lmap[pf_col[q] - d.cbase];
+        return my_rr[q] * ldD + l;
     };
     prefetch(0);
     for(int c = 0; c < nchunks; c++)
@@ -466,18 +471,28 @@ assemble_items_dmma_kernel(DevProblem P, NormalBuffers N, int ldD, const double*
         if(tid < DCH) D[tid * ldD + ntot] = pf_x;
         __syncthreads();
         if(c + 1 < nchunks) prefetch(c + 1);
+        // tiles in groups of 4: the operand pointers are formed once per tile, and the 4 accumulator
+        // chains are independent, so the DMMAs of a group issue back to back
 #pragma unroll
-        for(int i = 0; i < kDmmaMaxTiles; i++)
+        for(int i0 = 0; i0 < kDmmaMaxTiles; i0 += 4)
         {
-            if(i < my_ntiles)   // warp-uniform; compile-time i keeps acc[] in registers
-            {
-                const int q = warp + 8 * i;
-                const double* Da = D + 8 * s_ti[q] + g;     // A operand: element (row g of the tile, k = t) = D[k][8 ti + g]
-                const double* Db = D + 8 * s_tj[q] + g;     // B operand: element (k = t, col g)            = D[k][8 tj + g]
+            if(i0 >= my_ntiles) continue;   // warp-uniform
+            const double* Da[4];
+            const double* Db[4];
 #pragma unroll
-                for(int ks = 0; ks < DCH / 4; ks++)
-                    dmma884(acc[i][0], acc[i][1], Da[(ks * 4 + t) * ldD], Db[(ks * 4 + t) * ldD]);
+            for(int u = 0; u < 4; u++)
+            {
+                // past the warp's last tile: aim at tile 0 (harmless work into an accumulator that is never read)
+                const int q = (i0 + u < my_ntiles && i0 + u < kDmmaMaxTiles) ? warp + 8 * (i0 + u) : 0;
+                Da[u] = D + 8 * s_ti[q] + g + t * ldD;     // A operand: element (row g of the tile, k = t) = D[k][8 ti + g]
+                Db[u] = D + 8 * s_tj[q] + g + t * ldD;     // B operand: element (k = t, col g)            = D[k][8 tj + g]
             }
+#pragma unroll
+            for(int ks = 0; ks < DCH / 4; ks++)
+#pragma unroll
+                for(int u = 0; u < 4; u++)
+                    if(i0 + u < kDmmaMaxTiles)
+                        dmma884(acc[i0 + u][0], acc[i0 + u][1], Da[u][ks * 4 * ldD], Db[u][ks * 4 * ldD]);
         }
         __syncthreads();
         // un-scatter: cheaper than clearing the whole chunk
@@ -698,7 +713,7 @@ schur_groups_kernel(NormalBuffers N, double lambda)
         if(!s_ok) { atomicCAS(N.info, 0, 1000000000 + grp); for(int i = 0; i < 36; i++) Dinv[i] = 0.; }
         for(int i = 0; i < 36; i++) s_Dinv[i] = Dinv[i];
         // the eliminated part of the full gradient
-        for(int p = 0; p < nelim; p++) N.g_full[N.e0 + (grp < N.Nframe_groups ? 6 * grp : 6 * N.Nframe_groups + 3 * (grp - N.Nframe_groups)) + p] = s_gf[p];
+        for(int p = 0; p < nelim && blockIdx.y == 0; p++) N.g_full[N.e0 + (grp < N.Nframe_groups ? 6 * grp : 6 * N.Nframe_groups + 3 * (grp - N.Nframe_groups)) + p] = s_gf[p];
         for(int p = 0; p < 6; p++)
         {
             double t = 0.;
@@ -707,11 +722,15 @@ schur_groups_kernel(NormalBuffers N, double lambda)
         }
     }
     __syncthreads();
-    if(tid < 36) N.grp_Dinv[(size_t)grp * 36 + tid] = s_Dinv[tid];
-    if(tid < 6)  N.grp_gf[(size_t)grp * 6 + tid] = s_gf[tid];
+    if(blockIdx.y == 0)
+    {
+        if(tid < 36) N.grp_Dinv[(size_t)grp * 36 + tid] = s_Dinv[tid];
+        if(tid < 6)  N.grp_gf[(size_t)grp * 6 + tid] = s_gf[tid];
+    }
 
     double* C1 = dsm;   // [6][cap]: Dinv B1
-    for(int a1 = i0; a1 < i1; a1++)
+    // blockIdx.y picks the pairs (a1, a2 <= a1) with a1 = i0 + blockIdx.y, + gridDim.y, ...: more CTAs than groups
+    for(int a1 = i0 + blockIdx.y; a1 < i1; a1 += gridDim.y)
     {
         const int w1 = N.grp_items[a1];
         const int n1 = N.wi_nsh[w1];
@@ -805,6 +824,12 @@ __global__ void scatter_shared_kernel(NormalBuffers N, const double* __restrict_
     if(r < N.n_r) N.g_full[N.state_index(r)] = buf[r];
 }
 
+__global__ void augment_rhs_kernel(NormalBuffers N)
+{
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if(c < N.n_c) N.S[(size_t)N.n_c * N.ldS + c] = -N.gs[c];
+}
+
 bool normal_assemble(const DevProblem& dp, NormalBuffers& N, const EvalBuffers& op, const int* d_rowptr,
                      double lambda, cudaStream_t s, int* nlaunch)
 {
@@ -840,7 +865,8 @@ bool normal_assemble(const DevProblem& dp, NormalBuffers& N, const EvalBuffers& 
     MB200_CUDA_CHECK(cudaMemcpyAsync(N.h_stat, N.stat, 2 * sizeof(int), cudaMemcpyDeviceToHost, s));
     MB200_CUDA_CHECK(cudaStreamSynchronize(s));
     N.n_c = N.h_stat[0];
-    N.ldS = chol_padded(N.n_c > 0 ? N.n_c : 1);
+    // one padding row is always there: it carries the right-hand side through the factorization
+    N.ldS = chol_padded(N.n_c + 1);
     const int max_ntot = N.h_stat[1];
 
     // ---- pass 2: Gram matrices -> S, g', B, D
@@ -893,7 +919,7 @@ bool normal_assemble(const DevProblem& dp, NormalBuffers& N, const EvalBuffers& 
     }
     if(N.Ngroups > 0)
     {
-        schur_groups_kernel<<<N.Ngroups, 256, smem_schur, s>>>(N, lambda);
+        schur_groups_kernel<<<dim3(N.Ngroups, N.schur_split), 256, smem_schur, s>>>(N, lambda);
         (*nlaunch)++;
     }
     if(comm_active())
@@ -918,6 +944,28 @@ bool normal_assemble(const DevProblem& dp, NormalBuffers& N, const EvalBuffers& 
         set_diagonal_kernel<<<(N.n_c + 255) / 256, 256, 0, s>>>(N.S, N.ldS, 0, N.n_c, lambda, true);
         (*nlaunch)++;
     }
+    // The forward substitution for free: -g' goes in as row n_c (a padding row) of S. After the
+    // factorization that row of L is y' with L y = -g', because the panel TRSM treats it like any
+    // other row. Only the backward substitution is left to do explicitly.
+    if(N.n_c > 0)
+    {
+        augment_rhs_kernel<<<(N.n_c + 255) / 256, 256, 0, s>>>(N);
+        (*nlaunch)++;
+    }
+    MB200_CUDA_CHECK(cudaGetLastError());
+    return true;
+}
+
+// y (the forward-substituted right-hand side) out of row n_c of the factor; padding 0
+__global__ void extract_y_kernel(NormalBuffers N, double* __restrict__ rhs)
+{
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if(c < N.ldS) rhs[c] = c < N.n_c ? N.S[(size_t)N.n_c * N.ldS + c] : 0.;
+}
+bool normal_extract_y(const NormalBuffers& N, double* rhs, cudaStream_t s, int* nlaunch)
+{
+    extract_y_kernel<<<(N.ldS + 255) / 256, 256, 0, s>>>(N, rhs);
+    (*nlaunch)++;
     MB200_CUDA_CHECK(cudaGetLastError());
     return true;
 }

@@ -35,6 +35,7 @@ struct NormalBuffers
     double* wi_gf;    // [Nwi][6]
 
     int     Ngroups, Nframe_groups;
+    int     schur_split;   // CTAs per group in the Schur kernel (<= most items in any group)
     int*    grp_ptr;    // [Ngroups+1]
     int*    grp_items;  // work item ids
     double* grp_Dinv;   // [Ngroups][36]
@@ -48,6 +49,8 @@ struct NormalBuffers
 // Updates N.n_c / N.ldS (one small device->host read)
 bool normal_assemble(const DevProblem& dp, NormalBuffers& N, const EvalBuffers& op, const int* d_rowptr,
                      double lambda, cudaStream_t s, int* nlaunch);
+// rhs <- y, L y = -g': read from the augmented row of the factor (valid after chol_factor)
+bool normal_extract_y(const NormalBuffers& N, double* rhs, cudaStream_t s, int* nlaunch);
 // rhs <- -g' (compact numbering, ldS entries)
 bool normal_rhs(const NormalBuffers& N, double* rhs, cudaStream_t s, int* nlaunch);
 // full-length Gauss-Newton step from the compact solution: active shared unknowns, inactive shared

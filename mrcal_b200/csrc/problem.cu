@@ -205,7 +205,7 @@ mrcal_b200_problem_create(const double* intrinsics, const mrcal_pose_t* rt_cam_r
               A.alloc(&d_imagersizes, 2 * (size_t)d.Ncam_i) &&
               A.alloc(&dp.u_intr, (size_t)d.Ncam_i * L.Nintr) && A.alloc(&dp.u_rtcam, 6 * (size_t)d.Ncam_e) &&
               A.alloc(&dp.u_rtframe, 6 * (size_t)d.Nframes) && A.alloc(&dp.u_points, 3 * (size_t)d.Npoints) &&
-              A.alloc(&dp.u_warp, 2, true);
+              A.alloc(&dp.u_warp, 2, true) && A.alloc(&dp.u_rot_frame, 36 * (size_t)d.Nframes) && A.alloc(&dp.u_rot_cam, 36 * (size_t)d.Ncam_e);
     for(int k = 0; k < 2 && ok; k++)
         ok = A.alloc(&P->op[k].p, L.Nstate, true) && A.alloc(&P->op[k].x, L.Nmeas, true) &&
              A.alloc(&P->op[k].Jval, P->nnz) && A.alloc(&P->op[k].Jcol, P->nnz) && A.alloc(&P->op[k].norm2, 1, true);

@@ -60,6 +60,8 @@ struct DevProblem
     double* u_rtframe;   // [Nframes][6]
     double* u_points;    // [Npoints][3]
     double* u_warp;      // [2]
+    double* u_rot_frame; // [Nframes][36]  R (9) then dR/dr (27) of each frame's Rodrigues vector
+    double* u_rot_cam;   // [Ncam_e][36]   same for each camera
 };
 
 // One set of evaluation outputs ("operating point" in libdogleg's language)

@@ -151,10 +151,11 @@ static bool build_workspace(mrcal_b200_problem* P)
     N.e0 = elim ? (L.i_frame0 >= 0 ? L.i_frame0 : L.i_point0) : L.Nstate;
     N.e1 = elim ? N.e0 + (L.i_frame0 >= 0 ? 6 * L.d.Nframes : 0) + (L.i_point0 >= 0 ? 3 * L.Npoints_variable : 0) : L.Nstate;
     N.n_r = L.Nstate - (N.e1 - N.e0);
-    N.ldS_max = chol_padded(N.n_r > 0 ? N.n_r : 1);
+    N.ldS_max = chol_padded(N.n_r + 1);
     N.ldS = N.ldS_max;
     N.n_c = N.n_r;
     N.splined = L.splined;
+    N.schur_split = 1;
     // gs | gsh contiguous (one reduction)
     N.cap = L.Nintr_state + 8;
     N.Nframe_groups = (elim && L.i_frame0 >= 0) ? L.d.Nframes : 0;
@@ -176,10 +177,12 @@ static bool build_workspace(mrcal_b200_problem* P)
             }
         for(int g = 0; g < N.Ngroups; g++)
         {
+            if((int)buckets[g].size() > N.schur_split) N.schur_split = (int)buckets[g].size();
             ptr[g] = (int)items.size();
             items.insert(items.end(), buckets[g].begin(), buckets[g].end());
         }
         ptr[N.Ngroups] = (int)items.size();
+        if(N.schur_split > 8) N.schur_split = 8;
     }
 
     bool ok = A.alloc(&N.S, (size_t)N.ldS_max * N.ldS_max) && A.alloc(&N.gs, 2 * (size_t)N.ldS_max, true) && A.alloc(&N.g_full, L.Nstate, true) &&
@@ -408,8 +411,8 @@ static bool dogleg_pass(mrcal_b200_problem* P, const mrcal_b200_solver_parameter
                         if(!assemble(P->cur)) return false;
                     }
                     const int a = T->mark();
-                    if(!normal_rhs(N, ws->rhs, s, nl)) return false;
-                    if(N.n_c > 0 && !chol_solve(N.S, N.ldS, ws->invL, ws->rhs, N.ldS, 1, s, nl)) return false;
+                    if(!normal_extract_y(N, ws->rhs, s, nl)) return false;
+                    if(N.n_c > 0 && !chol_solve_backward(N.S, N.ldS, ws->invL, ws->rhs, N.ldS, s, nl)) return false;
                     if(!normal_expand_step(P->dp, N, P->op[P->cur], *lambda, ws->rhs, ws->ds_r, ws->step_gn, s, nl)) return false;
                     dots_kernel<<<3, 1024, 0, s>>>(ws->step_gn, N.g_full, e0, e1, Nstate, ws->scal + 11);
                     (*nl)++;
