@@ -235,39 +235,45 @@ __device__ __forceinline__ void dmma(double& c0, double& c1, double a, double b)
                  : "+d"(c0), "+d"(c1) : "d"(a), "d"(b));
 }
 
-__global__ void __launch_bounds__(256, 1)
+// TILE = 128: 8 warps as 4 x 2, warp tile 32 x 64 (4 x 8 DMMA tiles)   -- large trailing matrices
+// TILE =  64: 8 warps as 4 x 2, warp tile 16 x 32 (2 x 4 DMMA tiles)   -- small ones: 4x the CTAs, so the
+//             update spreads over the whole chip instead of a few dozen SMs
+template <int TILE>
+__global__ void __launch_bounds__(256, TILE == 128 ? 1 : 2)
 syrk_dmma_kernel(double* __restrict__ A, int ld, int n, int c0, int c1, int k0, int k1)
 {
+    constexpr int MI = TILE / 32, NJ = TILE / 16;    // DMMA tiles per warp along m, n
+    constexpr int WM = TILE / 4, WN = TILE / 2;      // warp tile
     const int tj = blockIdx.x, ti = blockIdx.y;
     if(ti < tj) return;
     extern __shared__ __align__(16) double smem[];
-    double* sA = smem;                               // [STAGES][BM][LDS]
-    double* sB = smem + (size_t)STAGES * BM * LDS;   // [STAGES][BM][LDS]
+    double* sA = smem;                                 // [STAGES][TILE][LDS]
+    double* sB = smem + (size_t)STAGES * TILE * LDS;   // [STAGES][TILE][LDS]
 
-    const int row0 = c0 + ti * BM, col0 = c0 + tj * BM;
+    const int row0 = c0 + ti * TILE, col0 = c0 + tj * TILE;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int wm = warp >> 1, wn = warp & 1;   // 4 x 2 warps
     const int g = lane >> 2, t = lane & 3;
 
-    double acc[4][8][2];
+    double acc[MI][NJ][2];
 #pragma unroll
-    for(int i = 0; i < 4; i++)
+    for(int i = 0; i < MI; i++)
 #pragma unroll
-        for(int j = 0; j < 8; j++) acc[i][j][0] = acc[i][j][1] = 0.;
+        for(int j = 0; j < NJ; j++) acc[i][j][0] = acc[i][j][1] = 0.;
 
     const int nk = (k1 - k0) / BK;
-    // each thread copies 4 x 16B per operand per stage: 128 rows x 8 chunks = 1024 chunks
+    // TILE rows x 8 chunks of 16 B per operand per stage
     auto load_stage = [&](int stage, int kb)
     {
         const int kk = k0 + kb * BK;
 #pragma unroll
-        for(int it = 0; it < 4; it++)
+        for(int it = 0; it < TILE / 32; it++)
         {
             const int chunk = tid + it * 256;
             const int r = chunk >> 3, cc = (chunk & 7) * 2;
             const int gi = row0 + r, gj = col0 + r;
-            cp_async16(&sA[((size_t)stage * BM + r) * LDS + cc], &A[(size_t)(gi < n ? gi : 0) * ld + kk + cc], gi < n);
-            cp_async16(&sB[((size_t)stage * BM + r) * LDS + cc], &A[(size_t)(gj < c1 ? gj : 0) * ld + kk + cc], gj < c1);
+            cp_async16(&sA[((size_t)stage * TILE + r) * LDS + cc], &A[(size_t)(gi < n ? gi : 0) * ld + kk + cc], gi < n);
+            cp_async16(&sB[((size_t)stage * TILE + r) * LDS + cc], &A[(size_t)(gj < c1 ? gj : 0) * ld + kk + cc], gj < c1);
         }
     };
 #pragma unroll
@@ -285,34 +291,34 @@ syrk_dmma_kernel(double* __restrict__ A, int ld, int n, int c0, int c1, int k0, 
             if(nxt < nk) load_stage(nxt % STAGES, nxt);
             cp_async_commit();
         }
-        const double* a_s = &sA[((size_t)(kb % STAGES) * BM + wm * 32) * LDS];
-        const double* b_s = &sB[((size_t)(kb % STAGES) * BM + wn * 64) * LDS];
+        const double* a_s = &sA[((size_t)(kb % STAGES) * TILE + wm * WM) * LDS];
+        const double* b_s = &sB[((size_t)(kb % STAGES) * TILE + wn * WN) * LDS];
 #pragma unroll
         for(int ks = 0; ks < BK / 4; ks++)
         {
-            double af[4], bf[8];
+            double af[MI], bf[NJ];
 #pragma unroll
-            for(int i = 0; i < 4; i++) af[i] = a_s[(i * 8 + g) * LDS + ks * 4 + t];
+            for(int i = 0; i < MI; i++) af[i] = a_s[(i * 8 + g) * LDS + ks * 4 + t];
 #pragma unroll
-            for(int j = 0; j < 8; j++) bf[j] = b_s[(j * 8 + g) * LDS + ks * 4 + t];
+            for(int j = 0; j < NJ; j++) bf[j] = b_s[(j * 8 + g) * LDS + ks * 4 + t];
 #pragma unroll
-            for(int i = 0; i < 4; i++)
+            for(int i = 0; i < MI; i++)
 #pragma unroll
-                for(int j = 0; j < 8; j++) dmma(acc[i][j][0], acc[i][j][1], af[i], bf[j]);
+                for(int j = 0; j < NJ; j++) dmma(acc[i][j][0], acc[i][j][1], af[i], bf[j]);
         }
     }
     cp_async_wait<0>();
 
     // C -= acc, lower triangle only
 #pragma unroll
-    for(int i = 0; i < 4; i++)
+    for(int i = 0; i < MI; i++)
     {
-        const int gi = row0 + wm * 32 + i * 8 + g;
+        const int gi = row0 + wm * WM + i * 8 + g;
         if(gi >= n) continue;
 #pragma unroll
-        for(int j = 0; j < 8; j++)
+        for(int j = 0; j < NJ; j++)
         {
-            const int gj = col0 + wn * 64 + j * 8 + 2 * t;
+            const int gj = col0 + wn * WN + j * 8 + 2 * t;
             if(gj >= c1) continue;
             double* p = &A[(size_t)gi * ld + gj];
             if(gj + 1 <= gi)
@@ -328,14 +334,15 @@ syrk_dmma_kernel(double* __restrict__ A, int ld, int n, int c0, int c1, int k0, 
     }
 }
 
-static const size_t kSyrkSmem = (size_t)2 * STAGES * BM * LDS * sizeof(double);
+static const size_t kSyrkSmem = (size_t)2 * STAGES * BM * LDS * sizeof(double);   // TILE = 128; half of it for TILE = 64
 static const size_t kBlockSmem = (size_t)2 * NB * (NB + 1) * sizeof(double);   // potrf_diag / trsm
 
 static bool configure_kernels()
 {
     static bool configured = false;
     if(configured) return true;
-    MB200_CUDA_CHECK(cudaFuncSetAttribute(syrk_dmma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSyrkSmem));
+    MB200_CUDA_CHECK(cudaFuncSetAttribute(syrk_dmma_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSyrkSmem));
+    MB200_CUDA_CHECK(cudaFuncSetAttribute(syrk_dmma_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSyrkSmem));
     MB200_CUDA_CHECK(cudaFuncSetAttribute(trsm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kBlockSmem));
     MB200_CUDA_CHECK(cudaFuncSetAttribute(potrf_diag_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kBlockSmem));
     configured = true;
@@ -345,8 +352,18 @@ static bool configure_kernels()
 static bool syrk_update(double* A, int ld, int n, int c0, int c1, int k0, int k1, cudaStream_t s, int* nlaunch)
 {
     if(c1 <= c0 || n <= c0) return true;
-    dim3 grid((c1 - c0 + BM - 1) / BM, (n - c0 + BM - 1) / BM);
-    syrk_dmma_kernel<<<grid, 256, kSyrkSmem, s>>>(A, ld, n, c0, c1, k0, k1);
+    // big tiles when they fill the chip twice over, small tiles otherwise
+    const long nt128 = (long)((c1 - c0 + 127) / 128) * ((n - c0 + 127) / 128);
+    if(nt128 >= 2 * 148)
+    {
+        dim3 grid((c1 - c0 + 127) / 128, (n - c0 + 127) / 128);
+        syrk_dmma_kernel<128><<<grid, 256, kSyrkSmem, s>>>(A, ld, n, c0, c1, k0, k1);
+    }
+    else
+    {
+        dim3 grid((c1 - c0 + 63) / 64, (n - c0 + 63) / 64);
+        syrk_dmma_kernel<64><<<grid, 256, kSyrkSmem / 2, s>>>(A, ld, n, c0, c1, k0, k1);
+    }
     if(nlaunch) (*nlaunch)++;
     return true;
 }
