@@ -4,12 +4,76 @@
 
 using namespace mb200;
 
+#include <mutex>
+
 namespace {
-struct ProblemGuard
+// The reference-named entry points are called over and over with problems of the same shape
+// (mrcal-calibrate-cameras solves 5-6 times; the uncertainty tools hundreds of times). Creating a
+// device problem means ~0.7 GB of cudaMalloc, pinned allocations and CUDA-graph captures: ~0.5 s.
+// So the last problem is kept and re-used when the next call has the same shape; only the values
+// (seed, observations) are re-uploaded. One entry, guarded by a mutex: the reference is single-threaded.
+struct ProblemCache
 {
-    mrcal_b200_problem_t* p;
-    ~ProblemGuard() { mrcal_b200_problem_destroy(p); }
-};
+    std::mutex mtx;
+    mrcal_b200_problem_t* p = nullptr;
+    std::vector<int> imagersizes;
+    bool have_warp = false;
+    double spacing = 0.;
+    ~ProblemCache() { /* the CUDA context may already be gone at process exit: leak on purpose */ }
+} g_cache;
+
+mrcal_b200_problem_t* acquire_problem(const double* intrinsics, const mrcal_pose_t* rt_cam_ref, const mrcal_pose_t* rt_ref_frame,
+                                      const mrcal_point3_t* points, const mrcal_calobject_warp_t* calobject_warp,
+                                      int Ncam_i, int Ncam_e, int Nframes, int Npoints, int Npoints_fixed,
+                                      const mrcal_observation_board_t* ob, const mrcal_observation_point_t* op,
+                                      int Nob, int Nop, const mrcal_point3_t* pool_b, const mrcal_point3_t* pool_p,
+                                      const mrcal_lensmodel_t* lensmodel, const int* imagersizes,
+                                      mrcal_problem_selections_t sel, double spacing, int W, int H)
+{
+    if(Nob < 0) Nob = 0;
+    if(Nop < 0) Nop = 0;
+    mrcal_b200_problem_t* P = g_cache.p;
+    bool same = P != nullptr;
+    if(same)
+    {
+        const Dims& d = P->L.d;
+        mrcal_problem_selections_t s2 = sel;
+        if(Nob <= 0) s2.do_optimize_calobject_warp = false;
+        same = d.Ncam_i == Ncam_i && d.Ncam_e == Ncam_e && d.Nframes == Nframes && d.Npoints == Npoints &&
+               d.Npoints_fixed == Npoints_fixed && d.Nobs_board == Nob && d.Nobs_point == Nop &&
+               (Nob == 0 || (d.W == W && d.H == H)) &&
+               memcmp(&P->L.lensmodel, lensmodel, sizeof(*lensmodel)) == 0 &&
+               memcmp(&P->L.sel, &s2, sizeof(s2)) == 0 &&
+               g_cache.have_warp == (calobject_warp != nullptr) && g_cache.spacing == spacing &&
+               (int)g_cache.imagersizes.size() == 2 * Ncam_i &&
+               (Ncam_i == 0 || memcmp(g_cache.imagersizes.data(), imagersizes, 2 * Ncam_i * sizeof(int)) == 0) &&
+               !P->sharded;
+        for(int i = 0; same && i < Nob; i++)
+            same = P->h_obs_board[3 * i] == ob[i].icam.intrinsics &&
+                   P->h_obs_board[3 * i + 1] == (ob[i].icam.extrinsics < 0 ? -1 : ob[i].icam.extrinsics) &&
+                   P->h_obs_board[3 * i + 2] == ob[i].iframe;
+        for(int i = 0; same && i < Nop; i++)
+            same = P->h_obs_point[3 * i] == op[i].icam.intrinsics &&
+                   P->h_obs_point[3 * i + 1] == (op[i].icam.extrinsics < 0 ? -1 : op[i].icam.extrinsics) &&
+                   P->h_obs_point[3 * i + 2] == op[i].i_point;
+    }
+    if(same)
+    {
+        if(!mrcal_b200_problem_upload(P, intrinsics, rt_cam_ref, rt_ref_frame, points, calobject_warp, pool_b, pool_p))
+            return nullptr;
+        return P;
+    }
+    if(P) { mrcal_b200_problem_destroy(P); g_cache.p = nullptr; }
+    P = mrcal_b200_problem_create(intrinsics, rt_cam_ref, rt_ref_frame, points, calobject_warp,
+                                  Ncam_i, Ncam_e, Nframes, Npoints, Npoints_fixed, ob, op, Nob, Nop, pool_b, pool_p,
+                                  lensmodel, imagersizes, sel, spacing, W, H);
+    if(P == nullptr) return nullptr;
+    g_cache.p = P;
+    g_cache.imagersizes.assign(imagersizes, imagersizes + 2 * Ncam_i);
+    g_cache.have_warp = calobject_warp != nullptr;
+    g_cache.spacing = spacing;
+    return P;
+}
 
 bool have_triangulated(const mrcal_observation_point_triangulated_t* o, int N) { return o != nullptr && N > 0; }
 }  // namespace
@@ -47,7 +111,8 @@ extern "C" bool mrcal_optimizer_callback(double* b_packed, int buffer_size_b_pac
         set_error("mrcal_optimizer_callback(): b_packed and x may not be NULL");
         return false;
     }
-    ProblemGuard g{mrcal_b200_problem_create(intrinsics, rt_cam_ref, rt_ref_frame, points, calobject_warp,
+    std::lock_guard<std::mutex> lock(g_cache.mtx);
+    struct { mrcal_b200_problem_t* p; } g{acquire_problem(intrinsics, rt_cam_ref, rt_ref_frame, points, calobject_warp,
                                              Ncameras_intrinsics, Ncameras_extrinsics, Nframes, Npoints, Npoints_fixed,
                                              observations_board, observations_point, Nobservations_board, Nobservations_point,
                                              observations_board_pool, observations_point_pool, lensmodel, imagersizes,
@@ -110,7 +175,8 @@ extern "C" mrcal_stats_t mrcal_optimize(double* b_packed_final, int buffer_size_
         set_error("ERROR: triangulated points are not implemented in the CUDA path yet");
         return bad;
     }
-    ProblemGuard g{mrcal_b200_problem_create(intrinsics, rt_cam_ref, rt_ref_frame, points, calobject_warp,
+    std::lock_guard<std::mutex> lock(g_cache.mtx);
+    struct { mrcal_b200_problem_t* p; } g{acquire_problem(intrinsics, rt_cam_ref, rt_ref_frame, points, calobject_warp,
                                              Ncameras_intrinsics, Ncameras_extrinsics, Nframes, Npoints, Npoints_fixed,
                                              observations_board, observations_point, Nobservations_board, Nobservations_point,
                                              observations_board_pool, observations_point_pool, lensmodel, imagersizes,
