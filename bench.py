@@ -246,6 +246,30 @@ def main():
 
     ###### e2e: the reference-facing call with host buffers, H2D + D2H inside the timed region
     e2e = None
+    if world > 1:
+        # sharded: the public multi-GPU API (mrcal_b200.distributed): each step re-uploads this rank's host
+        # inputs, solves, and brings the solution back (D2H + all-gather of the frame poses)
+        from mrcal_b200 import distributed
+        h2d = sum(v.nbytes for v in kw_local.values() if isinstance(v, np.ndarray))
+        e_it, e_s, d2h = 0, 0.0, 0
+        for i in range(args.warmup + args.steps):
+            flush.zero_()
+            barrier()
+            t0 = time.perf_counter()
+            P.upload()
+            st = P.optimize(max_iterations=args.max_iterations)
+            sol = distributed.gather_solution(P, shard)
+            barrier()
+            dt = time.perf_counter() - t0
+            if i >= args.warmup:
+                e_s += dt
+                e_it += st["Niterations"]
+                d2h = sum(v.nbytes for v in sol.values() if isinstance(v, np.ndarray)) + 8 * (P.Nstate + P.Nmeasurements)
+        t = torch.tensor([e_s], device="cuda", dtype=torch.float64)
+        torch.distributed.all_reduce(t, op=torch.distributed.ReduceOp.MAX)
+        e2e = {"value": e_it / float(t.item()), "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
+               "ms_per_step": 1e3 * float(t.item()) / args.steps,
+               "call": "mrcal_b200.distributed: Problem.upload() + Problem.optimize() + gather_solution(), per-rank host numpy buffers"}
     if world == 1:
         names = ("intrinsics", "rt_cam_ref", "rt_ref_frame", "calobject_warp", "observations_board")
         pinned = {n: torch.from_numpy(kw[n].copy()).pin_memory() for n in names}
@@ -271,7 +295,11 @@ def main():
                "ms_per_step": 1e3 * e_s / args.steps,
                "call": "mrcal_b200.optimize(**optimization_inputs) -> C-ABI mrcal_optimize(), host numpy buffers"}
 
+    if world > 1:
+        torch.distributed.barrier()
     if rank != 0:
+        if world > 1:
+            torch.distributed.destroy_process_group()
         return 0
 
     ###### roofline of the dominant kernel family
@@ -322,6 +350,8 @@ def main():
                                       for k in ("ms_evaluate", "ms_assemble", "ms_factor", "ms_solve")},
            "clocks": clocks, "e2e": e2e, "roofline": roofline, "roofline_jacobian_fill": fill, "cpu_baseline": cpu}
     print(json.dumps(out))
+    if world > 1:
+        torch.distributed.destroy_process_group()
     return 0
 
 

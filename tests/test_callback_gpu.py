@@ -65,7 +65,7 @@ def test_callback_matches_reference_golden_vectors(i):
     assert np.allclose(J2, J.toarray(), rtol=1e-14, atol=0)
 
 
-@pytest.mark.parametrize("config", [1, 2, 3])
+@pytest.mark.parametrize("config", [1, 2, 3, 5])
 def test_callback_matches_compiled_reference_at_baseline_sizes(ref, config):
     """BASELINE.json configs 1-3 at full size against the compiled reference (oracle/_ref)."""
     kw, _ = synthetic.baseline_config(config)
