@@ -91,6 +91,7 @@ enum LensKind
     LENS_PINHOLE = 0, LENS_STEREOGRAPHIC, LENS_LONLAT, LENS_LATLON,
     LENS_OPENCV4, LENS_OPENCV5, LENS_OPENCV8, LENS_OPENCV12,
     LENS_SPLINED3, LENS_SPLINED2,
+    LENS_CAHVOR,
     LENS_NKINDS
 };
 
@@ -99,6 +100,7 @@ template <> struct LensTraits<LENS_OPENCV4>  { static constexpr int NDIST = 4;  
 template <> struct LensTraits<LENS_OPENCV5>  { static constexpr int NDIST = 5;  static constexpr bool SPLINED = false; static constexpr int RUN = 0; };
 template <> struct LensTraits<LENS_OPENCV8>  { static constexpr int NDIST = 8;  static constexpr bool SPLINED = false; static constexpr int RUN = 0; };
 template <> struct LensTraits<LENS_OPENCV12> { static constexpr int NDIST = 12; static constexpr bool SPLINED = false; static constexpr int RUN = 0; };
+template <> struct LensTraits<LENS_CAHVOR>   { static constexpr int NDIST = 5;  static constexpr bool SPLINED = false; static constexpr int RUN = 0; };
 template <> struct LensTraits<LENS_SPLINED3> { static constexpr int NDIST = 0;  static constexpr bool SPLINED = true;  static constexpr int RUN = 4; };
 template <> struct LensTraits<LENS_SPLINED2> { static constexpr int NDIST = 0;  static constexpr bool SPLINED = true;  static constexpr int RUN = 3; };
 
@@ -169,6 +171,77 @@ __device__ __forceinline__ void project_parametric(double q[2], double dq_dp[2][
         dq_dp[1][0] = 0.; dq_dp[1][1] = fy * yz2i * p[2]; dq_dp[1][2] = -fy * yz2i * p[1];
         q[0] = asin(p[0] * ni) * fx + cx;
         q[1] = atan2(p[1], p[2]) * fy + cy;
+    }
+    else if constexpr(KIND == LENS_CAHVOR)
+    {
+        // JPL CAHVOR in mrcal's parametrisation (mrcal.c:1067-1240): distortions (alpha, beta, r0, r1, r2).
+        //   o = optical axis from (alpha,beta); w = p.o ; tau = |p|^2/w^2 - 1 ; mu = r0 + r1 tau + r2 tau^2
+        //   p' = p + mu (p - w o) ; q = pinhole(p')
+        const double al = intr[4], be = intr[5], r0 = intr[6], r1 = intr[7], r2 = intr[8];
+        double sa, ca, sb, cb;
+        sincos(al, &sa, &ca);
+        sincos(be, &sb, &cb);
+        const double o[3]   = {sa * cb, sb, ca * cb};
+        const double o_a[3] = {ca * cb, 0., -sa * cb};
+        const double o_b[3] = {-sa * sb, cb, -ca * sb};
+        const double n2 = p[0] * p[0] + p[1] * p[1] + p[2] * p[2];
+        const double w = p[0] * o[0] + p[1] * o[1] + p[2] * o[2];
+        const double wi = 1. / w;
+        const double tau = n2 * wi * wi - 1.;
+        const double mu = r0 + tau * (r1 + tau * r2);
+        const double dmu = r1 + 2. * tau * r2;                       // d mu / d tau
+        double u[3], pd[3], dmu_dp[3];
+#pragma unroll
+        for(int i = 0; i < 3; i++)
+        {
+            u[i] = p[i] - w * o[i];
+            pd[i] = p[i] + mu * u[i];
+            dmu_dp[i] = dmu * (2. * p[i] * wi * wi - 2. * n2 * wi * wi * wi * o[i]);
+        }
+        const double zi = 1. / pd[2];
+        q[0] = pd[0] * zi * fx + cx;
+        q[1] = pd[1] * zi * fy + cy;
+        // dq/dp' (pinhole) then dp'/dp = (1+mu) I - mu o o' + u dmu_dp'
+        const double gx[3] = {fx * zi, 0., -fx * pd[0] * zi * zi};
+        const double gy[3] = {0., fy * zi, -fy * pd[1] * zi * zi};
+#pragma unroll
+        for(int j = 0; j < 3; j++)
+        {
+            double cxj = 0., cyj = 0.;
+#pragma unroll
+            for(int i = 0; i < 3; i++)
+            {
+                const double d = (i == j ? 1. + mu : 0.) - mu * o[i] * o[j] + u[i] * dmu_dp[j];
+                cxj += gx[i] * d;
+                cyj += gy[i] * d;
+            }
+            dq_dp[0][j] = cxj;
+            dq_dp[1][j] = cyj;
+        }
+        if(dq_ddist != nullptr)
+        {
+            // dp'/d(alpha,beta): w_t = p.o_t ; tau_t = -2 |p|^2 w_t / w^3 ; dp' = dmu tau_t u - mu (w_t o + w o_t)
+            const double w_a = p[0] * o_a[0] + p[1] * o_a[1] + p[2] * o_a[2];
+            const double w_b = p[0] * o_b[0] + p[1] * o_b[1] + p[2] * o_b[2];
+            const double mu_a = dmu * (-2. * n2 * wi * wi * wi) * w_a;
+            const double mu_b = dmu * (-2. * n2 * wi * wi * wi) * w_b;
+            double d[5][3];
+#pragma unroll
+            for(int i = 0; i < 3; i++)
+            {
+                d[0][i] = mu_a * u[i] - mu * (w_a * o[i] + w * o_a[i]);
+                d[1][i] = mu_b * u[i] - mu * (w_b * o[i] + w * o_b[i]);
+                d[2][i] = u[i];
+                d[3][i] = tau * u[i];
+                d[4][i] = tau * tau * u[i];
+            }
+#pragma unroll
+            for(int k = 0; k < 5; k++)
+            {
+                dq_ddist[0][k] = gx[0] * d[k][0] + gx[2] * d[k][2];
+                dq_ddist[1][k] = gy[1] * d[k][1] + gy[2] * d[k][2];
+            }
+        }
     }
     else
     {

@@ -672,6 +672,7 @@ bool launch_evaluate(const DevProblem& dp, const EvalBuffers& out, bool with_jac
     case LENS_OPENCV12:      launch_kind<LENS_OPENCV12>(dp, out, with_jacobian, stream, nlaunch); break;
     case LENS_SPLINED3:      launch_kind<LENS_SPLINED3>(dp, out, with_jacobian, stream, nlaunch); break;
     case LENS_SPLINED2:      launch_kind<LENS_SPLINED2>(dp, out, with_jacobian, stream, nlaunch); break;
+    case LENS_CAHVOR:        launch_kind<LENS_CAHVOR>(dp, out, with_jacobian, stream, nlaunch); break;
     default: set_error("lens model kind %d has no CUDA implementation", dp.lens_kind); return false;
     }
     const bool splined = dp.lens_kind == LENS_SPLINED3 || dp.lens_kind == LENS_SPLINED2;

@@ -19,6 +19,7 @@ static int lens_kind_of(const mrcal_lensmodel_t* lm)
     case MRCAL_LENSMODEL_OPENCV5:       return LENS_OPENCV5;
     case MRCAL_LENSMODEL_OPENCV8:       return LENS_OPENCV8;
     case MRCAL_LENSMODEL_OPENCV12:      return LENS_OPENCV12;
+    case MRCAL_LENSMODEL_CAHVOR:        return LENS_CAHVOR;
     case MRCAL_LENSMODEL_SPLINED_STEREOGRAPHIC:
         return lm->LENSMODEL_SPLINED_STEREOGRAPHIC__config.order == 3 ? LENS_SPLINED3 :
                lm->LENSMODEL_SPLINED_STEREOGRAPHIC__config.order == 2 ? LENS_SPLINED2 : -1;
@@ -122,7 +123,7 @@ mrcal_b200_problem_create(const double* intrinsics, const mrcal_pose_t* rt_cam_r
     {
         char name[256] = "?";
         mrcal_lensmodel_name(name, sizeof(name), lensmodel);
-        set_error("lens model %s has no CUDA implementation yet (supported: PINHOLE, STEREOGRAPHIC, LONLAT, LATLON, OPENCV4/5/8/12, SPLINED_STEREOGRAPHIC order 2,3)", name);
+        set_error("lens model %s has no CUDA implementation yet (supported: PINHOLE, STEREOGRAPHIC, LONLAT, LATLON, OPENCV4/5/8/12, CAHVOR, SPLINED_STEREOGRAPHIC order 2,3)", name);
         return nullptr;
     }
 

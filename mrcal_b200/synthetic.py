@@ -80,6 +80,14 @@ def project(p, lensmodel, intrinsics):
         s = (1 + k[0] * r2 + k[1] * r4 + k[4] * r6) / (1 + k[5] * r2 + k[6] * r4 + k[7] * r6)
         u = np.stack((xn * s + 2 * k[2] * xn * yn + k[3] * (r2 + 2 * xn * xn) + k[8] * r2 + k[9] * r4,
                       yn * s + k[2] * (r2 + 2 * yn * yn) + 2 * k[3] * xn * yn + k[10] * r2 + k[11] * r4), -1)
+    elif lensmodel == "LENSMODEL_CAHVOR":
+        al, be, r0, r1, r2 = intr[4:9]
+        o = np.array((np.sin(al) * np.cos(be), np.sin(be), np.cos(al) * np.cos(be)))
+        w = p @ o
+        tau = (p * p).sum(-1) / (w * w) - 1.
+        mu = r0 + tau * r1 + tau * tau * r2
+        pd = p + mu[..., None] * (p - w[..., None] * o)
+        u = np.stack((pd[..., 0] / pd[..., 2], pd[..., 1] / pd[..., 2]), -1)
     elif lensmodel == "LENSMODEL_LONLAT":
         u = np.stack((np.arctan2(x, z), np.arcsin(y / np.linalg.norm(p, axis=-1))), -1)
     elif lensmodel == "LENSMODEL_LATLON":
@@ -156,6 +164,8 @@ def true_intrinsics(lensmodel, Ncameras, rng):
         elif lensmodel.startswith("LENSMODEL_OPENCV"):
             n = int(lensmodel[len("LENSMODEL_OPENCV"):])
             out.append(np.concatenate((core, _OPENCV_DIST[:n] * (1. + 0.1 * rng.uniform(-1, 1, n)))))
+        elif lensmodel == "LENSMODEL_CAHVOR":
+            out.append(np.concatenate((core, np.array((0.01, -0.02, 0.0, 0.03, 0.01)) * (1. + 0.1 * rng.uniform(-1, 1, 5)))))
         elif lensmodel in ("LENSMODEL_LONLAT", "LENSMODEL_LATLON"):
             out.append(core * np.array((1., 1., 1., 1.)))
         else:

@@ -52,7 +52,8 @@ def golden_cases():
     for lm, tag in (("LENSMODEL_PINHOLE", "pinhole"), ("LENSMODEL_STEREOGRAPHIC", "stereographic"),
                     ("LENSMODEL_LONLAT", "lonlat"), ("LENSMODEL_LATLON", "latlon"),
                     ("LENSMODEL_OPENCV4", "opencv4"), ("LENSMODEL_OPENCV5", "opencv5"),
-                    ("LENSMODEL_OPENCV8", "opencv8"), ("LENSMODEL_OPENCV12", "opencv12")):
+                    ("LENSMODEL_OPENCV8", "opencv8"), ("LENSMODEL_OPENCV12", "opencv12"),
+                    ("LENSMODEL_CAHVOR", "cahvor")):
         add(f"{tag}_2cam_all", lm, 2, 4, _sel(True, True, True, True, True))
     add("splined3_2cam_corelocked", SPL3, 2, 4, _sel(False, True, True, True, True), outliers=7)
     add("splined3_3cam_all", SPL3, 3, 3, _sel(True, True, True, True, True), which="some")
@@ -72,6 +73,8 @@ def golden_cases():
     add("splined3_points_core", SPL3, 2, 3, _sel(True, True, True, True, True), Npoints=6, Npoints_fixed=2,
         point_outliers=2)
     add("pinhole_points_noframes", "LENSMODEL_PINHOLE", 2, 3, _sel(True, False, True, False, False), Npoints=5)
+    add("cahvor_points", "LENSMODEL_CAHVOR", 3, 3, _sel(True, True, True, True, True), Npoints=6, Npoints_fixed=1,
+        outliers=3, which="some")
     return cases
 
 

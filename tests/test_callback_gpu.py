@@ -80,6 +80,31 @@ def test_callback_matches_compiled_reference_at_baseline_sizes(ref, config):
         assert (len(b), len(x), J.nnz) == (7220, 324800, 9129600)
 
 
+def test_projection_known_answers():
+    """The reference's in-source projection known answers (test/test-projections.py:337-514): project the given
+    camera-frame points with the given intrinsics. Done through the real path: a one-camera problem whose fixed
+    points sit at p, observed at pixel (0,0) with weight 1, so that x = q."""
+    g = np.load(os.path.join(GOLDEN, "projections.npz"))
+    ntested = 0
+    for i in range(int(g["N"])):
+        lm = str(g[f"lensmodel_{i}"])
+        if lm.startswith("LENSMODEL_CAHVORE"):
+            continue    # no CUDA implementation yet
+        intr, p, q_ref = g[f"intrinsics_{i}"], g[f"p_{i}"], g[f"q_{i}"]
+        for k in range(p.shape[0]):
+            ii = np.ascontiguousarray((intr[k] if intr.ndim == 2 else intr)[None, :])
+            kw = dict(lensmodel=lm, intrinsics=ii, imagersizes=np.array(((4000, 2200),), np.int32),
+                      points=np.ascontiguousarray(p[k:k + 1]), Npoints_fixed=1,
+                      observations_point=np.array(((0., 0., 1.),)),
+                      indices_point_camintrinsics_camextrinsics=np.array(((0, 0, -1),), np.int32),
+                      do_optimize_intrinsics_core=True, do_optimize_intrinsics_distortions=False,
+                      do_optimize_frames=False, do_apply_regularization=False)
+            x = mrcal_b200.optimizer_callback(**kw, no_jacobian=True, no_factorization=True)[1]
+            assert np.abs(x[:2] - q_ref[k]).max() < 2e-6 * max(1., np.abs(q_ref[k]).max()), (lm, k, x[:2], q_ref[k])
+            ntested += 1
+    assert ntested >= 27
+
+
 def test_callback_size_independent_properties():
     """Full-size config 3 without the oracle: perfect observations give zero board residuals
     (test-basic-calibration.py:371-382) and J predicts finite differences of x."""
@@ -114,7 +139,7 @@ def test_callback_error_behaviour():
     bad = dict(kw, indices_frame_camintrinsics_camextrinsics=kw["indices_frame_camintrinsics_camextrinsics"][::-1].copy())
     with pytest.raises(RuntimeError, match="monotonically|sequentially"):
         mrcal_b200.optimizer_callback(**bad)
-    bad = dict(kw, lensmodel="LENSMODEL_CAHVOR", intrinsics=np.zeros((2, 9)))
+    bad = dict(kw, lensmodel="LENSMODEL_CAHVORE_linearity=0.40", intrinsics=np.zeros((2, 12)))
     with pytest.raises(RuntimeError, match="no CUDA implementation"):
         mrcal_b200.optimizer_callback(**bad)
     # None-valued kwargs are ignored, as in the reference (mrcal-pywrap.c:1491-1555)

@@ -149,6 +149,6 @@ def test_pack_unpack_matches_reference(ref):
 
 
 def test_corresponding_icam_extrinsics():
-    kw = problems.golden_cases()[9][1]   # 3 cameras, camera 0 at the reference
+    kw = dict(problems.golden_cases())["splined3_3cam_all"]   # 3 cameras, camera 0 at the reference
     assert mrcal_b200.corresponding_icam_extrinsics(0, **kw) == -1
     assert mrcal_b200.corresponding_icam_extrinsics(2, **kw) == 1

@@ -48,7 +48,7 @@ def check_parity(r_gpu, kw_gpu, r_cpu, tol_b=1e-5):
     for name, ref_arr in (("intrinsics", P.intrinsics), ("rt_cam_ref", P.rt_cam_ref), ("rt_ref_frame", P.rt_ref_frame),
                           ("points", P.points), ("calobject_warp", P.calobject_warp)):
         if name in kw_gpu and kw_gpu[name] is not None and np.size(kw_gpu[name]):
-            assert np.allclose(kw_gpu[name], ref_arr, rtol=0, atol=1e-5 * max(1., np.abs(ref_arr).max())), name
+            assert np.allclose(kw_gpu[name], ref_arr, rtol=0, atol=max(tol_b, 1e-5) * max(1., np.abs(ref_arr).max())), name
     if "observations_board" in kw_gpu:
         assert np.array_equal(kw_gpu["observations_board"][..., 2] < 0, P.observations_board[..., 2] < 0)
 
@@ -58,6 +58,7 @@ def check_parity(r_gpu, kw_gpu, r_cpu, tol_b=1e-5):
     ("LENSMODEL_OPENCV4", 3, 6),
     ("LENSMODEL_PINHOLE", 1, 5),
     ("LENSMODEL_STEREOGRAPHIC", 2, 5),
+    ("LENSMODEL_CAHVOR", 2, 8),
     (SPL3_COVERED, 2, 40),
     (SPL2_COVERED, 2, 40),
 ])
@@ -69,7 +70,10 @@ def test_optimize_matches_cpu_restatement(ref, lensmodel, Ncameras, Nframes):
     # (squared step < 1e-7) ends them at slightly different points of the same flat valley: the COST
     # agrees to 1e-9 either way, the state only to ~1e-3 there. test_splined_tight_convergence
     # removes the stopping-rule slack and compares the states strictly.
-    check_parity(r_gpu, kw_gpu, r_cpu, tol_b=1e-5 if "SPLINED" not in lensmodel else 5e-3)
+    # packed-state agreement at the converged point: limited by how flat the cost is along the least-constrained
+    # direction (the spline knots at the edge of the data; CAHVOR's r1/r2 terms), not by the arithmetic
+    tol_b = 5e-3 if "SPLINED" in lensmodel else 1e-4 if "CAHVOR" in lensmodel else 1e-5
+    check_parity(r_gpu, kw_gpu, r_cpu, tol_b=tol_b)
     assert r_gpu["rms_reproj_error__pixels"] < 0.3
 
 
