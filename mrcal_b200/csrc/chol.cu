@@ -11,7 +11,7 @@
 //   for each 256-column outer panel:
 //       for each 64-column inner block of it:
 //           potrf_diag   one CTA: factor the 64x64 diagonal block in shared
-//                        memory, and invert the factor (for the TRSMs/solves)
+//                        memory, and invert the factor (potrf_block.cuh)
 //           trsm         rows below: X <- A inv(L_kk)'   (small GEMM)
 //           syrk (K=64)  update of the REST OF THE PANEL only
 //       syrk (K=256)     one DMMA update of the whole trailing matrix
@@ -24,6 +24,7 @@
 #include <vector>
 
 #include "chol.h"
+#include "potrf_block.cuh"
 #include "problem.h"
 
 namespace mb200 {
@@ -32,145 +33,40 @@ constexpr int NB = 64;     // inner block
 constexpr int NBO = 256;   // outer panel
 
 ////////////////////////////////////////////////////////////////////////////////
-// diagonal block: Cholesky + inverse of the factor, one CTA of 256 threads, block in
-// shared memory. The 64 pivots are an inherently serial chain (rsqrt + a dependent
-// update each); everything is arranged to keep that chain short:
-//   4 panels of 16 columns. Per panel
-//     (a) ONE WARP factors the 16x16 diagonal sub-block with a row per lane in registers,
-//         columns exchanged by shuffles (no barriers), and inverts it the same way
-//     (b) all threads: the 16 columns below it  X = A inv(D)'          (48..0 rows)
-//     (c) all threads: trailing update of the block  A -= X X'
-//   then the off-diagonal blocks of inv(L) row-block by row-block:
-//         inv(L)_ij = -inv(L)_ii sum_{j<=k<i} L_ik inv(L)_kj
+// diagonal block: Cholesky + inverse of the factor, one CTA (potrf_block.cuh)
 ////////////////////////////////////////////////////////////////////////////////
-constexpr int SB = 16;   // sub-block
-
-__global__ void __launch_bounds__(256)
-potrf_diag_kernel(double* __restrict__ A, int ld, int k0, double* __restrict__ invL, int* __restrict__ info, int nreal)
+template <bool STAMP>
+__global__ void __launch_bounds__(256, 1)
+potrf_diag_kernel(double* __restrict__ A, int ld, int k0, double* __restrict__ invL, int* __restrict__ info, int nreal, long long* stamps)
 {
-    extern __shared__ __align__(16) double dsm[];
-    double (*sL)[NB + 1] = reinterpret_cast<double (*)[NB + 1]>(dsm);
-    double (*sX)[NB + 1] = reinterpret_cast<double (*)[NB + 1]>(dsm + NB * (NB + 1));
-    __shared__ double sT[NB - SB][SB + 1];   // panel scratch
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int ty = tid >> 4, tx = tid & 15;
-
+    extern __shared__ __align__(16) unsigned char dsm_raw[];
+    PotrfSmem& sm = *reinterpret_cast<PotrfSmem*>(dsm_raw);
+    const int tid = threadIdx.x;
+    if(STAMP && tid == 0) stamps[30] = clock64();
+    {
+        // all 16 loads of a thread in flight at once
+        double v[NB * NB / 256];
+#pragma unroll
+        for(int q = 0; q < NB * NB / 256; q++)
+        {
+            const int e = tid + q * 256, r = e / NB, c = e % NB;
+            v[q] = c <= r ? A[(size_t)(k0 + r) * ld + k0 + c] : 0.;
+        }
+#pragma unroll
+        for(int q = 0; q < NB * NB / 256; q++)
+        {
+            const int e = tid + q * 256;
+            sm.L[(e / NB) * PLD + e % NB] = v[q];
+        }
+    }
+    potrf_block<STAMP>(sm, info, k0, nreal, stamps);
     for(int e = tid; e < NB * NB; e += 256)
     {
         const int r = e / NB, c = e % NB;
-        sL[r][c] = c <= r ? A[(size_t)(k0 + r) * ld + k0 + c] : 0.;
-        sX[r][c] = 0.;
+        if(c <= r) A[(size_t)(k0 + r) * ld + k0 + c] = sm.L[r * PLD + c];
+        invL[e] = sm.X[r * PLD + c];
     }
-    __syncthreads();
-
-    for(int p = 0; p < NB / SB; p++)
-    {
-        const int c0 = p * SB;
-        if(warp == 0)
-        {
-            // (a) lanes 0..15 own rows c0..c0+15 of the diagonal sub-block (lanes 16..31 shadow them)
-            const int li = lane & 15;
-            double a[SB], xinv[SB], rinv[SB];
-#pragma unroll
-            for(int k = 0; k < SB; k++) a[k] = sL[c0 + li][c0 + k];
-#pragma unroll
-            for(int j = 0; j < SB; j++)
-            {
-                double d = __shfl_sync(0xffffffffu, a[j], j);
-                if(!(d > 0.))
-                {
-                    // not positive definite: remember the first failing pivot, carry on with a harmless value
-                    if(lane == 0 && k0 + c0 + j < nreal) atomicCAS(info, 0, k0 + c0 + j + 1);
-                    d = 1.;
-                }
-                const double r = rsqrt(d);
-                rinv[j] = r;
-                a[j] = (li == j) ? d * r : a[j] * r;
-#pragma unroll
-                for(int k = j + 1; k < SB; k++)
-                {
-                    const double lkj = __shfl_sync(0xffffffffu, a[j], k);
-                    a[k] -= a[j] * lkj;
-                }
-            }
-            // column li of inv(D): x_i = ((i==li) - sum_{k<i} L_ik x_k) / L_ii ; x_k = 0 for k < li
-#pragma unroll
-            for(int i = 0; i < SB; i++)
-            {
-                double acc = (i == li) ? 1. : 0.;
-#pragma unroll
-                for(int k = 0; k < i; k++)
-                {
-                    const double lik = __shfl_sync(0xffffffffu, a[k], i);
-                    acc -= lik * xinv[k];
-                }
-                xinv[i] = i < li ? 0. : acc * rinv[i];
-            }
-            if(lane < SB)
-            {
-#pragma unroll
-                for(int k = 0; k < SB; k++)
-                {
-                    if(k <= li) sL[c0 + li][c0 + k] = a[k];
-                    sX[c0 + k][c0 + li] = xinv[k];
-                }
-            }
-        }
-        __syncthreads();
-        const int m = NB - SB - c0;   // rows below this panel
-        if(m > 0)
-        {
-            // (b) X[r][j] = sum_{k<=j} A[c0+16+r][c0+k] inv(D)[j][k]
-            for(int r = ty; r < m; r += 16)
-            {
-                double acc = 0.;
-#pragma unroll
-                for(int k = 0; k < SB; k++) acc += sL[c0 + SB + r][c0 + k] * sX[c0 + tx][c0 + k];
-                sT[r][tx] = acc;
-            }
-            __syncthreads();
-            for(int r = ty; r < m; r += 16) sL[c0 + SB + r][c0 + tx] = sT[r][tx];
-            // (c) A[r][c] -= sum_k X[r][k] X[c][k], lower triangle of the trailing m x m
-            for(int r = ty; r < m; r += 16)
-                for(int c = tx; c <= r; c += 16)
-                {
-                    double acc = 0.;
-#pragma unroll
-                    for(int k = 0; k < SB; k++) acc += sT[r][k] * sT[c][k];
-                    sL[c0 + SB + r][c0 + SB + c] -= acc;
-                }
-            __syncthreads();
-        }
-    }
-    // L back to global (lower triangle), coalesced
-    for(int e = tid; e < NB * NB; e += 256)
-    {
-        const int r = e / NB, c = e % NB;
-        if(c <= r) A[(size_t)(k0 + r) * ld + k0 + c] = sL[r][c];
-    }
-    // off-diagonal blocks of inv(L), one row-block at a time
-    for(int ib = 1; ib < NB / SB; ib++)
-    {
-        const int r0 = ib * SB, w = r0;   // columns 0..w-1
-        // T[r][c] = sum_{k=c..w-1} L[r0+r][k] X[k][c]   (X lower triangular: X[k][c] = 0 for k < c)
-        for(int c = ty; c < w; c += 16)
-        {
-            double acc = 0.;
-            for(int k = c; k < w; k++) acc += sL[r0 + tx][k] * sX[k][c];
-            sT[c][tx] = acc;   // stored transposed: T[tx][c]
-        }
-        __syncthreads();
-        // X[r0+r][c] = -sum_{q<=r} X_ii[r][q] T[q][c]
-        for(int c = ty; c < w; c += 16)
-        {
-            double acc = 0.;
-#pragma unroll
-            for(int q = 0; q < SB; q++) acc += sX[r0 + tx][r0 + q] * sT[c][q];
-            sX[r0 + tx][c] = -acc;
-        }
-        __syncthreads();
-    }
-    for(int e = tid; e < NB * NB; e += 256) invL[e] = sX[e / NB][e % NB];
+    if(STAMP && tid == 0) stamps[31] = clock64();
 }
 
 ////////////////////////////////////////////////////////////////////////////////
@@ -335,7 +231,8 @@ syrk_dmma_kernel(double* __restrict__ A, int ld, int n, int c0, int c1, int k0, 
 }
 
 static const size_t kSyrkSmem = (size_t)2 * STAGES * BM * LDS * sizeof(double);   // TILE = 128; half of it for TILE = 64
-static const size_t kBlockSmem = (size_t)2 * NB * (NB + 1) * sizeof(double);   // potrf_diag / trsm
+static const size_t kBlockSmem = (size_t)2 * NB * (NB + 1) * sizeof(double);   // trsm
+static const size_t kPotrfSmem = sizeof(PotrfSmem);
 
 static bool configure_kernels()
 {
@@ -344,7 +241,8 @@ static bool configure_kernels()
     MB200_CUDA_CHECK(cudaFuncSetAttribute(syrk_dmma_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSyrkSmem));
     MB200_CUDA_CHECK(cudaFuncSetAttribute(syrk_dmma_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSyrkSmem));
     MB200_CUDA_CHECK(cudaFuncSetAttribute(trsm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kBlockSmem));
-    MB200_CUDA_CHECK(cudaFuncSetAttribute(potrf_diag_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kBlockSmem));
+    MB200_CUDA_CHECK(cudaFuncSetAttribute(potrf_diag_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kPotrfSmem));
+    MB200_CUDA_CHECK(cudaFuncSetAttribute(potrf_diag_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kPotrfSmem));
     configured = true;
     return true;
 }
@@ -427,6 +325,7 @@ void chol_forget_graphs(const void* A)
 bool chol_factor(double* A, int npad, int nreal, double* invL, int* d_info, cudaStream_t s, int* nlaunch)
 {
     if(!configure_kernels()) return false;
+    if(chol_dataflow_usable(npad)) return chol_factor_dataflow(A, npad, nreal, invL, d_info, s, nlaunch);
     return run_graphed(GraphKey{A, d_info, npad, nreal, 0}, s, nlaunch,
                        [&](int* n) { return chol_factor_enqueue(A, npad, nreal, invL, d_info, s, n); });
 }
@@ -441,8 +340,9 @@ bool chol_solve(const double* L, int npad, const double* invL, double* B, int ld
 static bool chol_solve_bwd_enqueue(const double* L, int npad, const double* invL, double* B, int ldb, cudaStream_t s, int* nlaunch);
 
 // L' z = y only (the forward half came out of the factorization itself: see normal_assemble's augmented row)
-bool chol_solve_backward(const double* L, int npad, const double* invL, double* B, int ldb, cudaStream_t s, int* nlaunch)
+bool chol_solve_backward(const double* L, int npad, const double* invL, double* B, int ldb, int* d_info, cudaStream_t s, int* nlaunch)
 {
+    if(chol_dataflow_usable(npad)) return chol_solve_backward_dataflow(L, npad, invL, B, d_info, s, nlaunch);
     return run_graphed(GraphKey{L, B, npad, ldb, 2}, s, nlaunch,
                        [&](int* n) { return chol_solve_bwd_enqueue(L, npad, invL, B, ldb, s, n); });
 }
@@ -458,7 +358,7 @@ static bool chol_factor_enqueue(double* A, int npad, int nreal, double* invL, in
         {
             if(kinds & 1)
             {
-                potrf_diag_kernel<<<1, 256, kBlockSmem, s>>>(A, npad, k0, invL + (size_t)(k0 / NB) * NB * NB, d_info, nreal);
+                potrf_diag_kernel<false><<<1, 256, kPotrfSmem, s>>>(A, npad, k0, invL + (size_t)(k0 / NB) * NB * NB, d_info, nreal, nullptr);
                 if(nlaunch) (*nlaunch)++;
             }
             const int nrows_below = npad - (k0 + NB);
@@ -599,10 +499,26 @@ double chol_debug_time(int n, int reps, int kinds, int graph)
         cudaGraphDestroy(g);
     }
     cudaEvent_t e0, e1; cudaEventCreate(&e0); cudaEventCreate(&e1);
+    double* rhs = nullptr;
+    if(kinds >= 32)
+    {
+        // 32: persistent factorization; 64: persistent backward substitution; 128: multi-kernel backward substitution
+        cudaMalloc(&rhs, (size_t)npad * sizeof(double));
+        cudaMemsetAsync(rhs, 0, (size_t)npad * sizeof(double), s);
+        chol_factor_dataflow(A, npad, n, invL, info, s, nullptr);
+    }
     for(int r = -1; r < reps; r++)
     {
         if(r == 0) cudaEventRecord(e0, s);
-        if(graph) cudaGraphLaunch(exec, s);
+        if(kinds == 32)
+        {
+            if(r >= 0) debug_fill_spd_kernel<<<(unsigned)(((size_t)npad * npad + 255) / 256), 256, 0, s>>>(A, npad);
+            chol_factor_dataflow(A, npad, n, invL, info, s, nullptr);
+        }
+        else if(kinds == 33) debug_fill_spd_kernel<<<(unsigned)(((size_t)npad * npad + 255) / 256), 256, 0, s>>>(A, npad);
+        else if(kinds == 64) chol_solve_backward_dataflow(A, npad, invL, rhs, info, s, nullptr);
+        else if(kinds == 128) run_graphed(GraphKey{A, rhs, npad, npad, 2}, s, nullptr, [&](int* nn) { return chol_solve_bwd_enqueue(A, npad, invL, rhs, npad, s, nn); });
+        else if(graph) cudaGraphLaunch(exec, s);
         else      chol_factor_enqueue(A, npad, n, invL, info, s, nullptr, kinds == 15 ? 7 : kinds);
     }
     cudaEventRecord(e1, s);
@@ -610,9 +526,32 @@ double chol_debug_time(int n, int reps, int kinds, int graph)
     float ms = 0.f; cudaEventElapsedTime(&ms, e0, e1);
     if(exec) cudaGraphExecDestroy(exec);
     cudaEventDestroy(e0); cudaEventDestroy(e1);
+    chol_forget_graphs(A);
     cudaStreamDestroy(s);
-    cudaFree(A); cudaFree(invL); cudaFree(info);
+    cudaFree(A); cudaFree(invL); cudaFree(info); cudaFree(rhs);
     return ms / reps;
+}
+
+// Debugging aid: clock64() stamps of the phases of one diagonal-block factorization (64 values)
+bool chol_debug_potrf_stamps(long long* out64)
+{
+    const int npad = 128;
+    double *A, *invL; int* info; long long* st;
+    if(!configure_kernels()) return false;
+    MB200_CUDA_CHECK(cudaMalloc(&A, (size_t)npad * npad * sizeof(double)));
+    MB200_CUDA_CHECK(cudaMalloc(&invL, (size_t)npad * NB * sizeof(double)));
+    MB200_CUDA_CHECK(cudaMalloc(&info, sizeof(int)));
+    MB200_CUDA_CHECK(cudaMalloc(&st, 64 * sizeof(long long)));
+    debug_fill_spd_kernel<<<(npad * npad + 255) / 256, 256>>>(A, npad);
+    for(int r = 0; r < 3; r++)
+    {
+        cudaMemset(st, 0, 64 * sizeof(long long));
+        potrf_diag_kernel<true><<<1, 256, kPotrfSmem>>>(A, npad, 0, invL, info, npad, st);
+    }
+    MB200_CUDA_CHECK(cudaDeviceSynchronize());
+    MB200_CUDA_CHECK(cudaMemcpy(out64, st, 64 * sizeof(long long), cudaMemcpyDeviceToHost));
+    cudaFree(A); cudaFree(invL); cudaFree(info); cudaFree(st);
+    return true;
 }
 
 static bool chol_solve_bwd_enqueue(const double* L, int npad, const double* invL, double* B, int ldb, cudaStream_t s, int* nlaunch)

@@ -16,13 +16,20 @@ bool chol_factor(double* A, int npad, int nreal, double* invL, int* d_info, cuda
 // Solve L L' X = B in place for nrhs right-hand sides stored as rows B[r][0..npad)
 bool chol_solve(const double* L, int npad, const double* invL, double* B, int ldb, int nrhs, cudaStream_t s, int* nlaunch);
 
-// Only the backward half, L' Z = B in place, one right-hand side
-bool chol_solve_backward(const double* L, int npad, const double* invL, double* B, int ldb, cudaStream_t s, int* nlaunch);
+// Only the backward half, L' Z = B in place, one right-hand side. d_info (may be the factorization's): set to -9
+// if the persistent kernel gave up waiting (never expected; the alternative would be to hang the GPU)
+bool chol_solve_backward(const double* L, int npad, const double* invL, double* B, int ldb, int* d_info, cudaStream_t s, int* nlaunch);
+
+// chol_dataflow.cu: the same two operations as one persistent kernel each (n <= 2560)
+bool chol_dataflow_usable(int npad);
+bool chol_factor_dataflow(double* A, int npad, int nreal, double* invL, int* d_info, cudaStream_t s, int* nlaunch);
+bool chol_solve_backward_dataflow(const double* L, int npad, const double* invL, double* B, int* d_info, cudaStream_t s, int* nlaunch);
 
 // drop cached CUDA graphs that reference this buffer (call before freeing it)
 void chol_forget_graphs(const void* A);
 
 double chol_debug_time(int n, int reps, int kinds, int graph);
+bool chol_debug_potrf_stamps(long long* out64);
 
 // d_out2[0] = min, d_out2[1] = max of diag(L)[0..nreal)
 bool chol_diag_minmax(const double* L, int npad, int nreal, double* d_out2, cudaStream_t s);

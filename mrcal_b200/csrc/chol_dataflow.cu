@@ -1,0 +1,346 @@
+// Kernel family 2c: the dense Cholesky factorization and the backward substitution
+// as ONE persistent kernel each, for the sizes where the multi-kernel version
+// (chol.cu) is bound by the latency of its chain of ~5 kernels per 64 columns.
+//
+// Left-looking tile algorithm, 64x64 tiles, one CTA per SM, tiles dealt round-robin
+// in column-major order. The owner of tile (i,j) computes
+//       C = A_ij - sum_{k<j} L_ik L_jk'          (DMMA, operands staged with cp.async)
+//       i == j:  L_jj = chol(C), and its inverse (potrf_block.cuh)
+//       i >  j:  L_ij = C inv(L_jj)'             (DMMA)
+// and then raises a flag in global memory (st.release). Consumers poll the flags of the
+// tiles they need (ld.acquire) and pull them from L2. All CTAs are co-resident
+// (cooperative launch), and every tile depends only on tiles that come earlier in the
+// column-major order, which each CTA walks in increasing order: the scheme cannot
+// deadlock. Waits are bounded all the same (a wedged GPU box costs more than a wrong
+// answer that the caller can detect): on timeout *info = -9.
+//
+// The critical path per 64 columns is  potrf_block + one flag hop + one triangular tile
+// + one flag hop + the last rank-64 update, instead of five kernel boundaries.
+//
+// Stands in for cholmod_factorize / cholmod_solve as libdogleg calls them (call site
+// mrcal.c:6435); the reference has no counterpart of this structure.
+#include <cuda_runtime.h>
+#include <cstdint>
+
+#include "chol.h"
+#include "potrf_block.cuh"
+#include "problem.h"
+
+namespace mb200 {
+
+namespace {
+
+constexpr int T = 64;
+constexpr long long kSpinLimit = 4000000000ll;   // ~2 s of SM clocks
+
+struct DfSmem
+{
+    PotrfSmem pb;          // pb.L doubles as the C tile
+    double opA[T * PLD];
+    double opB[T * PLD];
+    int ok;
+};
+
+__device__ __forceinline__ int ld_acquire(const int* p)
+{
+    int v;
+    asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_release(int* p, int v)
+{
+    asm volatile("st.release.gpu.global.s32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ void cp16(void* smem, const void* gmem)
+{
+    const unsigned s = (unsigned)__cvta_generic_to_shared(smem);
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(s), "l"(gmem));
+}
+__device__ __forceinline__ void cp_commit() { asm volatile("cp.async.commit_group;\n" ::); }
+__device__ __forceinline__ void cp_wait_all() { asm volatile("cp.async.wait_group 0;\n" ::); }
+
+// 64x64 tile, row stride ld in global -> [64][PLD] in shared. 2048 16-byte chunks, 8 per thread
+__device__ __forceinline__ void tile_to_smem(double* dst, const double* src, size_t ld)
+{
+#pragma unroll
+    for(int q = 0; q < 8; q++)
+    {
+        const int chunk = threadIdx.x + q * 256, r = chunk >> 5, c = (chunk & 31) * 2;
+        cp16(&dst[r * PLD + c], &src[(size_t)r * ld + c]);
+    }
+}
+
+// thread 0 waits for up to two flags; everybody learns whether it worked
+__device__ __forceinline__ bool wait_flags(DfSmem& sm, const int* f0, const int* f1, int* abort_flag, int* info)
+{
+    if(threadIdx.x == 0)
+    {
+        int ok = 1;
+        const long long t0 = clock64();
+        while(ld_acquire(f0) == 0 || (f1 && ld_acquire(f1) == 0))
+        {
+            if(ld_acquire(abort_flag) != 0 || clock64() - t0 > kSpinLimit)
+            {
+                st_release(abort_flag, 1);
+                atomicExch(info, -9);
+                ok = 0;
+                break;
+            }
+        }
+        sm.ok = ok;
+    }
+    __syncthreads();
+    const bool ok = sm.ok != 0;
+    __syncthreads();
+    return ok;
+}
+
+// acc += A B' for two [64][PLD] operands; 8 warps as 4 x 2, warp tile 16 x 32
+__device__ __forceinline__ void tile_mma(double (&acc)[2][4][2], const double* A, const double* B)
+{
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int wm = warp >> 1, wn = warp & 1, g = lane >> 2, t = lane & 3;
+    const double* a_s = A + (wm * 16) * PLD;
+    const double* b_s = B + (wn * 32) * PLD;
+#pragma unroll 4
+    for(int ks = 0; ks < T / 4; ks++)
+    {
+        double af[2], bf[4];
+#pragma unroll
+        for(int i = 0; i < 2; i++) af[i] = a_s[(i * 8 + g) * PLD + ks * 4 + t];
+#pragma unroll
+        for(int j = 0; j < 4; j++) bf[j] = b_s[(j * 8 + g) * PLD + ks * 4 + t];
+#pragma unroll
+        for(int i = 0; i < 2; i++)
+#pragma unroll
+            for(int j = 0; j < 4; j++) pb_dmma(acc[i][j][0], acc[i][j][1], af[i], bf[j]);
+    }
+}
+
+__device__ __forceinline__ int tile_flag(int i, int j, int nb) { return j * nb - (j * (j - 1)) / 2 + (i - j); }
+
+__global__ void __launch_bounds__(256, 1)
+chol_dataflow_kernel(double* __restrict__ A, int ld, int nb, int nreal, double* __restrict__ invL, int* __restrict__ info,
+                     int* __restrict__ flags, int* __restrict__ abort_flag)
+{
+    extern __shared__ __align__(16) unsigned char dsm_raw[];
+    DfSmem& sm = *reinterpret_cast<DfSmem*>(dsm_raw);
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int wm = warp >> 1, wn = warp & 1, g = lane >> 2, t = lane & 3;
+    const int ntiles = nb * (nb + 1) / 2;
+
+    for(int tl = blockIdx.x; tl < ntiles; tl += gridDim.x)
+    {
+        int j = 0, rem = tl;
+        while(rem >= nb - j) { rem -= nb - j; j++; }
+        const int i = j + rem;
+        double* Aij = A + (size_t)i * T * ld + (size_t)j * T;
+
+        tile_to_smem(sm.pb.L, Aij, ld);
+        cp_commit();
+        double acc[2][4][2];
+#pragma unroll
+        for(int a = 0; a < 2; a++)
+#pragma unroll
+            for(int b = 0; b < 4; b++) acc[a][b][0] = acc[a][b][1] = 0.;
+
+        for(int k = 0; k < j; k++)
+        {
+            if(!wait_flags(sm, flags + tile_flag(i, k, nb), i != j ? flags + tile_flag(j, k, nb) : nullptr, abort_flag, info)) return;
+            tile_to_smem(sm.opA, A + (size_t)i * T * ld + (size_t)k * T, ld);
+            if(i != j) tile_to_smem(sm.opB, A + (size_t)j * T * ld + (size_t)k * T, ld);
+            cp_commit();
+            cp_wait_all();
+            __syncthreads();
+            tile_mma(acc, sm.opA, i != j ? sm.opB : sm.opA);
+            __syncthreads();
+        }
+        cp_wait_all();
+        __syncthreads();
+        // C = A_ij - acc
+#pragma unroll
+        for(int a = 0; a < 2; a++)
+#pragma unroll
+            for(int b = 0; b < 4; b++)
+            {
+                double2* c = reinterpret_cast<double2*>(&sm.pb.L[(wm * 16 + a * 8 + g) * PLD + wn * 32 + b * 8 + 2 * t]);
+                double2 v = *c;
+                v.x -= acc[a][b][0];
+                v.y -= acc[a][b][1];
+                *c = v;
+            }
+
+        if(i == j)
+        {
+            potrf_block(sm.pb, info, j * T, nreal);
+            double* invLj = invL + (size_t)j * T * T;
+            for(int e = tid; e < T * T; e += 256)
+            {
+                const int r = e / T, c = e % T;
+                if(c <= r) Aij[(size_t)r * ld + c] = sm.pb.L[r * PLD + c];
+                invLj[e] = sm.pb.X[r * PLD + c];
+            }
+        }
+        else
+        {
+            __syncthreads();
+            if(!wait_flags(sm, flags + tile_flag(j, j, nb), nullptr, abort_flag, info)) return;
+            // inv(L_jj): dense 64x64 in global
+            const double* invLj = invL + (size_t)j * T * T;
+            tile_to_smem(sm.opB, invLj, T);
+            cp_commit();
+            cp_wait_all();
+            __syncthreads();
+#pragma unroll
+            for(int a = 0; a < 2; a++)
+#pragma unroll
+                for(int b = 0; b < 4; b++) acc[a][b][0] = acc[a][b][1] = 0.;
+            tile_mma(acc, sm.pb.L, sm.opB);
+#pragma unroll
+            for(int a = 0; a < 2; a++)
+#pragma unroll
+                for(int b = 0; b < 4; b++)
+                    *reinterpret_cast<double2*>(&Aij[(size_t)(wm * 16 + a * 8 + g) * ld + wn * 32 + b * 8 + 2 * t]) =
+                        make_double2(acc[a][b][0], acc[a][b][1]);
+        }
+        __threadfence();
+        __syncthreads();
+        if(tid == 0) st_release(flags + tl, 1);
+    }
+}
+
+// Backward substitution L' x = y, one right-hand side, one CTA per 64-row block (walking
+// down from the last block). Block i needs x_j for all j > i: it polls the x values
+// themselves (the slots hold a sentinel until written), so a hop between consecutive
+// blocks costs one L2 round trip. The tiles L_ji are prefetched into registers before
+// the wait.
+__global__ void __launch_bounds__(256, 1)
+chol_backward_dataflow_kernel(const double* __restrict__ L, int ld, int nb, const double* __restrict__ invL,
+                              double* __restrict__ B, double* __restrict__ xbuf, int* __restrict__ abort_flag, int* __restrict__ info)
+{
+    __shared__ double xs[T];
+    __shared__ double red[4][T];
+    __shared__ double tv[T];
+    __shared__ int okflag;
+    const int tid = threadIdx.x, c = tid & 63, q = tid >> 6;
+    if(tid == 0) okflag = 1;
+    __syncthreads();
+    for(int i = nb - 1 - (int)blockIdx.x; i >= 0; i -= gridDim.x)
+    {
+        double part = 0.;
+        for(int jb = nb - 1; jb > i; jb--)
+        {
+            double v[16];
+#pragma unroll
+            for(int r = 0; r < 16; r++) v[r] = __ldcg(&L[(size_t)(jb * T + q * 16 + r) * ld + i * T + c]);
+            if(tid < T)
+            {
+                const volatile double* src = xbuf + jb * T + tid;
+                double x = *src;
+                int ok = 1;
+                const long long t0 = clock64();
+                while(__double_as_longlong(x) == -1ll)
+                {
+                    if(clock64() - t0 > kSpinLimit || *(volatile int*)abort_flag != 0) { *(volatile int*)abort_flag = 1; atomicExch(info, -9); ok = 0; break; }
+                    x = *src;
+                }
+                xs[tid] = x;
+                if(!ok) okflag = 0;
+            }
+            __syncthreads();
+            if(*(volatile int*)&okflag == 0) return;
+#pragma unroll
+            for(int r = 0; r < 16; r++) part = fma(v[r], xs[q * 16 + r], part);
+            __syncthreads();
+        }
+        red[q][c] = part;
+        __syncthreads();
+        if(tid < T) tv[tid] = B[i * T + tid] - (red[0][tid] + red[1][tid] + red[2][tid] + red[3][tid]);
+        __syncthreads();
+        // x_i = inv(L_ii)' t:  x[c] = sum_{m >= c} invL[m][c] t[m]
+        const double* Li = invL + (size_t)i * T * T;
+        double acc = 0.;
+#pragma unroll
+        for(int r = 0; r < 16; r++)
+        {
+            const int m = q * 16 + r;
+            acc = fma(__ldcg(&Li[m * T + c]), tv[m], acc);   // zeros above the diagonal
+        }
+        red[q][c] = acc;
+        __syncthreads();
+        if(tid < T)
+        {
+            const double x = red[0][tid] + red[1][tid] + red[2][tid] + red[3][tid];
+            B[i * T + tid] = x;
+            *(volatile double*)(xbuf + i * T + tid) = x;
+        }
+        __syncthreads();
+    }
+}
+
+int* g_flags = nullptr;       // [kMaxTiles] tile flags, then [1] abort
+double* g_xbuf = nullptr;     // [kMaxBlocks * 64]
+int g_num_sms = 0;
+bool g_configured = false, g_unavailable = false;
+constexpr int kMaxBlocks = 40;
+constexpr int kMaxTiles = kMaxBlocks * (kMaxBlocks + 1) / 2;
+
+bool configure()
+{
+    if(g_configured) return true;
+    if(g_unavailable) return false;
+    int dev = 0, coop = 0;
+    if(cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, dev) != cudaSuccess || !coop ||
+       cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess ||
+       cudaFuncSetAttribute(chol_dataflow_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(DfSmem)) != cudaSuccess ||
+       cudaMalloc(&g_flags, (kMaxTiles + 1) * sizeof(int)) != cudaSuccess || cudaMalloc(&g_xbuf, (size_t)kMaxBlocks * T * sizeof(double)) != cudaSuccess)
+    {
+        cudaGetLastError();
+        g_unavailable = true;
+        return false;
+    }
+    g_configured = true;
+    return true;
+}
+
+}  // namespace
+
+bool chol_dataflow_usable(int npad)
+{
+    static const bool disabled = getenv("MRCAL_B200_CHOL_CLASSIC") != nullptr;
+    return !disabled && npad / T <= kMaxBlocks && configure();
+}
+
+bool chol_factor_dataflow(double* A, int npad, int nreal, double* invL, int* d_info, cudaStream_t s, int* nlaunch)
+{
+    if(!configure()) { set_error("the persistent Cholesky kernel is not available on this device"); return false; }
+    int nb = npad / T;
+    const int ntiles = nb * (nb + 1) / 2;
+    MB200_CUDA_CHECK(cudaMemsetAsync(d_info, 0, sizeof(int), s));
+    MB200_CUDA_CHECK(cudaMemsetAsync(g_flags, 0, (kMaxTiles + 1) * sizeof(int), s));
+    int ld = npad;
+    int* flags = g_flags;
+    int* abort_flag = g_flags + kMaxTiles;
+    void* args[] = {&A, &ld, &nb, &nreal, &invL, &d_info, &flags, &abort_flag};
+    const int grid = ntiles < g_num_sms ? ntiles : g_num_sms;
+    MB200_CUDA_CHECK(cudaLaunchCooperativeKernel((const void*)chol_dataflow_kernel, dim3(grid), dim3(256), args, sizeof(DfSmem), s));
+    if(nlaunch) (*nlaunch)++;
+    return true;
+}
+
+bool chol_solve_backward_dataflow(const double* L, int npad, const double* invL, double* B, int* d_info, cudaStream_t s, int* nlaunch)
+{
+    if(!configure()) { set_error("the persistent Cholesky kernel is not available on this device"); return false; }
+    int nb = npad / T, ld = npad;
+    MB200_CUDA_CHECK(cudaMemsetAsync(g_xbuf, 0xff, (size_t)kMaxBlocks * T * sizeof(double), s));
+    MB200_CUDA_CHECK(cudaMemsetAsync(g_flags + kMaxTiles, 0, sizeof(int), s));
+    int* abort_flag = g_flags + kMaxTiles;
+    double* xbuf = g_xbuf;
+    void* args[] = {&L, &ld, &nb, &invL, &B, &xbuf, &abort_flag, &d_info};
+    const int grid = nb < g_num_sms ? nb : g_num_sms;
+    MB200_CUDA_CHECK(cudaLaunchCooperativeKernel((const void*)chol_backward_dataflow_kernel, dim3(grid), dim3(256), args, 0, s));
+    if(nlaunch) (*nlaunch)++;
+    return true;
+}
+
+}  // namespace mb200

@@ -142,3 +142,7 @@ extern "C" double mrcal_b200_debug_time_cholesky(int n, int reps, int kinds, int
 {
     return chol_debug_time(n, reps, kinds, graph);
 }
+extern "C" bool mrcal_b200_debug_potrf_stamps(long long* out64)
+{
+    return chol_debug_potrf_stamps(out64);
+}

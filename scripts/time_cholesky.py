@@ -11,5 +11,10 @@ for n in [int(a) for a in sys.argv[1:]] or [1268, 4820]:
     full_d = f(n, 10, 15, 0)
     parts = {name: f(n, 10, k, 1) for name, k in (("potrf_diag", 1), ("trsm", 2), ("syrk_panel", 4), ("syrk_trailing", 8))}
     gf = n ** 3 / 3 / 1e9
-    print(f"n={n}: graph {full_g:.3f} ms ({gf / full_g:.1f} TFLOP/s... GFLOP={gf:.2f}), direct launches {full_d:.3f} ms; "
+    print(f"n={n}: multi-kernel graph {full_g:.3f} ms ({gf / full_g:.1f} TFLOP/s, GFLOP={gf:.2f}), direct launches {full_d:.3f} ms; "
           + ", ".join(f"{k} {v:.3f}" for k, v in parts.items()))
+    if n <= 2560:
+        fill = f(n, 10, 33, 0)
+        df = f(n, 10, 32, 0) - fill
+        print(f"n={n}: persistent factorization {df:.3f} ms ({gf / df:.1f} TFLOP/s); backward substitution: persistent {f(n, 20, 64, 0):.4f} ms, "
+              f"multi-kernel graph {f(n, 20, 128, 0):.4f} ms")

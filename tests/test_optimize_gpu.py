@@ -37,11 +37,11 @@ def run_both(kw):
     return r_gpu, kw_gpu, r_cpu
 
 
-def check_parity(r_gpu, kw_gpu, r_cpu, tol_b=1e-5):
+def check_parity(r_gpu, kw_gpu, r_cpu, tol_b=1e-5, tol_cost=1e-9):
     assert np.abs(r_gpu["b_packed"] - r_cpu["b_packed"]).max() <= tol_b
     assert abs(r_gpu["rms_reproj_error__pixels"] - r_cpu["rms_reproj_error__pixels"]) <= 1e-7
     n_gpu = float(r_gpu["x"] @ r_gpu["x"])
-    assert abs(n_gpu - r_cpu["norm2_x"]) <= 1e-9 * r_cpu["norm2_x"]
+    assert abs(n_gpu - r_cpu["norm2_x"]) <= tol_cost * r_cpu["norm2_x"]
     assert r_gpu["Noutliers_board"] == r_cpu["Noutliers_board"]
     # the solution was written into the caller's arrays, and it is the unpacked b_packed
     P = r_cpu["problem"]
@@ -73,7 +73,8 @@ def test_optimize_matches_cpu_restatement(ref, lensmodel, Ncameras, Nframes):
     # packed-state agreement at the converged point: limited by how flat the cost is along the least-constrained
     # direction (the spline knots at the edge of the data; CAHVOR's r1/r2 terms), not by the arithmetic
     tol_b = 5e-3 if "SPLINED" in lensmodel else 1e-4 if "CAHVOR" in lensmodel else 1e-5
-    check_parity(r_gpu, kw_gpu, r_cpu, tol_b=tol_b)
+    # (CAHVOR: the two runs stop a step apart in a flat valley; the cost agrees to 1e-7 rather than 1e-9)
+    check_parity(r_gpu, kw_gpu, r_cpu, tol_b=tol_b, tol_cost=1e-7 if "CAHVOR" in lensmodel else 1e-9)
     assert r_gpu["rms_reproj_error__pixels"] < 0.3
 
 
