@@ -92,6 +92,7 @@ enum LensKind
     LENS_OPENCV4, LENS_OPENCV5, LENS_OPENCV8, LENS_OPENCV12,
     LENS_SPLINED3, LENS_SPLINED2,
     LENS_CAHVOR,
+    LENS_CAHVORE,
     LENS_NKINDS
 };
 
@@ -101,6 +102,7 @@ template <> struct LensTraits<LENS_OPENCV5>  { static constexpr int NDIST = 5;  
 template <> struct LensTraits<LENS_OPENCV8>  { static constexpr int NDIST = 8;  static constexpr bool SPLINED = false; static constexpr int RUN = 0; };
 template <> struct LensTraits<LENS_OPENCV12> { static constexpr int NDIST = 12; static constexpr bool SPLINED = false; static constexpr int RUN = 0; };
 template <> struct LensTraits<LENS_CAHVOR>   { static constexpr int NDIST = 5;  static constexpr bool SPLINED = false; static constexpr int RUN = 0; };
+template <> struct LensTraits<LENS_CAHVORE>  { static constexpr int NDIST = 8;  static constexpr bool SPLINED = false; static constexpr int RUN = 0; };
 template <> struct LensTraits<LENS_SPLINED3> { static constexpr int NDIST = 0;  static constexpr bool SPLINED = true;  static constexpr int RUN = 4; };
 template <> struct LensTraits<LENS_SPLINED2> { static constexpr int NDIST = 0;  static constexpr bool SPLINED = true;  static constexpr int RUN = 3; };
 
@@ -118,11 +120,12 @@ __device__ __forceinline__ void stereographic_u(double* u, double du_dp[2][3], c
     du_dp[1][0] = p[1] * Bm * p[0];         du_dp[1][1] = p[1] * Bm * p[1] + scale; du_dp[1][2] = p[1] * (Bm * p[2] + A);
 }
 
-// Parametric models with a closed form. intr = fx,fy,cx,cy,distortions...
+// Parametric models with a closed form. intr = fx,fy,cx,cy,distortions...; cfg: the model's configuration
+// scalar (CAHVORE: linearity)
 template <int KIND>
 __device__ __forceinline__ void project_parametric(double q[2], double dq_dp[2][3],
                                                    double (*dq_ddist)[LensTraits<KIND>::NDIST > 0 ? LensTraits<KIND>::NDIST : 1],
-                                                   const double* p, const double* __restrict__ intr)
+                                                   const double* p, const double* __restrict__ intr, double cfg = 0.)
 {
     const double fx = intr[0], fy = intr[1], cx = intr[2], cy = intr[3];
     if constexpr(KIND == LENS_PINHOLE)
@@ -240,6 +243,148 @@ __device__ __forceinline__ void project_parametric(double q[2], double dq_dp[2][
             {
                 dq_ddist[0][k] = gx[0] * d[k][0] + gx[2] * d[k][2];
                 dq_ddist[1][k] = gy[1] * d[k][1] + gy[2] * d[k][2];
+            }
+        }
+    }
+    else if constexpr(KIND == LENS_CAHVORE)
+    {
+        // JPL CAHVORE (noncentral) in mrcal's parametrisation: distortions (alpha, beta, r0,r1,r2, e0,e1,e2) and
+        // the configuration value "linearity". Same model and the same Newton iteration for theta as
+        // cahvore.cc:36-158; the reference pushes forward-mode derivatives through every operation, here theta
+        // carries its derivatives with respect to the five scalars it depends on (zeta, l, e0, e1, e2) through the
+        // iteration (so the gradients agree with the reference's to rounding, not just to the Newton tolerance)
+        // and everything after that is chained by hand.
+        //   zeta = p.o ; ll = p - zeta o ; l = |ll|
+        //   theta:  zeta sin - l cos - (theta - sin)(e0 + e1 theta^2 + e2 theta^4) = 0
+        //   chi = theta | sin(lin theta)/lin | tan(lin theta)/lin ; mu = r0 + r1 chi^2 + r2 chi^4
+        //   p' = o l/chi + ll (1 + mu) ; q = pinhole(p')
+        const double al = intr[4], be = intr[5], r0 = intr[6], r1 = intr[7], r2 = intr[8], e0 = intr[9], e1 = intr[10], e2 = intr[11];
+        const double lin = cfg;
+        double sa, ca, sb, cb;
+        sincos(al, &sa, &ca);
+        sincos(be, &sb, &cb);
+        const double o[3]   = {sa * cb, sb, ca * cb};
+        const double o_a[3] = {ca * cb, 0., -sa * cb};
+        const double o_b[3] = {-sa * sb, cb, -ca * sb};
+        const double zeta = p[0] * o[0] + p[1] * o[1] + p[2] * o[2];
+        const double ll[3] = {p[0] - zeta * o[0], p[1] - zeta * o[1], p[2] - zeta * o[2]};
+        const double l = sqrt(ll[0] * ll[0] + ll[1] * ll[1] + ll[2] * ll[2]);
+        double th = atan2(l, zeta);
+        double dth[5];   // d theta / d (zeta, l, e0, e1, e2)
+        {
+            const double n2i = 1. / (zeta * zeta + l * l);
+            dth[0] = -l * n2i; dth[1] = zeta * n2i; dth[2] = dth[3] = dth[4] = 0.;
+        }
+        bool failed = true;
+        for(int it = 0; it < 100; it++)
+        {
+            double s, c;
+            sincos(th, &s, &c);
+            const double th2 = th * th, th3 = th * th2, th4 = th * th3;
+            const double E = e0 + e1 * th2 + e2 * th4, E1 = 2. * e1 * th + 4. * e2 * th3, E2 = 2. * e1 + 12. * e2 * th2;
+            const double ts = th - s;
+            const double g = zeta * s - l * c - ts * E;
+            const double ups = zeta * c + l * s + (c - 1.) * E - ts * E1;
+            const double ups_th = -zeta * s + l * c - s * E + 2. * (c - 1.) * E1 - ts * E2;
+            const double step = g / ups;
+            const double g_x[5]   = {s, -c, -ts, -ts * th2, -ts * th4};
+            const double ups_x[5] = {c, s, c - 1., (c - 1.) * th2 - ts * 2. * th, (c - 1.) * th4 - ts * 4. * th3};
+#pragma unroll
+            for(int k = 0; k < 5; k++)
+            {
+                const double dg = ups * dth[k] + g_x[k];
+                const double du = ups_th * dth[k] + ups_x[k];
+                dth[k] -= (dg - step * du) / ups;
+            }
+            th -= step;
+            if(fabs(step) < 1e-8) { failed = false; break; }
+        }
+        if(failed || th * fabs(lin) > 1.5707963267948966)
+        {
+            // the reference refuses the whole evaluation here (cahvore.cc:104-116); the poisoned measurement does the same
+            th = nan("");
+        }
+        double pd[3], J_p[3][3], J_i[3][8];   // p', dp'/dp, dp'/d(alpha,beta,r0,r1,r2,e0,e1,e2)
+        if(th > 1e-8)
+        {
+            const double linth = th * lin;
+            double chi, chi_th;
+            if(lin < -1e-15)     { chi = sin(linth) / lin; chi_th = cos(linth); }
+            else if(lin > 1e-15) { chi = tan(linth) / lin; const double ci = 1. / cos(linth); chi_th = ci * ci; }
+            else                 { chi = th; chi_th = 1.; }
+            const double chi2 = chi * chi, chi3 = chi * chi2, chi4 = chi2 * chi2;
+            const double zp = l / chi;
+            const double mu = r0 + r1 * chi2 + r2 * chi4;
+            const double mu_chi = 2. * r1 * chi + 4. * r2 * chi3;
+#pragma unroll
+            for(int i = 0; i < 3; i++) pd[i] = o[i] * zp + ll[i] * (mu + 1.);
+            // partials of p' with respect to (zeta, l, e0, e1, e2) at fixed o, ll
+            double F[5][3];
+#pragma unroll
+            for(int k = 0; k < 5; k++)
+            {
+                const double chi_x = chi_th * dth[k];
+                const double zp_x = (k == 1 ? 1. / chi : 0.) - l * chi_x / chi2;
+                const double mu_x = mu_chi * chi_x;
+#pragma unroll
+                for(int i = 0; i < 3; i++) F[k][i] = o[i] * zp_x + ll[i] * mu_x;
+            }
+            const double li = 1. / l;
+            // wrt p: zeta_p = o, l_p = ll/l, ll_p = I - o o'
+#pragma unroll
+            for(int i = 0; i < 3; i++)
+#pragma unroll
+                for(int j = 0; j < 3; j++)
+                    J_p[i][j] = F[0][i] * o[j] + F[1][i] * ll[j] * li + (mu + 1.) * ((i == j ? 1. : 0.) - o[i] * o[j]);
+            // wrt alpha, beta
+#pragma unroll
+            for(int ab = 0; ab < 2; ab++)
+            {
+                const double* ot = ab == 0 ? o_a : o_b;
+                const double zeta_t = p[0] * ot[0] + p[1] * ot[1] + p[2] * ot[2];
+                const double l_t = -zeta * (ll[0] * ot[0] + ll[1] * ot[1] + ll[2] * ot[2]) * li;
+#pragma unroll
+                for(int i = 0; i < 3; i++)
+                    J_i[i][ab] = zp * ot[i] + (mu + 1.) * (-zeta_t * o[i] - zeta * ot[i]) + F[0][i] * zeta_t + F[1][i] * l_t;
+            }
+#pragma unroll
+            for(int i = 0; i < 3; i++)
+            {
+                J_i[i][2] = ll[i]; J_i[i][3] = ll[i] * chi2; J_i[i][4] = ll[i] * chi4;
+                J_i[i][5] = F[2][i]; J_i[i][6] = F[3][i]; J_i[i][7] = F[4][i];
+            }
+        }
+        else
+        {
+            // small-angle branch (cahvore.cc:118-149): p' = p. (NaN theta lands here too: poison p')
+#pragma unroll
+            for(int i = 0; i < 3; i++)
+            {
+                pd[i] = th == th ? p[i] : th;
+#pragma unroll
+                for(int j = 0; j < 3; j++) J_p[i][j] = i == j ? 1. : 0.;
+#pragma unroll
+                for(int k = 0; k < 8; k++) J_i[i][k] = 0.;
+            }
+        }
+        const double zi = 1. / pd[2];
+        q[0] = pd[0] * zi * fx + cx;
+        q[1] = pd[1] * zi * fy + cy;
+        const double gx[3] = {fx * zi, 0., -fx * pd[0] * zi * zi};
+        const double gy[3] = {0., fy * zi, -fy * pd[1] * zi * zi};
+#pragma unroll
+        for(int j = 0; j < 3; j++)
+        {
+            dq_dp[0][j] = gx[0] * J_p[0][j] + gx[2] * J_p[2][j];
+            dq_dp[1][j] = gy[1] * J_p[1][j] + gy[2] * J_p[2][j];
+        }
+        if(dq_ddist != nullptr)
+        {
+#pragma unroll
+            for(int k = 0; k < 8; k++)
+            {
+                dq_ddist[0][k] = gx[0] * J_i[0][k] + gx[2] * J_i[2][k];
+                dq_ddist[1][k] = gy[1] * J_i[1][k] + gy[2] * J_i[2][k];
             }
         }
     }

@@ -234,7 +234,7 @@ eval_boards_kernel(DevProblem P, double* __restrict__ x, double* __restrict__ Jv
         if constexpr(LensTraits<KIND>::SPLINED)
             project_splined<LensTraits<KIND>::RUN>(q, dq_dp, wx, wy, &ivar0, upd, p, intr, P.Nx, P.Ny, P.segments_per_u);
         else
-            project_parametric<KIND>(q, dq_dp, WITH_J ? ddist : nullptr, p, intr);
+            project_parametric<KIND>(q, dq_dp, WITH_J ? ddist : nullptr, p, intr, P.lens_cfg);
 
         const size_t ifeat = (size_t)iobs * NWH + ipt;
         const double qx_obs = P.obs_board_pool[3 * ifeat + 0];
@@ -392,7 +392,7 @@ eval_points_kernel(DevProblem P, double* __restrict__ x, double* __restrict__ Jv
             if constexpr(LensTraits<KIND>::SPLINED)
                 project_splined<LensTraits<KIND>::RUN>(q, dq_dp, wx, wy, &ivar0, upd, p, intr, P.Nx, P.Ny, P.segments_per_u);
             else
-                project_parametric<KIND>(q, dq_dp, WITH_J ? ddist : nullptr, p, intr);
+                project_parametric<KIND>(q, dq_dp, WITH_J ? ddist : nullptr, p, intr, P.lens_cfg);
         }
         const double e0 = outlier ? 0. : (q[0] - P.obs_point_pool[3 * iobs + 0]) * w;
         const double e1 = outlier ? 0. : (q[1] - P.obs_point_pool[3 * iobs + 1]) * w;
@@ -673,6 +673,7 @@ bool launch_evaluate(const DevProblem& dp, const EvalBuffers& out, bool with_jac
     case LENS_SPLINED3:      launch_kind<LENS_SPLINED3>(dp, out, with_jacobian, stream, nlaunch); break;
     case LENS_SPLINED2:      launch_kind<LENS_SPLINED2>(dp, out, with_jacobian, stream, nlaunch); break;
     case LENS_CAHVOR:        launch_kind<LENS_CAHVOR>(dp, out, with_jacobian, stream, nlaunch); break;
+    case LENS_CAHVORE:       launch_kind<LENS_CAHVORE>(dp, out, with_jacobian, stream, nlaunch); break;
     default: set_error("lens model kind %d has no CUDA implementation", dp.lens_kind); return false;
     }
     const bool splined = dp.lens_kind == LENS_SPLINED3 || dp.lens_kind == LENS_SPLINED2;

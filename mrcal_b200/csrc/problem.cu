@@ -20,6 +20,7 @@ static int lens_kind_of(const mrcal_lensmodel_t* lm)
     case MRCAL_LENSMODEL_OPENCV8:       return LENS_OPENCV8;
     case MRCAL_LENSMODEL_OPENCV12:      return LENS_OPENCV12;
     case MRCAL_LENSMODEL_CAHVOR:        return LENS_CAHVOR;
+    case MRCAL_LENSMODEL_CAHVORE:       return LENS_CAHVORE;
     case MRCAL_LENSMODEL_SPLINED_STEREOGRAPHIC:
         return lm->LENSMODEL_SPLINED_STEREOGRAPHIC__config.order == 3 ? LENS_SPLINED3 :
                lm->LENSMODEL_SPLINED_STEREOGRAPHIC__config.order == 2 ? LENS_SPLINED2 : -1;
@@ -123,7 +124,7 @@ mrcal_b200_problem_create(const double* intrinsics, const mrcal_pose_t* rt_cam_r
     {
         char name[256] = "?";
         mrcal_lensmodel_name(name, sizeof(name), lensmodel);
-        set_error("lens model %s has no CUDA implementation yet (supported: PINHOLE, STEREOGRAPHIC, LONLAT, LATLON, OPENCV4/5/8/12, CAHVOR, SPLINED_STEREOGRAPHIC order 2,3)", name);
+        set_error("lens model %s has no CUDA implementation yet (supported: PINHOLE, STEREOGRAPHIC, LONLAT, LATLON, OPENCV4/5/8/12, CAHVOR, CAHVORE, SPLINED_STEREOGRAPHIC order 2,3)", name);
         return nullptr;
     }
 
@@ -232,6 +233,7 @@ mrcal_b200_problem_create(const double* intrinsics, const mrcal_pose_t* rt_cam_r
     dp.m_point0 = L.m_point0; dp.m_reg0 = L.m_reg0; dp.Nmeas = L.Nmeas;
     dp.lens_kind = kind; dp.Nx = L.Nx; dp.Ny = L.Ny;
     dp.segments_per_u = 0.;
+    dp.lens_cfg = lensmodel->type == MRCAL_LENSMODEL_CAHVORE ? lensmodel->LENSMODEL_CAHVORE__config.linearity : 0.;
     if(L.splined && !spline_segments_per_u(&dp.segments_per_u, lensmodel)) return nullptr;
     dp.spacing = calibration_object_spacing;
     dp.opt_core = L.sel.do_optimize_intrinsics_core; dp.opt_dist = L.sel.do_optimize_intrinsics_distortions;

@@ -29,6 +29,7 @@ struct DevProblem
     int lens_kind;             // LensKind
     int Nx, Ny;
     double segments_per_u;
+    double lens_cfg;           // the lens model's configuration scalar (CAHVORE: linearity)
     double spacing;
     bool opt_core, opt_dist, opt_extr, opt_frames, opt_warp;
     bool have_warp;            // a calobject_warp was given (optimised or not)

@@ -88,6 +88,28 @@ def project(p, lensmodel, intrinsics):
         mu = r0 + tau * r1 + tau * tau * r2
         pd = p + mu[..., None] * (p - w[..., None] * o)
         u = np.stack((pd[..., 0] / pd[..., 2], pd[..., 1] / pd[..., 2]), -1)
+    elif lensmodel.startswith("LENSMODEL_CAHVORE_linearity="):
+        # noncentral JPL model: theta by Newton's method, as the reference does it (cahvore.cc:77-116)
+        lin = float(lensmodel[len("LENSMODEL_CAHVORE_linearity="):])
+        al, be, r0, r1, r2, e0, e1, e2 = intr[4:12]
+        o = np.array((np.sin(al) * np.cos(be), np.sin(be), np.cos(al) * np.cos(be)))
+        zeta = p @ o
+        ll = p - zeta[..., None] * o
+        l = np.sqrt((ll * ll).sum(-1))
+        th = np.arctan2(l, zeta)
+        for _ in range(100):
+            s_, c_ = np.sin(th), np.cos(th)
+            E = e0 + e1 * th**2 + e2 * th**4
+            ups = zeta * c_ + l * s_ + (c_ - 1.) * E - (th - s_) * (2. * e1 * th + 4. * e2 * th**3)
+            step = (zeta * s_ - l * c_ - (th - s_) * E) / ups
+            th = th - step
+            if np.abs(step).max() < 1e-12:
+                break
+        chi = th if abs(lin) <= 1e-15 else (np.sin(th * lin) if lin < 0 else np.tan(th * lin)) / lin
+        big = th > 1e-8
+        chis = np.where(big, chi, 1.)
+        pd = np.where(big[..., None], o * (l / chis)[..., None] + ll * (1. + r0 + r1 * chis**2 + r2 * chis**4)[..., None], p)
+        u = np.stack((pd[..., 0] / pd[..., 2], pd[..., 1] / pd[..., 2]), -1)
     elif lensmodel == "LENSMODEL_LONLAT":
         u = np.stack((np.arctan2(x, z), np.arcsin(y / np.linalg.norm(p, axis=-1))), -1)
     elif lensmodel == "LENSMODEL_LATLON":
@@ -166,6 +188,8 @@ def true_intrinsics(lensmodel, Ncameras, rng):
             out.append(np.concatenate((core, _OPENCV_DIST[:n] * (1. + 0.1 * rng.uniform(-1, 1, n)))))
         elif lensmodel == "LENSMODEL_CAHVOR":
             out.append(np.concatenate((core, np.array((0.01, -0.02, 0.0, 0.03, 0.01)) * (1. + 0.1 * rng.uniform(-1, 1, 5)))))
+        elif lensmodel.startswith("LENSMODEL_CAHVORE"):
+            out.append(np.concatenate((core, np.array((0.01, -0.02, 0.0, 0.03, 0.01, 0.002, 0.01, -0.004)) * (1. + 0.1 * rng.uniform(-1, 1, 8)))))
         elif lensmodel in ("LENSMODEL_LONLAT", "LENSMODEL_LATLON"):
             out.append(core * np.array((1., 1., 1., 1.)))
         else:

@@ -53,7 +53,7 @@ def golden_cases():
                     ("LENSMODEL_LONLAT", "lonlat"), ("LENSMODEL_LATLON", "latlon"),
                     ("LENSMODEL_OPENCV4", "opencv4"), ("LENSMODEL_OPENCV5", "opencv5"),
                     ("LENSMODEL_OPENCV8", "opencv8"), ("LENSMODEL_OPENCV12", "opencv12"),
-                    ("LENSMODEL_CAHVOR", "cahvor")):
+                    ("LENSMODEL_CAHVOR", "cahvor"), ("LENSMODEL_CAHVORE_linearity=0.37", "cahvore")):
         add(f"{tag}_2cam_all", lm, 2, 4, _sel(True, True, True, True, True))
     add("splined3_2cam_corelocked", SPL3, 2, 4, _sel(False, True, True, True, True), outliers=7)
     add("splined3_3cam_all", SPL3, 3, 3, _sel(True, True, True, True, True), which="some")
@@ -75,6 +75,9 @@ def golden_cases():
     add("pinhole_points_noframes", "LENSMODEL_PINHOLE", 2, 3, _sel(True, False, True, False, False), Npoints=5)
     add("cahvor_points", "LENSMODEL_CAHVOR", 3, 3, _sel(True, True, True, True, True), Npoints=6, Npoints_fixed=1,
         outliers=3, which="some")
+    add("cahvore_points", "LENSMODEL_CAHVORE_linearity=-0.25", 3, 3, _sel(True, True, True, True, True), Npoints=6, Npoints_fixed=1,
+        outliers=3, which="some")
+    add("cahvore_lin0_coreonly", "LENSMODEL_CAHVORE_linearity=0.00", 2, 3, _sel(True, False, True, True, True))
     return cases
 
 

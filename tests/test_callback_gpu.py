@@ -88,8 +88,6 @@ def test_projection_known_answers():
     ntested = 0
     for i in range(int(g["N"])):
         lm = str(g[f"lensmodel_{i}"])
-        if lm.startswith("LENSMODEL_CAHVORE"):
-            continue    # no CUDA implementation yet
         intr, p, q_ref = g[f"intrinsics_{i}"], g[f"p_{i}"], g[f"q_{i}"]
         for k in range(p.shape[0]):
             ii = np.ascontiguousarray((intr[k] if intr.ndim == 2 else intr)[None, :])
@@ -102,7 +100,7 @@ def test_projection_known_answers():
             x = mrcal_b200.optimizer_callback(**kw, no_jacobian=True, no_factorization=True)[1]
             assert np.abs(x[:2] - q_ref[k]).max() < 2e-6 * max(1., np.abs(q_ref[k]).max()), (lm, k, x[:2], q_ref[k])
             ntested += 1
-    assert ntested >= 27
+    assert ntested >= 36
 
 
 def test_callback_size_independent_properties():
@@ -139,7 +137,7 @@ def test_callback_error_behaviour():
     bad = dict(kw, indices_frame_camintrinsics_camextrinsics=kw["indices_frame_camintrinsics_camextrinsics"][::-1].copy())
     with pytest.raises(RuntimeError, match="monotonically|sequentially"):
         mrcal_b200.optimizer_callback(**bad)
-    bad = dict(kw, lensmodel="LENSMODEL_CAHVORE_linearity=0.40", intrinsics=np.zeros((2, 12)))
+    bad = dict(kw, lensmodel="LENSMODEL_SPLINED_STEREOGRAPHIC_order=4_Nx=8_Ny=6_fov_x_deg=100", intrinsics=np.zeros((2, 4 + 2 * 48)))
     with pytest.raises(RuntimeError, match="no CUDA implementation"):
         mrcal_b200.optimizer_callback(**bad)
     # None-valued kwargs are ignored, as in the reference (mrcal-pywrap.c:1491-1555)

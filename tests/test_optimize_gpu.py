@@ -59,6 +59,7 @@ def check_parity(r_gpu, kw_gpu, r_cpu, tol_b=1e-5, tol_cost=1e-9):
     ("LENSMODEL_PINHOLE", 1, 5),
     ("LENSMODEL_STEREOGRAPHIC", 2, 5),
     ("LENSMODEL_CAHVOR", 2, 8),
+    ("LENSMODEL_CAHVORE_linearity=0.37", 2, 8),
     (SPL3_COVERED, 2, 40),
     (SPL2_COVERED, 2, 40),
 ])
