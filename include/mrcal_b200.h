@@ -285,6 +285,18 @@ bool mrcal_corresponding_icam_extrinsics(int* icam_extrinsics,
 // owned by the caller, exactly as in the reference)
 ////////////////////////////////////////////////////////////////////////////////
 
+// replaces mrcal.h:165-191: q = project(p), N points in camera coordinates. dq_dp may be NULL;
+// dq_dintrinsics must be NULL (not provided by this library)
+bool mrcal_project(mrcal_point2_t* q, mrcal_point3_t* dq_dp, double* dq_dintrinsics,
+                   const mrcal_point3_t* p, int N,
+                   const mrcal_lensmodel_t* lensmodel, const double* intrinsics);
+// replaces mrcal.h:193-224: observation rays (not normalised) of N pixels. Models without a closed-form
+// inverse are inverted iteratively, as in the reference (mrcal.c:3106-3270); a point that cannot be inverted
+// comes back with NaN x,y. This is what turns mrcal.optimize()'s observations_point_triangulated pixels
+// into the rays of mrcal_observation_point_triangulated_t (mrcal-pywrap.c:1383-1401)
+bool mrcal_unproject(mrcal_point3_t* out, const mrcal_point2_t* q, int N,
+                     const mrcal_lensmodel_t* lensmodel, const double* intrinsics);
+
 // One evaluation of the cost function at the given (unpacked) seed:
 //   b_packed <- packed state, x <- residuals, Jt <- CSR Jacobian dx/db_packed
 // replaces mrcal.h:539-609 (mrcal.c:5972-6177). Buffer sizes are in BYTES and
@@ -409,6 +421,29 @@ mrcal_b200_problem_create(const double*                 intrinsics,
                           const mrcal_observation_board_t* observations_board,
                           const mrcal_observation_point_t* observations_point,
                           int Nobservations_board, int Nobservations_point,
+                          const mrcal_point3_t* observations_board_pool,
+                          const mrcal_point3_t* observations_point_pool,
+                          const mrcal_lensmodel_t* lensmodel,
+                          const int* imagersizes,
+                          mrcal_problem_selections_t problem_selections,
+                          double calibration_object_spacing,
+                          int calibration_object_width_n, int calibration_object_height_n);
+// The same with triangulated-point observations (mrcal_optimize()'s observations_point_triangulated: rays in
+// camera coordinates, sets closed by last_in_set; mrcal.c:5180-5653). Allowed only with the intrinsics locked
+// and the extrinsics optimized, as in the reference (mrcal.c:6260-6275)
+mrcal_b200_problem_t*
+mrcal_b200_problem_create_triangulated(const double*                 intrinsics,
+                          const mrcal_pose_t*           rt_cam_ref,
+                          const mrcal_pose_t*           rt_ref_frame,
+                          const mrcal_point3_t*         points,
+                          const mrcal_calobject_warp_t* calobject_warp,
+                          int Ncameras_intrinsics, int Ncameras_extrinsics, int Nframes,
+                          int Npoints, int Npoints_fixed,
+                          const mrcal_observation_board_t* observations_board,
+                          const mrcal_observation_point_t* observations_point,
+                          int Nobservations_board, int Nobservations_point,
+                          const mrcal_observation_point_triangulated_t* observations_point_triangulated,
+                          int Nobservations_point_triangulated,
                           const mrcal_point3_t* observations_board_pool,
                           const mrcal_point3_t* observations_point_pool,
                           const mrcal_lensmodel_t* lensmodel,

@@ -13,7 +13,7 @@ from .api import (  # noqa: F401
     measurement_index_regularization,
     num_measurements, num_measurements_boards, num_measurements_points,
     num_measurements_points_triangulated, num_measurements_regularization,
-    corresponding_icam_extrinsics, pack_state, unpack_state,
+    corresponding_icam_extrinsics, pack_state, unpack_state, project, unproject,
 )
 from ._capi import lib as _lib
 

@@ -32,6 +32,12 @@ class Stats(C.Structure):
                 ("Noutliers_triangulated_point", C.c_int)]
 
 
+class ObservationPointTriangulated(C.Structure):
+    """mrcal_observation_point_triangulated_t (types.h:243-263): bit 0 of `bits` = last_in_set, bit 1 = outlier."""
+    _fields_ = [("icam_intrinsics", C.c_int), ("icam_extrinsics", C.c_int),
+                ("bits", C.c_uint8), ("px", C.c_double * 3)]
+
+
 class Sparse(C.Structure):
     """mrcal_b200_sparse_t (== the public cholmod_sparse layout)."""
     _fields_ = [("nrow", C.c_size_t), ("ncol", C.c_size_t), ("nzmax", C.c_size_t),
@@ -75,6 +81,7 @@ SELECTION_BITS = ("do_optimize_intrinsics_core",
 
 # every symbol include/mrcal_b200.h declares; tests check the .so exports each
 EXPORTED_SYMBOLS = (
+    "mrcal_project", "mrcal_unproject", "mrcal_b200_problem_create_triangulated",
     "mrcal_lensmodel_from_name", "mrcal_lensmodel_type_from_name", "mrcal_lensmodel_name",
     "mrcal_lensmodel_name_unconfigured", "mrcal_lensmodel_metadata", "mrcal_lensmodel_num_params",
     "mrcal_supported_lensmodel_names", "mrcal_knots_for_splined_models",
@@ -125,7 +132,7 @@ for _n in ["mrcal_lensmodel_from_name", "mrcal_lensmodel_name", "mrcal_knots_for
            "mrcal_b200_problem_reset", "mrcal_b200_problem_upload", "mrcal_b200_problem_callback",
            "mrcal_b200_problem_optimize", "mrcal_b200_problem_download", "mrcal_b200_problem_reduced_system",
            "mrcal_b200_nccl_get_unique_id", "mrcal_b200_nccl_comm_init", "mrcal_b200_problem_set_sharding",
-           "mrcal_b200_factorization_solve_xt_JtJ_bt"]:
+           "mrcal_b200_factorization_solve_xt_JtJ_bt", "mrcal_project", "mrcal_unproject"]:
     getattr(lib, _n).restype = C.c_bool
 lib.mrcal_lensmodel_metadata.restype = Metadata
 lib.mrcal_lensmodel_name_unconfigured.restype = C.c_char_p
@@ -134,6 +141,7 @@ lib.mrcal_optimize.restype = Stats
 lib.mrcal_b200_version.restype = C.c_char_p
 lib.mrcal_b200_last_error.restype = C.c_char_p
 lib.mrcal_b200_problem_create.restype = C.c_void_p
+lib.mrcal_b200_problem_create_triangulated.restype = C.c_void_p
 lib.mrcal_b200_problem_destroy.restype = None
 lib.mrcal_b200_problem_time_callback.restype = C.c_double
 lib.mrcal_b200_factorization_create.restype = C.c_void_p

@@ -174,8 +174,19 @@ class _Inputs:
         if self.indices_tri.shape[0] != self.Nobs_tri:
             raise RuntimeError("Inconsistent Nobservations_point_triangulated")
         if self.Nobs_tri > 0:
-            raise RuntimeError("observations_point_triangulated: the triangulated-point path is not implemented "
-                               "in the CUDA backend yet")
+            it = self.indices_tri
+            if (it[:, 1] < 0).any() or (it[:, 1] >= self.Ncam_i).any():
+                raise RuntimeError(f"icam_intrinsics MUST be in [0,{self.Ncam_i - 1}] in indices_point_triangulated_camintrinsics_camextrinsics")
+            if (it[:, 2] < -1).any() or (it[:, 2] >= self.Ncam_e).any():
+                raise RuntimeError(f"icam_extrinsics MUST be in [-1,{self.Ncam_e - 1}] in indices_point_triangulated_camintrinsics_camextrinsics")
+            # mrcal-pywrap.c:1406-1440: sets are runs of equal ipoint, consecutive, each seen at least twice
+            if (it[:, 0] < 0).any():
+                raise RuntimeError("Error in indices_point_triangulated_camintrinsics_camextrinsics. Each ipoint must be >=0")
+            d = np.diff(it[:, 0])
+            if ((d != 0) & (d != 1)).any() or it[0, 0] != 0:
+                raise RuntimeError("Error in indices_point_triangulated_camintrinsics_camextrinsics. All ipoint must be consecutive and monotonic")
+            if (np.bincount(it[:, 0]) < 2).any():
+                raise RuntimeError("Error in indices_point_triangulated_camintrinsics_camextrinsics. Each point must be observed at least 2 times")
 
         ib = self.indices_board
         if self.Nobs_board:
@@ -233,6 +244,38 @@ class _Inputs:
         op = np.ascontiguousarray(self.indices_point[:, (1, 2, 0)]) if self.Nobs_point else np.zeros((0, 3), np.int32)
         return ob, op
 
+    def c_triangulated(self, rays=False):
+        """(pointer, count) of the mrcal_observation_point_triangulated_t array: the pixel observations are
+        unprojected to rays with the (fixed) intrinsics of their camera, weight <= 0 marks an outlier, the last
+        observation of each point closes its set (mrcal-pywrap.c:1311-1440). The layout functions only look at
+        the sets: rays=False leaves the rays zero (and needs no GPU)."""
+        if self.Nobs_tri == 0:
+            return None, 0
+        if getattr(self, "_tri", None) is None or (rays and not self._tri_has_rays):
+            it = self.indices_tri
+            want = rays
+            rays = np.zeros((self.Nobs_tri, 3))
+            if want and self.observations_tri.shape[0] and self.intrinsics.shape[0]:
+                _require_gpu()
+                for icam in np.unique(it[:, 1]):
+                    sel = np.flatnonzero(it[:, 1] == icam)
+                    q = np.ascontiguousarray(self.observations_tri[sel, :2])
+                    v = np.zeros((len(sel), 3))
+                    intr = np.ascontiguousarray(self.intrinsics[icam])
+                    if not lib.mrcal_unproject(_ptr(v), _ptr(q), len(sel), self.lm_ref(), _ptr(intr)):
+                        raise RuntimeError("mrcal_unproject() failed: " + _capi.last_error())
+                    rays[sel] = v
+            arr = (_capi.ObservationPointTriangulated * self.Nobs_tri)()
+            last = np.concatenate((np.diff(it[:, 0]) != 0, [True]))
+            for i in range(self.Nobs_tri):
+                arr[i].icam_intrinsics = int(it[i, 1])
+                arr[i].icam_extrinsics = int(it[i, 2])
+                arr[i].bits = (1 if last[i] else 0) | (2 if self.observations_tri[i, 2] <= 0.0 else 0)
+                arr[i].px[0], arr[i].px[1], arr[i].px[2] = rays[i]
+            self._tri = arr
+            self._tri_has_rays = bool(want)
+        return self._tri, self.Nobs_tri
+
     def counts(self):
         return (self.Ncam_i, self.Ncam_e, self.Nframes, self.Npoints, self.Npoints_fixed, self.Nobs_board)
 
@@ -245,13 +288,15 @@ class _Inputs:
         return lib.mrcal_num_states(*self.counts(), self.selections, self.lm_ref())
 
     def num_measurements(self):
-        return lib.mrcal_num_measurements(self.Nobs_board, self.Nobs_point, None, 0, self.W, self.H,
+        tri, ntri = self.c_triangulated()
+        return lib.mrcal_num_measurements(self.Nobs_board, self.Nobs_point, tri, ntri, self.W, self.H,
                                           self.Ncam_i, self.Ncam_e, self.Nframes, self.Npoints, self.Npoints_fixed,
                                           self.selections, self.lm_ref())
 
     def num_j_nonzero(self):
         ob, op = self.c_observations()
-        return lib._mrcal_num_j_nonzero(self.Nobs_board, self.Nobs_point, None, 0, self.W, self.H,
+        tri, ntri = self.c_triangulated()
+        return lib._mrcal_num_j_nonzero(self.Nobs_board, self.Nobs_point, tri, ntri, self.W, self.H,
                                         self.Ncam_i, self.Ncam_e, self.Nframes, self.Npoints, self.Npoints_fixed,
                                         _ptr(ob), _ptr(op), self.selections, self.lm_ref())
 
@@ -289,13 +334,14 @@ def optimizer_callback(no_jacobian=False, no_factorization=False, **kwargs):
                           sorted=1, packed=1)
         keep = (P, Ii, X)
     ob, op = I.c_observations()
+    tri, ntri = I.c_triangulated(rays=True)
     ok = lib.mrcal_optimizer_callback(
         _ptr(b), C.c_int(b.nbytes), _ptr(x), C.c_int(x.nbytes),
         C.byref(Jt) if Jt is not None else None,
         _ptr(I.intrinsics), _ptr(I.rt_cam_ref), _ptr(I.rt_ref_frame), _ptr(I.points),
         _ptr(I.calobject_warp) if I.calobject_warp is not None else None,
         I.Ncam_i, I.Ncam_e, I.Nframes, I.Npoints, I.Npoints_fixed,
-        _ptr(ob), _ptr(op), I.Nobs_board, I.Nobs_point, None, 0,
+        _ptr(ob), _ptr(op), I.Nobs_board, I.Nobs_point, tri, ntri,
         _ptr(I.observations_board), _ptr(I.observations_point),
         I.lm_ref(), _ptr(I.imagersizes), I.selections, None,
         C.c_double(I.spacing), max(I.W, 0), max(I.H, 0), C.c_bool(I.verbose))
@@ -329,12 +375,13 @@ def optimize(**kwargs):
     b = np.zeros(Nstate)
     x = np.zeros(Nmeas)
     ob, op = I.c_observations()
+    tri, ntri = I.c_triangulated(rays=True)
     stats = lib.mrcal_optimize(
         _ptr(b), C.c_int(b.nbytes), _ptr(x), C.c_int(x.nbytes),
         _ptr(I.intrinsics), _ptr(I.rt_cam_ref), _ptr(I.rt_ref_frame), _ptr(I.points),
         _ptr(I.calobject_warp) if I.calobject_warp is not None else None,
         I.Ncam_i, I.Ncam_e, I.Nframes, I.Npoints, I.Npoints_fixed,
-        _ptr(ob), _ptr(op), I.Nobs_board, I.Nobs_point, None, 0,
+        _ptr(ob), _ptr(op), I.Nobs_board, I.Nobs_point, tri, ntri,
         _ptr(I.observations_board), _ptr(I.observations_point),
         I.lm_ref(), _ptr(I.imagersizes), I.selections, None,
         C.c_double(I.spacing), max(I.W, 0), max(I.H, 0), C.c_bool(I.verbose), C.c_bool(False))
@@ -354,11 +401,12 @@ class Problem:
         _require_gpu()
         I = self._I = _Inputs(kwargs)
         ob, op = I.c_observations()
-        self._h = lib.mrcal_b200_problem_create(
+        tri, ntri = I.c_triangulated(rays=True)
+        self._h = lib.mrcal_b200_problem_create_triangulated(
             _ptr(I.intrinsics), _ptr(I.rt_cam_ref), _ptr(I.rt_ref_frame), _ptr(I.points),
             _ptr(I.calobject_warp) if I.calobject_warp is not None else None,
             I.Ncam_i, I.Ncam_e, I.Nframes, I.Npoints, I.Npoints_fixed,
-            _ptr(ob), _ptr(op), I.Nobs_board, I.Nobs_point,
+            _ptr(ob), _ptr(op), I.Nobs_board, I.Nobs_point, tri, ntri,
             _ptr(I.observations_board), _ptr(I.observations_point),
             I.lm_ref(), _ptr(I.imagersizes), I.selections,
             C.c_double(I.spacing), max(I.W, 0), max(I.H, 0))
@@ -645,22 +693,24 @@ def num_measurements_points(**kwargs):
 
 def measurement_index_points_triangulated(i_point_triangulated, **kwargs):
     I = _layout_inputs(kwargs)
-    if I.Nobs_tri:
-        raise RuntimeError("triangulated points are not implemented in the CUDA backend yet")
-    return None
+    tri, ntri = I.c_triangulated()
+    if ntri == 0:
+        return None
+    return _none_if_negative(lib.mrcal_measurement_index_points_triangulated(
+        int(i_point_triangulated), I.Nobs_board, I.Nobs_point, tri, ntri, max(I.W, 0), max(I.H, 0)))
 
 
 def num_measurements_points_triangulated(**kwargs):
     I = _layout_inputs(kwargs)
-    if I.Nobs_tri:
-        raise RuntimeError("triangulated points are not implemented in the CUDA backend yet")
-    return 0
+    tri, ntri = I.c_triangulated()
+    return lib.mrcal_num_measurements_points_triangulated(tri, ntri)
 
 
 def measurement_index_regularization(**kwargs):
     I = _layout_inputs(kwargs)
+    tri, ntri = I.c_triangulated()
     return _none_if_negative(lib.mrcal_measurement_index_regularization(
-        None, 0, I.W, I.H, I.Ncam_i, I.Ncam_e, I.Nframes, I.Npoints, I.Npoints_fixed, I.Nobs_board, I.Nobs_point,
+        tri, ntri, I.W, I.H, I.Ncam_i, I.Ncam_e, I.Nframes, I.Npoints, I.Npoints_fixed, I.Nobs_board, I.Nobs_point,
         I.selections, I.lm_ref()))
 
 
@@ -707,3 +757,40 @@ def pack_state(b, **kwargs):
 
 def unpack_state(b, **kwargs):
     return _pack_unpack(b, False, kwargs)
+
+
+def project(v, lensmodel, intrinsics_data, get_gradients=False):
+    """q = project(v): the reference's mrcal.project() for one camera (mrcal-pywrap.c / mrcal.h:165-191).
+    v: (...,3) points in camera coordinates. Returns q (...,2), and dq_dv (...,2,3) too with get_gradients
+    (the gradient with respect to the intrinsics is not provided by this library)."""
+    _require_gpu()
+    v = np.ascontiguousarray(v, dtype=np.float64)
+    if v.shape[-1] != 3:
+        raise RuntimeError("project(): the last dimension of v must be 3")
+    lm = _lensmodel(lensmodel)
+    intr = np.ascontiguousarray(intrinsics_data, dtype=np.float64)
+    if intr.shape != (lib.mrcal_lensmodel_num_params(C.byref(lm)),):
+        raise RuntimeError(f"project(): intrinsics_data must have shape ({lib.mrcal_lensmodel_num_params(C.byref(lm))},)")
+    flat = v.reshape(-1, 3)
+    q = np.zeros((flat.shape[0], 2))
+    g = np.zeros((flat.shape[0], 2, 3)) if get_gradients else None
+    if not lib.mrcal_project(_ptr(q), _ptr(g) if g is not None else None, None, _ptr(flat), flat.shape[0], C.byref(lm), _ptr(intr)):
+        raise RuntimeError("mrcal_project() failed: " + _capi.last_error())
+    q = q.reshape(v.shape[:-1] + (2,))
+    return (q, g.reshape(v.shape[:-1] + (2, 3))) if get_gradients else q
+
+
+def unproject(q, lensmodel, intrinsics_data):
+    """Observation rays (not normalised) of pixels q (...,2): the reference's mrcal.unproject() without
+    gradients (mrcal.h:193-224)."""
+    _require_gpu()
+    q = np.ascontiguousarray(q, dtype=np.float64)
+    if q.shape[-1] != 2:
+        raise RuntimeError("unproject(): the last dimension of q must be 2")
+    lm = _lensmodel(lensmodel)
+    intr = np.ascontiguousarray(intrinsics_data, dtype=np.float64)
+    flat = q.reshape(-1, 2)
+    v = np.zeros((flat.shape[0], 3))
+    if not lib.mrcal_unproject(_ptr(v), _ptr(flat), flat.shape[0], C.byref(lm), _ptr(intr)):
+        raise RuntimeError("mrcal_unproject() failed: " + _capi.last_error())
+    return v.reshape(q.shape[:-1] + (3,))

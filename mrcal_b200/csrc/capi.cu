@@ -28,12 +28,15 @@ mrcal_b200_problem_t* acquire_problem(const double* intrinsics, const mrcal_pose
                                       const mrcal_observation_board_t* ob, const mrcal_observation_point_t* op,
                                       int Nob, int Nop, const mrcal_point3_t* pool_b, const mrcal_point3_t* pool_p,
                                       const mrcal_lensmodel_t* lensmodel, const int* imagersizes,
-                                      mrcal_problem_selections_t sel, double spacing, int W, int H)
+                                      mrcal_problem_selections_t sel, double spacing, int W, int H,
+                                      const mrcal_observation_point_triangulated_t* otri = nullptr, int Notri = 0)
 {
+    if(otri == nullptr || Notri < 0) Notri = 0;
     if(Nob < 0) Nob = 0;
     if(Nop < 0) Nop = 0;
     mrcal_b200_problem_t* P = g_cache.p;
-    bool same = P != nullptr;
+    // (problems with triangulated observations carry their rays on the device: not reused)
+    bool same = P != nullptr && Notri == 0 && P->dp.Ntri == 0;
     if(same)
     {
         const Dims& d = P->L.d;
@@ -64,9 +67,9 @@ mrcal_b200_problem_t* acquire_problem(const double* intrinsics, const mrcal_pose
         return P;
     }
     if(P) { mrcal_b200_problem_destroy(P); g_cache.p = nullptr; }
-    P = mrcal_b200_problem_create(intrinsics, rt_cam_ref, rt_ref_frame, points, calobject_warp,
-                                  Ncam_i, Ncam_e, Nframes, Npoints, Npoints_fixed, ob, op, Nob, Nop, pool_b, pool_p,
-                                  lensmodel, imagersizes, sel, spacing, W, H);
+    P = mrcal_b200_problem_create_triangulated(intrinsics, rt_cam_ref, rt_ref_frame, points, calobject_warp,
+                                               Ncam_i, Ncam_e, Nframes, Npoints, Npoints_fixed, ob, op, Nob, Nop, otri, Notri,
+                                               pool_b, pool_p, lensmodel, imagersizes, sel, spacing, W, H);
     if(P == nullptr) return nullptr;
     g_cache.p = P;
     g_cache.imagersizes.assign(imagersizes, imagersizes + 2 * Ncam_i);
@@ -75,7 +78,6 @@ mrcal_b200_problem_t* acquire_problem(const double* intrinsics, const mrcal_pose
     return P;
 }
 
-bool have_triangulated(const mrcal_observation_point_triangulated_t* o, int N) { return o != nullptr && N > 0; }
 }  // namespace
 
 extern "C" bool mrcal_optimizer_callback(double* b_packed, int buffer_size_b_packed,
@@ -101,11 +103,6 @@ extern "C" bool mrcal_optimizer_callback(double* b_packed, int buffer_size_b_pac
                                          bool verbose)
 {
     (void)problem_constants; (void)verbose;
-    if(have_triangulated(observations_point_triangulated, Nobservations_point_triangulated))
-    {
-        set_error("ERROR: triangulated points are not implemented in the CUDA path yet");
-        return false;
-    }
     if(b_packed == nullptr || x == nullptr)
     {
         set_error("mrcal_optimizer_callback(): b_packed and x may not be NULL");
@@ -117,7 +114,8 @@ extern "C" bool mrcal_optimizer_callback(double* b_packed, int buffer_size_b_pac
                                              observations_board, observations_point, Nobservations_board, Nobservations_point,
                                              observations_board_pool, observations_point_pool, lensmodel, imagersizes,
                                              problem_selections, calibration_object_spacing,
-                                             calibration_object_width_n, calibration_object_height_n)};
+                                             calibration_object_width_n, calibration_object_height_n,
+                                             observations_point_triangulated, Nobservations_point_triangulated)};
     if(g.p == nullptr) return false;
     const int Nstate = g.p->L.Nstate, Nmeas = g.p->L.Nmeas;
     if(buffer_size_b_packed != Nstate * (int)sizeof(double))
@@ -170,18 +168,14 @@ extern "C" mrcal_stats_t mrcal_optimize(double* b_packed_final, int buffer_size_
         set_error("mrcal_optimize(check_gradient=true) is a libdogleg debugging facility and is not provided by the CUDA path");
         return bad;
     }
-    if(have_triangulated(observations_point_triangulated, Nobservations_point_triangulated))
-    {
-        set_error("ERROR: triangulated points are not implemented in the CUDA path yet");
-        return bad;
-    }
     std::lock_guard<std::mutex> lock(g_cache.mtx);
     struct { mrcal_b200_problem_t* p; } g{acquire_problem(intrinsics, rt_cam_ref, rt_ref_frame, points, calobject_warp,
                                              Ncameras_intrinsics, Ncameras_extrinsics, Nframes, Npoints, Npoints_fixed,
                                              observations_board, observations_point, Nobservations_board, Nobservations_point,
                                              observations_board_pool, observations_point_pool, lensmodel, imagersizes,
                                              problem_selections, calibration_object_spacing,
-                                             calibration_object_width_n, calibration_object_height_n)};
+                                             calibration_object_width_n, calibration_object_height_n,
+                                             observations_point_triangulated, Nobservations_point_triangulated)};
     if(g.p == nullptr) return bad;
     const int Nstate = g.p->L.Nstate, Nmeas = g.p->L.Nmeas;
     if(b_packed_final != nullptr && buffer_size_b_packed_final != Nstate * (int)sizeof(double))

@@ -36,6 +36,7 @@ struct Dims
     int Ncam_i = 0, Ncam_e = 0, Nframes = 0, Npoints = 0, Npoints_fixed = 0;
     int Nobs_board = 0, Nobs_point = 0;
     int W = 0, H = 0;   // calibration object corners
+    int Nmeas_tri = 0;  // measurements of the triangulated points: one per pair of observations of a point
 };
 
 // Everything integer about one problem: where each block of the state vector
@@ -64,7 +65,7 @@ struct Layout
     int nnz_row_board_geom = 0;   // frames + warp (no extrinsics)
 
     int m_board0 = 0, m_point0 = 0, m_tri0 = 0, m_reg0 = 0;
-    int Nmeas_board = 0, Nmeas_point = 0, Nmeas_reg = 0, Nmeas = 0;
+    int Nmeas_board = 0, Nmeas_point = 0, Nmeas_tri = 0, Nmeas_reg = 0, Nmeas = 0;
     int Nreg_dist = 0, Nreg_center = 0, Nreg_unity = 0;
 };
 

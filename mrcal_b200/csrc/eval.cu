@@ -10,6 +10,7 @@
 // in registers and writes its two fixed-width Jacobian rows. Row positions are
 // analytic (fixed nnz per row class), so there is no serial fill pointer.
 #include "device_math.cuh"
+#include "triangulated.cuh"
 #include "problem.h"
 
 namespace mb200 {
@@ -571,6 +572,112 @@ eval_regularization_kernel(DevProblem P, bool splined, double* __restrict__ x, d
     if(threadIdx.x == 0 && s != 0. && P.reg_owner) atomicAdd(norm2, s);
 }
 
+// One thread per triangulated measurement = per pair (i0 < i1) of observations of the same point
+// (mrcal.c:5180-5653). The point has no state: the rows depend on the extrinsics of the two cameras only.
+//   v0_ref = R_0r' v0,  t_r0 = -R_0r' t_0r        (camera 0 -> reference)
+//   v0_cam1 = R_1r v0_ref,  t_10 = R_1r t_r0 + t_1r
+//   x = err(v1, v0_cam1, t_10)
+// Row layout as the reference writes it: [r_0r, t_0r] if camera 0 has extrinsics, then [r_1r, t_1r] likewise.
+template <bool WITH_J>
+__global__ void __launch_bounds__(128)
+eval_triangulated_kernel(DevProblem P, double* __restrict__ x, double* __restrict__ Jval, int* __restrict__ Jcol,
+                         double* __restrict__ norm2)
+{
+    __shared__ double red[32];
+    const int ip = blockIdx.x * blockDim.x + threadIdx.x;
+    double sumsq = 0.;
+    if(ip < P.Ntri)
+    {
+        const int i0 = P.tri_pairs[2 * ip], i1 = P.tri_pairs[2 * ip + 1];
+        const int e0 = P.tri_cam_e[i0], e1 = P.tri_cam_e[i1];
+        const bool outlier = P.tri_outlier[i0] || P.tri_outlier[i1];
+        double err = 0.;
+        double J0[6] = {}, J1[6] = {};
+        if(!outlier)
+        {
+            const double* v0 = &P.tri_px[3 * i0];
+            const double* v1 = &P.tri_px[3 * i1];
+            double R0[9], dR0[27], R1[9], dR1[27];
+            double v0_ref[3], t_r0[3] = {0., 0., 0.}, v0_cam1[3], t_10[3];
+            const double* rt0 = e0 >= 0 ? &P.u_rtcam[6 * e0] : nullptr;
+            const double* rt1 = e1 >= 0 ? &P.u_rtcam[6 * e1] : nullptr;
+            if(rt0)
+            {
+                rodrigues(R0, WITH_J ? dR0 : nullptr, rt0);
+#pragma unroll
+                for(int c = 0; c < 3; c++)
+                {
+                    v0_ref[c] = R0[c] * v0[0] + R0[3 + c] * v0[1] + R0[6 + c] * v0[2];
+                    t_r0[c] = -(R0[c] * rt0[3] + R0[3 + c] * rt0[4] + R0[6 + c] * rt0[5]);
+                }
+            }
+            else
+                for(int c = 0; c < 3; c++) v0_ref[c] = v0[c];
+            if(rt1)
+            {
+                rodrigues(R1, WITH_J ? dR1 : nullptr, rt1);
+                mat3_vec(v0_cam1, R1, v0_ref);
+                mat3_vec(t_10, R1, t_r0);
+                t_10[0] += rt1[3]; t_10[1] += rt1[4]; t_10[2] += rt1[5];
+            }
+            else
+                for(int c = 0; c < 3; c++) { v0_cam1[c] = v0_ref[c]; t_10[c] = t_r0[c]; }
+
+            double g_v[3], g_t[3];
+            err = triangulated_error(g_v, g_t, v1, v0_cam1, t_10);
+            if constexpr(WITH_J)
+            {
+                // gradients pulled back to the reference frame: R_1r' g  (R_1r = I for a camera at the reference)
+                double gv_ref[3], gt_ref[3];
+                for(int c = 0; c < 3; c++)
+                {
+                    gv_ref[c] = rt1 ? R1[c] * g_v[0] + R1[3 + c] * g_v[1] + R1[6 + c] * g_v[2] : g_v[c];
+                    gt_ref[c] = rt1 ? R1[c] * g_t[0] + R1[3 + c] * g_t[1] + R1[6 + c] * g_t[2] : g_t[c];
+                }
+                if(rt0)
+                {
+                    for(int k = 0; k < 3; k++)
+                    {
+                        // d v0_ref / d r_k = dR0_k' v0 ; d t_r0 / d r_k = -dR0_k' t_0r
+                        const double* D = &dR0[9 * k];
+                        double acc = 0.;
+                        for(int c = 0; c < 3; c++)
+                        {
+                            const double dv = D[c] * v0[0] + D[3 + c] * v0[1] + D[6 + c] * v0[2];
+                            const double dt = -(D[c] * rt0[3] + D[3 + c] * rt0[4] + D[6 + c] * rt0[5]);
+                            acc += gv_ref[c] * dv + gt_ref[c] * dt;
+                        }
+                        J0[k] = acc * kScaleRotCam;
+                        // d t_r0 / d t_0r = -R0'  ->  derr/dt_0r[k] = -sum_c gt_ref[c] R0[k][c]
+                        J0[3 + k] = -(R0[3 * k] * gt_ref[0] + R0[3 * k + 1] * gt_ref[1] + R0[3 * k + 2] * gt_ref[2]) * kScaleTransCam;
+                    }
+                }
+                if(rt1)
+                {
+                    for(int k = 0; k < 3; k++)
+                    {
+                        double dv[3], dt[3];
+                        mat3_vec(dv, &dR1[9 * k], v0_ref);
+                        mat3_vec(dt, &dR1[9 * k], t_r0);
+                        J1[k] = (g_v[0] * dv[0] + g_v[1] * dv[1] + g_v[2] * dv[2] + g_t[0] * dt[0] + g_t[1] * dt[1] + g_t[2] * dt[2]) * kScaleRotCam;
+                        J1[3 + k] = g_t[k] * kScaleTransCam;
+                    }
+                }
+            }
+        }
+        x[P.m_tri0 + ip] = err;
+        sumsq = err * err;
+        if constexpr(WITH_J)
+        {
+            int j = P.tri_j0[ip];
+            if(e0 >= 0) for(int k = 0; k < 6; k++) { Jcol[j] = P.i_extr0 + 6 * e0 + k; Jval[j] = J0[k]; j++; }
+            if(e1 >= 0) for(int k = 0; k < 6; k++) { Jcol[j] = P.i_extr0 + 6 * e1 + k; Jval[j] = J1[k]; j++; }
+        }
+    }
+    const double s = block_sum(sumsq, red);
+    if(threadIdx.x == 0 && s != 0.) atomicAdd(norm2, s);
+}
+
 // CSR row pointers. Analytic: every row of an observation has the same width
 __global__ void fill_rowptr_kernel(DevProblem P, bool splined, int nnz_total, int* __restrict__ rowptr)
 {
@@ -584,13 +691,15 @@ __global__ void fill_rowptr_kernel(DevProblem P, bool splined, int nnz_total, in
         const int j0 = P.board_j0[iobs], j1 = P.board_j0[iobs + 1];
         rowptr[m] = j0 + r * ((j1 - j0) / per_obs);
     }
-    else if(m < P.m_reg0)
+    else if(m < P.m_tri0)
     {
         const int r = m - P.m_point0;
         const int iobs = r >> 1;
         const int j0 = P.point_j0[iobs], j1 = P.point_j0[iobs + 1];
         rowptr[m] = j0 + (r & 1) * ((j1 - j0) / 2);
     }
+    else if(m < P.m_reg0)
+        rowptr[m] = P.tri_j0[m - P.m_tri0];
     else
     {
         const int t = m - P.m_reg0;
@@ -675,6 +784,13 @@ bool launch_evaluate(const DevProblem& dp, const EvalBuffers& out, bool with_jac
     case LENS_CAHVOR:        launch_kind<LENS_CAHVOR>(dp, out, with_jacobian, stream, nlaunch); break;
     case LENS_CAHVORE:       launch_kind<LENS_CAHVORE>(dp, out, with_jacobian, stream, nlaunch); break;
     default: set_error("lens model kind %d has no CUDA implementation", dp.lens_kind); return false;
+    }
+    if(dp.Ntri > 0)
+    {
+        const int threads = 128, blocks = (dp.Ntri + threads - 1) / threads;
+        if(with_jacobian) eval_triangulated_kernel<true ><<<blocks, threads, 0, stream>>>(dp, out.x, out.Jval, out.Jcol, out.norm2);
+        else              eval_triangulated_kernel<false><<<blocks, threads, 0, stream>>>(dp, out.x, out.Jval, out.Jcol, out.norm2);
+        (*nlaunch)++;
     }
     const bool splined = dp.lens_kind == LENS_SPLINED3 || dp.lens_kind == LENS_SPLINED2;
     const int Nreg = dp.Nmeas - dp.m_reg0;

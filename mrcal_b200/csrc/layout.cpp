@@ -123,7 +123,8 @@ bool make_layout(Layout* L, const Dims& d, mrcal_problem_selections_t sel, const
     L->m_board0 = 0;
     L->m_point0 = L->Nmeas_board;
     L->m_tri0   = L->m_point0 + L->Nmeas_point;
-    L->m_reg0   = L->m_tri0;
+    L->Nmeas_tri = d.Nmeas_tri;
+    L->m_reg0   = L->m_tri0 + L->Nmeas_tri;
     L->Nmeas    = L->m_reg0 + L->Nmeas_reg;
     return true;
 }

@@ -129,6 +129,7 @@ extern "C" void mrcal_b200_nccl_comm_destroy(void)
 extern "C" bool mrcal_b200_problem_set_sharding(mrcal_b200_problem_t* P, int frame_offset, int Nframes_global,
                                                 int point_offset, int Npoints_global)
 {
+    if(P->dp.Ntri > 0) { set_error("sharded solves with triangulated points are not supported"); return false; }
     P->sharded = true;
     P->dp.reg_owner = comm_rank() == 0;
     P->frame_offset = frame_offset; P->Nframes_global = Nframes_global;

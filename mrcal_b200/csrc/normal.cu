@@ -150,6 +150,16 @@ __global__ void mark_reg_active_kernel(DevProblem P, NormalBuffers N)
     if(P.reg_unity && threadIdx.x < 3) N.active[N.reduced_index(P.i_extr0 + 3 + threadIdx.x)] = 1;
 }
 
+// ... and so must the extrinsics of every camera that observes a triangulated point
+__global__ void mark_tri_active_kernel(DevProblem P, NormalBuffers N)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if(i >= 2 * P.Ntri) return;
+    const int e = P.tri_cam_e[P.tri_pairs[i]];
+    if(e >= 0)
+        for(int k = 0; k < 6; k++) N.active[N.reduced_index(P.i_extr0 + 6 * e + k)] = 1;
+}
+
 // compact numbering of the active shared unknowns: one CTA
 __global__ void __launch_bounds__(1024)
 compact_scan_kernel(NormalBuffers N)
@@ -558,12 +568,13 @@ assemble_items_dmma_kernel(DevProblem P, NormalBuffers N, int ldD, const double*
 
 // Regularization rows touch shared unknowns only: one thread per row. A row whose unknowns are
 // inactive (touched by no observation) stays out of S: inactive_step_kernel deals with it
+// (Also used for the triangulated-point rows [m_begin, m_end) = [m_tri0, m_reg0): extrinsics only.)
 __global__ void assemble_reg_kernel(DevProblem P, NormalBuffers N, const double* __restrict__ x,
                                     const double* __restrict__ Jval, const int* __restrict__ Jcol,
-                                    const int* __restrict__ rowptr)
+                                    const int* __restrict__ rowptr, int m_begin, int m_end)
 {
-    const int m = P.m_reg0 + blockIdx.x * blockDim.x + threadIdx.x;
-    if(m >= P.Nmeas || !P.reg_owner) return;
+    const int m = m_begin + blockIdx.x * blockDim.x + threadIdx.x;
+    if(m >= m_end || !P.reg_owner) return;
     const int j0 = rowptr[m], j1 = rowptr[m + 1];
     const double xm = x[m];
     bool all_active = true;
@@ -858,6 +869,7 @@ bool normal_assemble(const DevProblem& dp, NormalBuffers& N, const EvalBuffers& 
     MB200_CUDA_CHECK(cudaMemsetAsync(N.stat, 0, 4 * sizeof(int), s));
     if(Nwi > 0) { item_columns_kernel<<<Nwi, 256, lmap_bytes, s>>>(dp, N, op.Jcol); (*nlaunch)++; }
     if(dp.reg_unity) { mark_reg_active_kernel<<<1, 32, 0, s>>>(dp, N); (*nlaunch)++; }
+    if(dp.Ntri > 0) { mark_tri_active_kernel<<<(2 * dp.Ntri + 127) / 128, 128, 0, s>>>(dp, N); (*nlaunch)++; }
     // sharded solve: every rank must number the union of the active sets identically
     if(comm_active() && N.n_r > 0 && !comm_allreduce_max_int(N.active, (size_t)N.n_r, s)) return false;
     compact_scan_kernel<<<1, 1024, 0, s>>>(N);
@@ -914,7 +926,12 @@ bool normal_assemble(const DevProblem& dp, NormalBuffers& N, const EvalBuffers& 
     const int Nreg = dp.Nmeas - dp.m_reg0;
     if(Nreg > 0)
     {
-        assemble_reg_kernel<<<(Nreg + 127) / 128, 128, 0, s>>>(dp, N, op.x, op.Jval, op.Jcol, d_rowptr);
+        assemble_reg_kernel<<<(Nreg + 127) / 128, 128, 0, s>>>(dp, N, op.x, op.Jval, op.Jcol, d_rowptr, dp.m_reg0, dp.Nmeas);
+        (*nlaunch)++;
+    }
+    if(dp.Ntri > 0)
+    {
+        assemble_reg_kernel<<<(dp.Ntri + 127) / 128, 128, 0, s>>>(dp, N, op.x, op.Jval, op.Jcol, d_rowptr, dp.m_tri0, dp.m_reg0);
         (*nlaunch)++;
     }
     if(N.Ngroups > 0)

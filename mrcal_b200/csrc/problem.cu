@@ -7,7 +7,7 @@ namespace mb200 {
 
 bool spline_segments_per_u(double* out, const mrcal_lensmodel_t* lm);   // layout.cpp
 
-static int lens_kind_of(const mrcal_lensmodel_t* lm)
+int lens_kind_of(const mrcal_lensmodel_t* lm)
 {
     switch(lm->type)
     {
@@ -96,6 +96,31 @@ mrcal_b200_problem_create(const double* intrinsics, const mrcal_pose_t* rt_cam_r
                           double calibration_object_spacing,
                           int calibration_object_width_n, int calibration_object_height_n)
 {
+    return mrcal_b200_problem_create_triangulated(intrinsics, rt_cam_ref, rt_ref_frame, points, calobject_warp,
+                                                  Ncameras_intrinsics, Ncameras_extrinsics, Nframes, Npoints, Npoints_fixed,
+                                                  observations_board, observations_point, Nobservations_board, Nobservations_point,
+                                                  nullptr, 0,
+                                                  observations_board_pool, observations_point_pool, lensmodel, imagersizes, sel,
+                                                  calibration_object_spacing, calibration_object_width_n, calibration_object_height_n);
+}
+
+extern "C" mrcal_b200_problem_t*
+mrcal_b200_problem_create_triangulated(const double* intrinsics, const mrcal_pose_t* rt_cam_ref, const mrcal_pose_t* rt_ref_frame,
+                          const mrcal_point3_t* points, const mrcal_calobject_warp_t* calobject_warp,
+                          int Ncameras_intrinsics, int Ncameras_extrinsics, int Nframes,
+                          int Npoints, int Npoints_fixed,
+                          const mrcal_observation_board_t* observations_board,
+                          const mrcal_observation_point_t* observations_point,
+                          int Nobservations_board, int Nobservations_point,
+                          const mrcal_observation_point_triangulated_t* observations_point_triangulated,
+                          int Nobservations_point_triangulated,
+                          const mrcal_point3_t* observations_board_pool,
+                          const mrcal_point3_t* observations_point_pool,
+                          const mrcal_lensmodel_t* lensmodel, const int* imagersizes,
+                          mrcal_problem_selections_t sel,
+                          double calibration_object_spacing,
+                          int calibration_object_width_n, int calibration_object_height_n)
+{
     if(mrcal_b200_device_count() <= 0)
     {
         set_error("no usable CUDA device: libmrcal_b200 has no CPU fallback");
@@ -128,8 +153,41 @@ mrcal_b200_problem_create(const double* intrinsics, const mrcal_pose_t* rt_cam_r
         return nullptr;
     }
 
+    // triangulated points: pairs within each set of consecutive observations (mrcal.c:5197-5290)
+    std::vector<int> tri_pairs, tri_cam_e, tri_outlier;
+    std::vector<double> tri_px;
+    if(observations_point_triangulated == nullptr || Nobservations_point_triangulated < 0) Nobservations_point_triangulated = 0;
+    if(Nobservations_point_triangulated > 0)
+    {
+        // the reference's rule (mrcal.c:6260-6275)
+        if(sel.do_optimize_intrinsics_core || sel.do_optimize_intrinsics_distortions || !sel.do_optimize_extrinsics)
+        {
+            set_error("ERROR: We have triangulated points. At this time this is only allowed if we're NOT optimizing intrinsics AND if we ARE optimizing extrinsics.");
+            return nullptr;
+        }
+        const int N = Nobservations_point_triangulated;
+        if(!observations_point_triangulated[N - 1].last_in_set)
+        { set_error("the last triangulated observation must close its set (last_in_set)"); return nullptr; }
+        for(int i = 0; i < N; i++)
+        {
+            const auto& o = observations_point_triangulated[i];
+            if(o.icam.intrinsics < 0 || o.icam.intrinsics >= Ncameras_intrinsics || o.icam.extrinsics >= Ncameras_extrinsics)
+            { set_error("triangulated observation %d has out-of-range indices", i); return nullptr; }
+            tri_cam_e.push_back(o.icam.extrinsics < 0 ? -1 : o.icam.extrinsics);
+            tri_outlier.push_back(o.outlier ? 1 : 0);
+            tri_px.push_back(o.px.x); tri_px.push_back(o.px.y); tri_px.push_back(o.px.z);
+            if(o.last_in_set) continue;
+            for(int i1 = i + 1; i1 < N; i1++)
+            {
+                tri_pairs.push_back(i); tri_pairs.push_back(i1);
+                if(observations_point_triangulated[i1].last_in_set) break;
+            }
+        }
+    }
+
     std::unique_ptr<mrcal_b200_problem> P(new mrcal_b200_problem());
     Dims d;
+    d.Nmeas_tri = (int)(tri_pairs.size() / 2);
     d.Ncam_i = Ncameras_intrinsics; d.Ncam_e = Ncameras_extrinsics; d.Nframes = Nframes;
     d.Npoints = Npoints; d.Npoints_fixed = Npoints_fixed;
     d.Nobs_board = Nobservations_board; d.Nobs_point = Nobservations_point;
@@ -182,6 +240,13 @@ mrcal_b200_problem_create(const double* intrinsics, const mrcal_pose_t* rt_cam_r
         P->h_obs_point[3 * i + 2] = observations_point[i].i_point;
     }
     P->h_point_j0[d.Nobs_point] = (int)j;
+    std::vector<int> tri_j0(d.Nmeas_tri + 1);
+    for(int ip = 0; ip < d.Nmeas_tri; ip++)
+    {
+        tri_j0[ip] = (int)j;
+        j += (tri_cam_e[tri_pairs[2 * ip]] >= 0 ? 6 : 0) + (tri_cam_e[tri_pairs[2 * ip + 1]] >= 0 ? 6 : 0);
+    }
+    tri_j0[d.Nmeas_tri] = (int)j;
     const int reg_j0 = (int)j;
     j += (long)(L.splined ? 2 : 1) * L.Nreg_dist + L.Nreg_center + 3 * L.Nreg_unity;
     if(j > 0x7fffffffL) { set_error("Jacobian has %ld nonzeros: too many for int32 indices", j); return nullptr; }
@@ -196,7 +261,11 @@ mrcal_b200_problem_create(const double* intrinsics, const mrcal_pose_t* rt_cam_r
     memset(&dp, 0, sizeof(dp));
     const size_t nfeat = (size_t)d.Nobs_board * d.W * d.H;
     int *d_obs_board, *d_obs_point, *d_board_j0, *d_point_j0, *d_imagersizes;
-    bool ok = A.alloc(&P->d_seed_intr, (size_t)d.Ncam_i * L.Nintr) && A.alloc(&P->d_seed_rtcam, 6 * (size_t)d.Ncam_e) &&
+    int *d_tri_pairs = nullptr, *d_tri_cam_e = nullptr, *d_tri_outlier = nullptr, *d_tri_j0 = nullptr;
+    double* d_tri_px = nullptr;
+    bool ok = A.alloc(&d_tri_pairs, tri_pairs.size()) && A.alloc(&d_tri_cam_e, tri_cam_e.size()) && A.alloc(&d_tri_outlier, tri_outlier.size()) &&
+              A.alloc(&d_tri_j0, tri_j0.size()) && A.alloc(&d_tri_px, tri_px.size()) &&
+              A.alloc(&P->d_seed_intr, (size_t)d.Ncam_i * L.Nintr) && A.alloc(&P->d_seed_rtcam, 6 * (size_t)d.Ncam_e) &&
               A.alloc(&P->d_seed_rtframe, 6 * (size_t)d.Nframes) && A.alloc(&P->d_seed_points, 3 * (size_t)d.Npoints) &&
               A.alloc(&P->d_seed_warp, 2, true) &&
               A.alloc(&P->d_pool_board, 3 * nfeat) && A.alloc(&P->d_pool_board_seed, 3 * nfeat) &&
@@ -221,8 +290,12 @@ mrcal_b200_problem_create(const double* intrinsics, const mrcal_pose_t* rt_cam_r
          upload(d_board_j0, P->h_board_j0.data(), P->h_board_j0.size(), s) &&
          upload(d_point_j0, P->h_point_j0.data(), P->h_point_j0.size(), s) &&
          upload(d_imagersizes, imagersizes, 2 * (size_t)d.Ncam_i, s) &&
-         upload(P->d_scale, scale.data(), scale.size(), s);
+         upload(P->d_scale, scale.data(), scale.size(), s) &&
+         upload(d_tri_pairs, tri_pairs.data(), tri_pairs.size(), s) && upload(d_tri_cam_e, tri_cam_e.data(), tri_cam_e.size(), s) &&
+         upload(d_tri_outlier, tri_outlier.data(), tri_outlier.size(), s) && upload(d_tri_j0, tri_j0.data(), tri_j0.size(), s) &&
+         upload(d_tri_px, tri_px.data(), tri_px.size(), s);
     if(!ok) return nullptr;
+    if(cudaStreamSynchronize(s) != cudaSuccess) { set_error("upload failed"); return nullptr; }   // the staging vectors go out of scope
 
     dp.Ncam_i = d.Ncam_i; dp.Ncam_e = d.Ncam_e; dp.Nframes = d.Nframes; dp.Npoints = d.Npoints;
     dp.Npoints_variable = L.Npoints_variable; dp.Nobs_board = d.Nobs_board; dp.Nobs_point = d.Nobs_point;
@@ -247,6 +320,10 @@ mrcal_b200_problem_create(const double* intrinsics, const mrcal_pose_t* rt_cam_r
     dp.obs_board = d_obs_board; dp.obs_board_pool = P->d_pool_board;
     dp.obs_point = d_obs_point; dp.obs_point_pool = P->d_pool_point;
     dp.board_j0 = d_board_j0; dp.point_j0 = d_point_j0; dp.reg_j0 = reg_j0;
+    dp.m_tri0 = L.m_tri0; dp.Ntri = d.Nmeas_tri;
+    dp.tri_px = d_tri_px; dp.tri_cam_e = d_tri_cam_e; dp.tri_outlier = d_tri_outlier; dp.tri_pairs = d_tri_pairs; dp.tri_j0 = d_tri_j0;
+    P->Noutliers_tri = 0;
+    for(int v : tri_outlier) P->Noutliers_tri += v;
     // the extrinsics regularization needs the frames off/extrinsics on case to see u_rtcam: always unpacked
 
     P->Nframes_global = d.Nframes;

@@ -54,6 +54,13 @@ struct DevProblem
     const int*    board_j0;        // [Nobs_board+1] index of each observation's first Jacobian entry
     const int*    point_j0;        // [Nobs_point+1]
     int           reg_j0;          // first Jacobian entry of the regularization rows
+    // triangulated points (mrcal.c:5180-5653): observation rays in camera coordinates, pairs of them
+    int           m_tri0, Ntri;    // first measurement, number of measurements (= pairs)
+    const double* tri_px;          // [Nobs_tri][3]
+    const int*    tri_cam_e;       // [Nobs_tri] icam_extrinsics (-1: at the reference)
+    const int*    tri_outlier;     // [Nobs_tri]
+    const int*    tri_pairs;       // [Ntri][2] observation indices i0 < i1
+    const int*    tri_j0;          // [Ntri+1] first Jacobian entry of each pair's row
 
     // the current state, unpacked (written by unpack_state_kernel each evaluation)
     double* u_intr;      // [Ncam_i][Nintr]

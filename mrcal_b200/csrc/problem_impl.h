@@ -63,6 +63,7 @@ struct mrcal_b200_problem
     std::vector<int> h_board_j0, h_point_j0;
     std::vector<int> h_obs_board;         // [Nobs][3] icam_i, icam_e, iframe
     std::vector<int> h_obs_point;
+    int Noutliers_tri = 0;                // triangulated observations flagged as outliers by the caller
 
     std::unique_ptr<mb200::SolverWorkspace, void (*)(mb200::SolverWorkspace*)> ws{nullptr, nullptr};
     int launches = 0;                     // kernel launches so far (this library's kernels only)

@@ -548,7 +548,7 @@ bool solver_run(mrcal_b200_problem* P, const mrcal_b200_solver_parameters_t* par
         // mrcal.c:6607-6612
         stats->rms_reproj_error__pixels = sqrt(norm2 / (double)L.Nmeas);
         stats->Noutliers_board = Noutliers;
-        stats->Noutliers_triangulated_point = 0;
+        stats->Noutliers_triangulated_point = P->Noutliers_tri;
     }
     if(info_out) *info_out = info;
     return true;

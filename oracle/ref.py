@@ -109,8 +109,47 @@ def _dp(a):
     return a.ctypes.data_as(C.c_void_p) if a is not None and a.size else None
 
 
+class ObservationPointTriangulated(C.Structure):
+    """mrcal_observation_point_triangulated_t (types.h:243-263); bits: 1 = last_in_set, 2 = outlier."""
+    _fields_ = [("icam_intrinsics", C.c_int), ("icam_extrinsics", C.c_int),
+                ("bits", C.c_uint8), ("px", C.c_double * 3)]
+
+
+def unproject(q, lensmodel_name, intrinsics):
+    """Observation rays of pixels q (N,2). Closed-form models: the reference's mrcal_unproject (mrcal.c:3082).
+    The others: the reference inverts them with libdogleg, which this build stubs out, so the same fixed point
+    is found here by Newton's method on the reference's OWN mrcal_project() and its gradients, in the same
+    stereographic parametrisation (mrcal.c:3106-3270)."""
+    q = np.ascontiguousarray(q, dtype=np.float64).reshape(-1, 2)
+    intr = np.ascontiguousarray(intrinsics, dtype=np.float64)
+    if lensmodel_name in ("LENSMODEL_PINHOLE", "LENSMODEL_STEREOGRAPHIC", "LENSMODEL_LONLAT", "LENSMODEL_LATLON"):
+        lm = lensmodel_from_name(lensmodel_name)
+        v = np.zeros((q.shape[0], 3))
+        lib().mrcal_unproject.restype = C.c_bool
+        if not lib().mrcal_unproject(_dp(v), _dp(q), q.shape[0], C.byref(lm), _dp(intr)):
+            raise RuntimeError("reference mrcal_unproject() failed")
+        return v
+    xy = (q - intr[2:4]) / intr[0:2]
+    u = 2. * xy / (np.sqrt((xy * xy).sum(-1, keepdims=True) + 1.) + 1.)
+    for _ in range(50):
+        v = np.concatenate((u, 1. - 0.25 * (u * u).sum(-1, keepdims=True)), -1)
+        qq, g = project(v, lensmodel_name, intr, gradients=True)
+        r = qq - q
+        J = g[..., :2] - 0.5 * g[..., 2:3] * u[:, None, :]
+        du = -np.einsum("nij,nj->ni", np.linalg.pinv(J), r)
+        u = u + du
+        if np.abs(du).max() < 1e-15:
+            break
+    v = np.concatenate((u, 1. - 0.25 * (u * u).sum(-1, keepdims=True)), -1)
+    return v
+
+
 class Problem:
-    """Normalised view of a mrcal `optimization_inputs` dict (mrcal-pywrap.c:890-937)."""
+    """Normalised view of a mrcal `optimization_inputs` dict (mrcal-pywrap.c:890-937).
+
+    Triangulated points: `observations_point_triangulated` (N,3: pixel x, y, weight) with
+    `indices_point_triangulated_camintrinsics_camextrinsics` (N,3) as in the reference's Python API; the rays
+    come from unproject() above, as mrcal-pywrap.c:1383-1401 does it."""
 
     def __init__(self, kw):
         kw = dict(kw)
@@ -132,6 +171,23 @@ class Problem:
         self.indices_board = i4("indices_frame_camintrinsics_camextrinsics", (0, 3))
         self.observations_point = f8("observations_point", (0, 3)).copy()
         self.indices_point = i4("indices_point_camintrinsics_camextrinsics", (0, 3))
+        self.observations_tri = f8("observations_point_triangulated", (0, 3)).copy()
+        self.indices_tri = i4("indices_point_triangulated_camintrinsics_camextrinsics", (0, 3))
+        self.Nobs_tri = self.indices_tri.shape[0]
+        self.c_tri = None
+        if self.Nobs_tri:
+            rays = np.zeros((self.Nobs_tri, 3))
+            for icam in np.unique(self.indices_tri[:, 1]):
+                sel = np.flatnonzero(self.indices_tri[:, 1] == icam)
+                rays[sel] = unproject(self.observations_tri[sel, :2], self.lensmodel_name, self.intrinsics[icam])
+            self.triangulated_rays = rays
+            last = np.concatenate((np.diff(self.indices_tri[:, 0]) != 0, [True]))
+            self.c_tri = (ObservationPointTriangulated * self.Nobs_tri)()
+            for i in range(self.Nobs_tri):
+                o = self.c_tri[i]
+                o.icam_intrinsics, o.icam_extrinsics = int(self.indices_tri[i, 1]), int(self.indices_tri[i, 2])
+                o.bits = (1 if last[i] else 0) | (2 if self.observations_tri[i, 2] <= 0.0 else 0)
+                o.px[0], o.px[1], o.px[2] = rays[i]
         cw = kw.get("calobject_warp")
         self.calobject_warp = None if cw is None else np.ascontiguousarray(cw, dtype=np.float64).copy()
         self.Npoints_fixed = int(kw.get("Npoints_fixed", 0) or 0)
@@ -184,13 +240,13 @@ class Problem:
 
     def num_measurements(self):
         return lib().mrcal_num_measurements(
-            self.Nobs_board, self.Nobs_point, None, 0, self.W, self.H,
+            self.Nobs_board, self.Nobs_point, self.c_tri, self.Nobs_tri, self.W, self.H,
             self.Ncam_i, self.Ncam_e, self.Nframes, self.Npoints, self.Npoints_fixed,
             self.effective_selections(), C.byref(self.lensmodel))
 
     def num_j_nonzero(self):
         return lib()._mrcal_num_j_nonzero(
-            self.Nobs_board, self.Nobs_point, None, 0, self.W, self.H,
+            self.Nobs_board, self.Nobs_point, self.c_tri, self.Nobs_tri, self.W, self.H,
             self.Ncam_i, self.Ncam_e, self.Nframes, self.Npoints, self.Npoints_fixed,
             _dp(self.c_obs_board), _dp(self.c_obs_point),
             self.effective_selections(), C.byref(self.lensmodel))
@@ -224,7 +280,7 @@ class Problem:
             return l.mrcal_measurement_index_points(i, self.Nobs_board, self.Nobs_point, self.W, self.H)
         if what == "regularization":
             return l.mrcal_measurement_index_regularization(
-                None, 0, self.W, self.H, self.Ncam_i, self.Ncam_e, self.Nframes,
+                self.c_tri, self.Nobs_tri, self.W, self.H, self.Ncam_i, self.Ncam_e, self.Nframes,
                 self.Npoints, self.Npoints_fixed, self.Nobs_board, self.Nobs_point,
                 s, C.byref(self.lensmodel))
         raise KeyError(what)
@@ -265,7 +321,7 @@ class Problem:
             _dp(self.calobject_warp) if self.calobject_warp is not None else None,
             self.Ncam_i, self.Ncam_e, self.Nframes, self.Npoints, self.Npoints_fixed,
             _dp(self.c_obs_board), _dp(self.c_obs_point), self.Nobs_board, self.Nobs_point,
-            None, 0,
+            self.c_tri, self.Nobs_tri,
             _dp(self.observations_board), _dp(self.observations_point),
             C.byref(self.lensmodel), _dp(self.imagersizes),
             self.selections, None,
@@ -302,12 +358,19 @@ def project(p, lensmodel_name, intrinsics, gradients=False):
     intrinsics = np.ascontiguousarray(intrinsics, dtype=np.float64)
     N = p.shape[0]
     q = np.zeros((N, 2))
-    dq_dp = np.zeros((N, 2, 3)) if gradients else None
-    ok = lib().mrcal_project(_dp(q), _dp(dq_dp) if gradients else None, None,
-                             _dp(p), N, C.byref(lm), _dp(intrinsics))
-    if not ok:
-        raise RuntimeError("reference mrcal_project() failed")
-    return (q, dq_dp) if gradients else q
+    if not gradients:
+        if not lib().mrcal_project(_dp(q), None, None, _dp(p), N, C.byref(lm), _dp(intrinsics)):
+            raise RuntimeError("reference mrcal_project() failed")
+        return q
+    # one point per call: with N > 1 and no intrinsics gradients the reference writes every point's dq_dp
+    # into the first slot (mrcal.c:2894-2907 passes dq_dp, not &dq_dp[2*i])
+    dq_dp = np.zeros((N, 2, 3))
+    for i in range(N):
+        qi, gi, pi = np.zeros(2), np.zeros((2, 3)), np.ascontiguousarray(p[i])
+        if not lib().mrcal_project(_dp(qi), _dp(gi), None, _dp(pi), 1, C.byref(lm), _dp(intrinsics)):
+            raise RuntimeError("reference mrcal_project() failed")
+        q[i], dq_dp[i] = qi, gi
+    return q, dq_dp
 
 
 def compose_rt(rt0, rt1):

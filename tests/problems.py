@@ -27,13 +27,39 @@ def _mark_outliers(inputs, n, seed):
     return inputs
 
 
+def add_triangulated_points(inp, truth, Npoints, seed, pixel_noise=0.3, outliers=1):
+    """Triangulated-point observations (the reference's SfM-style measurements, mrcal.c:5180-5653) for an
+    existing problem: Npoints world points, each seen by 2 or more of the cameras; pixels = projection with
+    the problem's (locked) intrinsics + noise; weight <= 0 marks an outlier."""
+    rng = np.random.default_rng(seed)
+    Ncam = inp["intrinsics"].shape[0]
+    rt_all = np.concatenate((np.zeros((1, 6)), truth["rt_cam_ref"]))   # camera 0 sits at the reference
+    # in front of the middle of the rig
+    centre = np.mean([-synthetic.R_from_r(rt[:3]).T @ rt[3:] for rt in rt_all], axis=0)
+    obs, idx = [], []
+    for ipt in range(Npoints):
+        p_ref = centre + np.array((rng.uniform(-1., 1.), rng.uniform(-0.7, 0.7), rng.uniform(4., 8.)))
+        cams = np.sort(rng.choice(Ncam, size=rng.integers(2, Ncam + 1), replace=False))
+        for icam in cams:
+            p_cam = synthetic.transform_rt(rt_all[icam], p_ref)
+            q = synthetic.project(p_cam, inp["lensmodel"], inp["intrinsics"][icam]) + rng.normal(0, pixel_noise, 2)
+            obs.append((q[0], q[1], 1.0))
+            idx.append((ipt, icam, icam - 1))
+    obs = np.array(obs)
+    if outliers:
+        obs[rng.choice(obs.shape[0], outliers, replace=False), 2] = np.array((-1., 0.))[np.arange(outliers) % 2]
+    inp["observations_point_triangulated"] = obs
+    inp["indices_point_triangulated_camintrinsics_camextrinsics"] = np.array(idx, np.int32)
+    return inp
+
+
 def golden_cases():
     """(name, optimization_inputs). Small: the whole set evaluates in seconds."""
     cases = []
 
     def add(name, lensmodel, Ncameras, Nframes, sel=None, W=6, H=5, outliers=0, Npoints=0, Npoints_fixed=0,
-            which="all", point_outliers=0, seed=3, nowarp=False):
-        inp, _ = synthetic.make_problem(lensmodel=lensmodel, Ncameras=Ncameras, Nframes=Nframes, W=W, H=H,
+            which="all", point_outliers=0, seed=3, nowarp=False, Ntri=0, tri_outliers=1, tri_only=False):
+        inp, truth = synthetic.make_problem(lensmodel=lensmodel, Ncameras=Ncameras, Nframes=Nframes, W=W, H=H,
                                         seed=seed, pixel_noise=0.3, which=which, Npoints=Npoints,
                                         Npoints_fixed=Npoints_fixed)
         inp["calobject_warp"] = np.array((1e-3, -2e-3))   # away from 0 so its gradient is exercised
@@ -47,6 +73,13 @@ def golden_cases():
         if point_outliers:
             # both flavours of "outlier" for points: weight <0 and weight ==0 (mrcal.c:4918)
             inp["observations_point"][:point_outliers, 2] = np.array((-1., 0.))[np.arange(point_outliers) % 2]
+        if Ntri:
+            add_triangulated_points(inp, truth, Ntri, seed + 100, outliers=tri_outliers)
+            if tri_only:
+                # no boards, no discrete points: the extrinsics are the whole state
+                for k in ("observations_board", "indices_frame_camintrinsics_camextrinsics", "rt_ref_frame", "calobject_warp",
+                          "observations_point", "indices_point_camintrinsics_camextrinsics", "points", "Npoints_fixed"):
+                    inp.pop(k, None)
         cases.append((name, inp))
 
     for lm, tag in (("LENSMODEL_PINHOLE", "pinhole"), ("LENSMODEL_STEREOGRAPHIC", "stereographic"),
@@ -78,6 +111,14 @@ def golden_cases():
     add("cahvore_points", "LENSMODEL_CAHVORE_linearity=-0.25", 3, 3, _sel(True, True, True, True, True), Npoints=6, Npoints_fixed=1,
         outliers=3, which="some")
     add("cahvore_lin0_coreonly", "LENSMODEL_CAHVORE_linearity=0.00", 2, 3, _sel(True, False, True, True, True))
+    # triangulated points: intrinsics locked, extrinsics in the state (mrcal.c:6260-6275)
+    add("tri_pinhole_only", "LENSMODEL_PINHOLE", 3, 2, _sel(False, False, True, False, False), Ntri=7, tri_only=True)
+    add("tri_latlon_only", "LENSMODEL_LATLON", 2, 2, _sel(False, False, True, False, False), Ntri=5, tri_only=True, tri_outliers=0)
+    add("tri_opencv4_boards_points", "LENSMODEL_OPENCV4", 3, 3, _sel(False, False, True, True, True), Npoints=5,
+        Npoints_fixed=1, Ntri=6, tri_outliers=2, outliers=3)
+    add("tri_pinhole_unity_only", "LENSMODEL_PINHOLE", 3, 2, _sel(False, False, True, False, False, unity=True), Ntri=20,
+        tri_only=True)
+    add("tri_stereographic_unity", "LENSMODEL_STEREOGRAPHIC", 3, 3, _sel(False, False, True, True, False, unity=True), Ntri=4)
     return cases
 
 

@@ -19,11 +19,11 @@ GOLDEN = os.path.join(os.path.dirname(__file__), "golden")
 TOL = 1e-9
 
 
-def assert_close(a, b, what):
+def assert_close(a, b, what, tol=TOL):
     a, b = np.asarray(a), np.asarray(b)
     assert a.shape == b.shape, f"{what}: shape {a.shape} vs {b.shape}"
     err = np.abs(a - b) / (1. + np.abs(b))
-    assert err.size == 0 or err.max() <= TOL, f"{what}: worst relative-to-scale error {err.max():.3g} at {err.argmax()}"
+    assert err.size == 0 or err.max() <= tol, f"{what}: worst relative-to-scale error {err.max():.3g} at {err.argmax()}"
 
 
 @pytest.mark.parametrize("name,kw", problems.golden_cases(), ids=[c[0] for c in problems.golden_cases()])
@@ -35,7 +35,18 @@ def test_callback_matches_stored_reference_output(name, kw):
     assert np.array_equal(J.indices, g[f"{name}__Ji"]), "column indices differ"
     assert_close(b, g[f"{name}__b"], "b_packed")
     assert_close(x, g[f"{name}__x"], "x")
-    assert_close(J.data, g[f"{name}__Jx"], "J values")
+    if "observations_point_triangulated" in kw:
+        # The triangulated error is a small angle th = sqrt(2 - 2 cos) (triangulation.cc:781-817): the rounding of
+        # cos (1e-16) is amplified by 1/th^2 ~ 1e8 in d th, in the reference as much as here. The other rows
+        # keep the 1e-9 gate; these gradients agree to the accuracy either implementation has
+        m0 = mrcal_b200.measurement_index_points_triangulated(0, **kw)
+        m1 = m0 + mrcal_b200.num_measurements_points_triangulated(**kw)
+        j0, j1 = J.indptr[m0], J.indptr[m1]
+        assert_close(J.data[:j0], g[f"{name}__Jx"][:j0], "J values before the triangulated rows")
+        assert_close(J.data[j1:], g[f"{name}__Jx"][j1:], "J values after the triangulated rows")
+        assert_close(J.data[j0:j1], g[f"{name}__Jx"][j0:j1], "J values of the triangulated rows", tol=1e-6)
+    else:
+        assert_close(J.data, g[f"{name}__Jx"], "J values")
     # no_jacobian path gives the same x
     b2, x2, J2, f2 = mrcal_b200.optimizer_callback(**kw, no_jacobian=True, no_factorization=True)
     assert J2 is None and f2 is None

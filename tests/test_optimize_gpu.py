@@ -117,6 +117,19 @@ def test_optimize_selections(ref, sel):
     check_parity(r_gpu, kw_gpu, r_cpu)
 
 
+@pytest.mark.parametrize("name", ["tri_pinhole_unity_only", "tri_opencv4_boards_points", "tri_stereographic_unity"])
+def test_optimize_with_triangulated_points(ref, name):
+    """Triangulated-point measurements (mrcal.c:5180-5653) in the solve: intrinsics locked, extrinsics free.
+    (Rays alone leave the scale of the rig free: something else -- boards, or the unity_cam01 regularization
+    -- has to pin it, mrcal.c:5903-5954.)"""
+    kw = clone(dict(problems.golden_cases())[name])
+    kw["do_apply_outlier_rejection"] = False
+    r_gpu, kw_gpu, r_cpu = run_both(kw)
+    # (costs here are ~1e-6 rad^2: the absolute stopping rule leaves them less converged in relative terms)
+    check_parity(r_gpu, kw_gpu, r_cpu, tol_b=1e-4, tol_cost=1e-6)
+    assert r_gpu["Noutliers_triangulated_point"] == int((kw["observations_point_triangulated"][:, 2] <= 0).sum())
+
+
 def test_optimize_outlier_rejection(ref):
     kw, truth = synthetic.make_problem(lensmodel="LENSMODEL_OPENCV4", Ncameras=2, Nframes=12, W=8, H=7, seed=6,
                                        pixel_noise=0.3)
