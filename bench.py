@@ -152,6 +152,9 @@ def main():
     ap.add_argument("--impl", default="ours", choices=("ours", "reference"))
     ap.add_argument("--config", type=int, default=3)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--profile", action="store_true",
+                    help="run under a profiler: only the device-resident steps (no e2e leg, no CPU baseline, no DGEMM peak "
+                         "measurement); the numbers printed are not bench values")
     ap.add_argument("--max-iterations", type=int, default=300,
                     help="cap on trust-region iterations per solve (300 = the reference's; smaller only for profiling runs)")
     args = ap.parse_args()
@@ -246,6 +249,12 @@ def main():
 
     ###### e2e: the reference-facing call with host buffers, H2D + D2H inside the timed region
     e2e = None
+    if args.profile:
+        print(json.dumps({"profile_run": True, "iterations": int(its.sum()), "ms": dev_ms,
+                          "note": "run under a profiler: not a bench value"}))
+        if world > 1:
+            torch.distributed.destroy_process_group()
+        return 0
     if world > 1:
         # sharded: the public multi-GPU API (mrcal_b200.distributed): each step re-uploads this rank's host
         # inputs, solves, and brings the solution back (D2H + all-gather of the frame poses)
@@ -303,6 +312,11 @@ def main():
         return 0
 
     ###### roofline of the dominant kernel family
+    # DRAM traffic per launch of the kernels named below, from the committed ncu capture (null if absent)
+    try:
+        traffic = json.load(open(os.path.join(ROOT, "profiles", "r01b_dram_traffic.json")))
+    except Exception:
+        traffic = {}
     last = infos[-1]
     n_c = last["Nreduced"]
     roofline = None
@@ -311,8 +325,9 @@ def main():
         per_fact_s = 1e-3 * sum(i["ms_factor"] for i in infos) / max(1, sum(i["Nfactorizations"] for i in infos))
         flops = n_c ** 3 / 3.0
         achieved = flops / per_fact_s / 1e12
-        roofline = {"bound": "tensor", "kernel": "reduced-system Cholesky (potrf_diag + trsm + syrk_dmma, chol.cu)",
-                    "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak, "traffic": None,
+        roofline = {"bound": "tensor", "kernel": "reduced-system Cholesky: chol_dataflow_kernel (persistent, DMMA; chol_dataflow.cu)",
+                    "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
+                    "traffic": traffic.get("chol_dataflow_kernel"), "traffic_unit": "bytes per launch (ncu dram read+write)",
                     "flops_per_launch": flops, "n_reduced": n_c,
                     "peak_source": "cuBLAS DGEMM 8192^3 (torch.matmul fp64) measured in this run: MEASURED_PEAKS.json has no fp64 entry"}
     except Exception as e:   # pragma: no cover
@@ -328,7 +343,7 @@ def main():
     bytes_cb = 24 * ncorners + 8 * P.Nstate + 8 * P.Nmeasurements + 12 * P.N_j_nonzero + 4 * (P.Nmeasurements + 1)
     fill = {"bound": "hbm", "kernel": "eval_boards_kernel (residual + Jacobian fill)", "achieved": bytes_cb / (ms_cb * 1e-3) / 1e9,
             "peak": hbm, "unit": "GB/s", "frac": bytes_cb / (ms_cb * 1e-3) / 1e9 / hbm, "bytes_per_launch": bytes_cb,
-            "ms_per_launch": ms_cb, "peak_source": hbm_src, "traffic": None}
+            "ms_per_launch": ms_cb, "peak_source": hbm_src, "traffic": traffic.get("eval_boards_kernel")}
 
     ###### CPU baseline on this box's host cores: a bounded sample
     cpu = None
