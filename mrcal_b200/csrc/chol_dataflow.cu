@@ -14,8 +14,9 @@
 // deadlock. Waits are bounded all the same (a wedged GPU box costs more than a wrong
 // answer that the caller can detect): on timeout *info = -9.
 //
-// The critical path per 64 columns is  potrf_block + one flag hop + one triangular tile
-// + one flag hop + the last rank-64 update, instead of five kernel boundaries.
+// The diagonal tile and the tile left of it form one task of one CTA, so the critical path
+// per 64 columns is  potrf_block + one flag hop + one triangular tile product + the last
+// rank-64 update (from shared memory), instead of five kernel boundaries.
 //
 // Stands in for cholmod_factorize / cholmod_solve as libdogleg calls them (call site
 // mrcal.c:6435); the reference has no counterpart of this structure.
@@ -35,7 +36,8 @@ constexpr long long kSpinLimit = 4000000000ll;   // ~2 s of SM clocks
 
 struct DfSmem
 {
-    PotrfSmem pb;          // pb.L doubles as the C tile
+    PotrfSmem pb;          // pb.L doubles as the C tile of a diagonal tile
+    double C2[T * PLD];    // the C tile of an off-diagonal tile
     double opA[T * PLD];
     double opB[T * PLD];
     int ok;
@@ -116,96 +118,157 @@ __device__ __forceinline__ void tile_mma(double (&acc)[2][4][2], const double* A
             for(int j = 0; j < 4; j++) pb_dmma(acc[i][j][0], acc[i][j][1], af[i], bf[j]);
     }
 }
+__device__ __forceinline__ void acc_zero(double (&acc)[2][4][2])
+{
+#pragma unroll
+    for(int a = 0; a < 2; a++)
+#pragma unroll
+        for(int b = 0; b < 4; b++) acc[a][b][0] = acc[a][b][1] = 0.;
+}
+// C -= acc for a [64][PLD] tile in shared memory (each thread its own fragment elements)
+__device__ __forceinline__ void tile_sub(double* C, const double (&acc)[2][4][2])
+{
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int wm = warp >> 1, wn = warp & 1, g = lane >> 2, t = lane & 3;
+#pragma unroll
+    for(int a = 0; a < 2; a++)
+#pragma unroll
+        for(int b = 0; b < 4; b++)
+        {
+            double2* c = reinterpret_cast<double2*>(&C[(wm * 16 + a * 8 + g) * PLD + wn * 32 + b * 8 + 2 * t]);
+            double2 v = *c;
+            v.x -= acc[a][b][0];
+            v.y -= acc[a][b][1];
+            *c = v;
+        }
+}
+
+// X = C W' for a LOWER TRIANGULAR W (the inverse of a diagonal block): 8 warps as 8 x 1, warp tile 8 x 64, and
+// column tile j only needs k < 8 (j+1): 72 instead of 128 DMMAs per warp. X goes to global memory (row stride
+// ld) and, if Xs is given, to a [64][PLD] tile in shared memory too
+__device__ __forceinline__ void tile_trsm(const double* C, const double* W, double* __restrict__ Xg, size_t ld, double* Xs)
+{
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, g = lane >> 2, t = lane & 3;
+    double acc[8][2];
+#pragma unroll
+    for(int j = 0; j < 8; j++) acc[j][0] = acc[j][1] = 0.;
+    const double* a_s = C + (warp * 8) * PLD;
+#pragma unroll
+    for(int ks = 0; ks < T / 4; ks++)
+    {
+        const double af = a_s[g * PLD + ks * 4 + t];
+#pragma unroll
+        for(int j = 0; j < 8; j++)
+            if(ks * 4 < 8 * (j + 1))
+                pb_dmma(acc[j][0], acc[j][1], af, W[(j * 8 + g) * PLD + ks * 4 + t]);
+    }
+#pragma unroll
+    for(int j = 0; j < 8; j++)
+    {
+        const int r = warp * 8 + g, c = j * 8 + 2 * t;
+        const double2 v = make_double2(acc[j][0], acc[j][1]);
+        *reinterpret_cast<double2*>(&Xg[(size_t)r * ld + c]) = v;
+        if(Xs) *reinterpret_cast<double2*>(&Xs[r * PLD + c]) = v;
+    }
+}
 
 __device__ __forceinline__ int tile_flag(int i, int j, int nb) { return j * nb - (j * (j - 1)) / 2 + (i - j); }
 
+// Tasks, in the order every CTA walks them (each depends only on earlier ones):
+//   task 0: the diagonal tile (0,0);
+//   then column by column, j = 0 .. nb-2:  the DIAGONAL STEP d = j+1 first -- the tile (d,j) left of the diagonal
+//   AND the diagonal tile (d,d), by the same CTA: the freshly solved L_dj goes straight from shared memory into
+//   the last rank-64 update of the diagonal tile, no store -> flag -> load hop on the spine -- and after it the
+//   tiles (i,j), i >= j+2.
 __global__ void __launch_bounds__(256, 1)
 chol_dataflow_kernel(double* __restrict__ A, int ld, int nb, int nreal, double* __restrict__ invL, int* __restrict__ info,
                      int* __restrict__ flags, int* __restrict__ abort_flag)
 {
     extern __shared__ __align__(16) unsigned char dsm_raw[];
     DfSmem& sm = *reinterpret_cast<DfSmem*>(dsm_raw);
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int wm = warp >> 1, wn = warp & 1, g = lane >> 2, t = lane & 3;
-    const int ntiles = nb * (nb + 1) / 2;
+    const int tid = threadIdx.x;
+    const int ntasks = 1 + (nb - 1) * nb / 2;
+    double acc[2][4][2];
 
-    for(int tl = blockIdx.x; tl < ntiles; tl += gridDim.x)
+    for(int tl = blockIdx.x; tl < ntasks; tl += gridDim.x)
     {
-        int j = 0, rem = tl;
-        while(rem >= nb - j) { rem -= nb - j; j++; }
-        const int i = j + rem;
-        double* Aij = A + (size_t)i * T * ld + (size_t)j * T;
-
-        tile_to_smem(sm.pb.L, Aij, ld);
-        cp_commit();
-        double acc[2][4][2];
-#pragma unroll
-        for(int a = 0; a < 2; a++)
-#pragma unroll
-            for(int b = 0; b < 4; b++) acc[a][b][0] = acc[a][b][1] = 0.;
-
-        for(int k = 0; k < j; k++)
+        int i, j;
+        bool diag_step;
+        if(tl == 0) { i = 0; j = 0; diag_step = true; }
+        else
         {
-            if(!wait_flags(sm, flags + tile_flag(i, k, nb), i != j ? flags + tile_flag(j, k, nb) : nullptr, abort_flag, info)) return;
+            int rem = tl - 1;
+            j = 0;
+            while(rem >= nb - 1 - j) { rem -= nb - 1 - j; j++; }
+            diag_step = rem == 0;
+            i = j + 1 + rem;
+        }
+        // diag_step: d = i; tiles (d, j = d-1) [none for d = 0] and (d, d). Otherwise the tile (i, j), i >= j+2
+        const int d = i;
+        const bool have_left = diag_step && d > 0;
+        double* Aij = A + (size_t)i * T * ld + (size_t)j * T;          // (i,j): the left tile of a diagonal step
+        double* Add = A + (size_t)d * T * ld + (size_t)d * T;
+        const int kend = diag_step ? (d > 0 ? d - 1 : 0) : j;         // operands L_ik, L_jk for k < kend
+
+        if(!diag_step || have_left) tile_to_smem(sm.C2, Aij, ld);
+        if(diag_step) tile_to_smem(sm.pb.L, Add, ld);
+        cp_commit();
+        for(int k = 0; k < kend; k++)
+        {
+            if(!wait_flags(sm, flags + tile_flag(i, k, nb), flags + tile_flag(j, k, nb), abort_flag, info)) return;
             tile_to_smem(sm.opA, A + (size_t)i * T * ld + (size_t)k * T, ld);
-            if(i != j) tile_to_smem(sm.opB, A + (size_t)j * T * ld + (size_t)k * T, ld);
+            tile_to_smem(sm.opB, A + (size_t)j * T * ld + (size_t)k * T, ld);
             cp_commit();
             cp_wait_all();
             __syncthreads();
-            tile_mma(acc, sm.opA, i != j ? sm.opB : sm.opA);
+            acc_zero(acc);
+            tile_mma(acc, sm.opA, sm.opB);
+            tile_sub(sm.C2, acc);
+            if(diag_step)
+            {
+                acc_zero(acc);
+                tile_mma(acc, sm.opA, sm.opA);
+                tile_sub(sm.pb.L, acc);
+            }
             __syncthreads();
         }
         cp_wait_all();
         __syncthreads();
-        // C = A_ij - acc
-#pragma unroll
-        for(int a = 0; a < 2; a++)
-#pragma unroll
-            for(int b = 0; b < 4; b++)
-            {
-                double2* c = reinterpret_cast<double2*>(&sm.pb.L[(wm * 16 + a * 8 + g) * PLD + wn * 32 + b * 8 + 2 * t]);
-                double2 v = *c;
-                v.x -= acc[a][b][0];
-                v.y -= acc[a][b][1];
-                *c = v;
-            }
 
-        if(i == j)
+        if(!diag_step || have_left)
         {
-            potrf_block(sm.pb, info, j * T, nreal);
-            double* invLj = invL + (size_t)j * T * T;
-            for(int e = tid; e < T * T; e += 256)
-            {
-                const int r = e / T, c = e % T;
-                if(c <= r) Aij[(size_t)r * ld + c] = sm.pb.L[r * PLD + c];
-                invLj[e] = sm.pb.X[r * PLD + c];
-            }
-        }
-        else
-        {
-            __syncthreads();
+            // L_ij = C2 inv(L_jj)'
             if(!wait_flags(sm, flags + tile_flag(j, j, nb), nullptr, abort_flag, info)) return;
-            // inv(L_jj): dense 64x64 in global
-            const double* invLj = invL + (size_t)j * T * T;
-            tile_to_smem(sm.opB, invLj, T);
+            tile_to_smem(sm.opB, invL + (size_t)j * T * T, T);
             cp_commit();
             cp_wait_all();
             __syncthreads();
-#pragma unroll
-            for(int a = 0; a < 2; a++)
-#pragma unroll
-                for(int b = 0; b < 4; b++) acc[a][b][0] = acc[a][b][1] = 0.;
-            tile_mma(acc, sm.pb.L, sm.opB);
-#pragma unroll
-            for(int a = 0; a < 2; a++)
-#pragma unroll
-                for(int b = 0; b < 4; b++)
-                    *reinterpret_cast<double2*>(&Aij[(size_t)(wm * 16 + a * 8 + g) * ld + wn * 32 + b * 8 + 2 * t]) =
-                        make_double2(acc[a][b][0], acc[a][b][1]);
+            tile_trsm(sm.C2, sm.opB, Aij, ld, have_left ? sm.opA : nullptr);
+            __threadfence();
+            __syncthreads();
+            if(tid == 0) st_release(flags + tile_flag(i, j, nb), 1);
         }
-        __threadfence();
+        if(diag_step)
+        {
+            if(have_left)
+            {
+                acc_zero(acc);
+                tile_mma(acc, sm.opA, sm.opA);
+                tile_sub(sm.pb.L, acc);
+            }
+            potrf_block(sm.pb, info, d * T, nreal);
+            double* invLd = invL + (size_t)d * T * T;
+            for(int e = tid; e < T * T; e += 256)
+            {
+                const int r = e / T, c = e % T;
+                if(c <= r) Add[(size_t)r * ld + c] = sm.pb.L[r * PLD + c];
+                invLd[e] = sm.pb.X[r * PLD + c];
+            }
+            __threadfence();
+            __syncthreads();
+            if(tid == 0) st_release(flags + tile_flag(d, d, nb), 1);
+        }
         __syncthreads();
-        if(tid == 0) st_release(flags + tl, 1);
     }
 }
 
@@ -315,7 +378,7 @@ bool chol_factor_dataflow(double* A, int npad, int nreal, double* invL, int* d_i
 {
     if(!configure()) { set_error("the persistent Cholesky kernel is not available on this device"); return false; }
     int nb = npad / T;
-    const int ntiles = nb * (nb + 1) / 2;
+    const int ntiles = 1 + (nb - 1) * nb / 2;   // tasks: see the kernel
     MB200_CUDA_CHECK(cudaMemsetAsync(d_info, 0, sizeof(int), s));
     MB200_CUDA_CHECK(cudaMemsetAsync(g_flags, 0, (kMaxTiles + 1) * sizeof(int), s));
     int ld = npad;

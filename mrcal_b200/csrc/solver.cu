@@ -48,24 +48,32 @@ static void delete_ws(SolverWorkspace* w) { delete w; }
 ////////////////////////////////////////////////////////////////////////////////
 // small vector kernels
 ////////////////////////////////////////////////////////////////////////////////
-// out[0] += (J v).x ; out[1] += |J v|^2. One warp per row
+// out[0] += (J v).x ; out[1] += |J v|^2. Eight lanes per row (rows are 2..32 entries wide), four rows per warp
+// in flight: the kernel streams J once and wants as many loads outstanding as it can get
 __global__ void __launch_bounds__(256)
 jv_kernel(const int* __restrict__ rowptr, const int* __restrict__ col, const double* __restrict__ val,
           const double* __restrict__ v, const double* __restrict__ x, int Nrows, double* __restrict__ out)
 {
     __shared__ double red0[8], red1[8];
-    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5, sub = lane & 7;
     const int nwarps = (gridDim.x * blockDim.x) >> 5;
     double s0 = 0., s1 = 0.;
-    for(int row = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; row < Nrows; row += nwarps)
+    // (the loop bound is per WARP, so that all 32 lanes reach the shuffles together)
+    for(int row0 = ((blockIdx.x * blockDim.x + threadIdx.x) >> 5) * 4; row0 < Nrows; row0 += nwarps * 4)
     {
-        const int j0 = rowptr[row], j1 = rowptr[row + 1];
+        const int row = row0 + (lane >> 3);
+        const bool live = row < Nrows;
+        const int j0 = live ? rowptr[row] : 0, j1 = live ? rowptr[row + 1] : 0;
         double acc = 0.;
-        for(int j = j0 + lane; j < j1; j += 32) acc += val[j] * v[col[j]];
-#pragma unroll
-        for(int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
-        if(lane == 0) { s0 += acc * x[row]; s1 += acc * acc; }
+#pragma unroll 4
+        for(int j = j0 + sub; j < j1; j += 8) acc += val[j] * v[col[j]];
+        acc += __shfl_xor_sync(0xffffffffu, acc, 4);
+        acc += __shfl_xor_sync(0xffffffffu, acc, 2);
+        acc += __shfl_xor_sync(0xffffffffu, acc, 1);
+        if(sub == 0 && live) { s0 += acc * x[row]; s1 += acc * acc; }
     }
+#pragma unroll
+    for(int o = 16; o >= 8; o >>= 1) { s0 += __shfl_xor_sync(0xffffffffu, s0, o); s1 += __shfl_xor_sync(0xffffffffu, s1, o); }
     if(lane == 0) { red0[wib] = s0; red1[wib] = s1; }
     __syncthreads();
     if(threadIdx.x == 0)
