@@ -20,7 +20,7 @@ bool chol_solve(const double* L, int npad, const double* invL, double* B, int ld
 // if the persistent kernel gave up waiting (never expected; the alternative would be to hang the GPU)
 bool chol_solve_backward(const double* L, int npad, const double* invL, double* B, int ldb, int* d_info, cudaStream_t s, int* nlaunch);
 
-// chol_dataflow.cu: the same two operations as one persistent kernel each (n <= 2560)
+// chol_dataflow.cu: the same two operations as one persistent kernel each (n <= 8192)
 bool chol_dataflow_usable(int npad);
 bool chol_factor_dataflow(double* A, int npad, int nreal, double* invL, int* d_info, cudaStream_t s, int* nlaunch);
 bool chol_solve_backward_dataflow(const double* L, int npad, const double* invL, double* B, int* d_info, cudaStream_t s, int* nlaunch);

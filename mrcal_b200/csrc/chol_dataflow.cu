@@ -345,7 +345,7 @@ int* g_flags = nullptr;       // [kMaxTiles] tile flags, then [1] abort
 double* g_xbuf = nullptr;     // [kMaxBlocks * 64]
 int g_num_sms = 0;
 bool g_configured = false, g_unavailable = false;
-constexpr int kMaxBlocks = 40;
+constexpr int kMaxBlocks = 128;
 constexpr int kMaxTiles = kMaxBlocks * (kMaxBlocks + 1) / 2;
 
 bool configure()

@@ -13,7 +13,7 @@ for n in [int(a) for a in sys.argv[1:]] or [1268, 4820]:
     gf = n ** 3 / 3 / 1e9
     print(f"n={n}: multi-kernel graph {full_g:.3f} ms ({gf / full_g:.1f} TFLOP/s, GFLOP={gf:.2f}), direct launches {full_d:.3f} ms; "
           + ", ".join(f"{k} {v:.3f}" for k, v in parts.items()))
-    if n <= 2560:
+    if n <= 8192:
         fill = f(n, 10, 33, 0)
         df = f(n, 10, 32, 0) - fill
         print(f"n={n}: persistent factorization {df:.3f} ms ({gf / df:.1f} TFLOP/s); backward substitution: persistent {f(n, 20, 64, 0):.4f} ms, "
