@@ -531,6 +531,14 @@ void mrcal_b200_factorization_destroy(mrcal_b200_factorization_t* factorization)
 // row-major. Corresponds to solve_xt_JtJ_bt(bt, sys='A') (mrcal-pywrap.c:425-578)
 bool mrcal_b200_factorization_solve_xt_JtJ_bt(mrcal_b200_factorization_t* factorization,
                                               double* out, const double* bt, int Nrhs);
+// The other systems of solve_xt_JtJ_bt(bt, sys=...) (mrcal-pywrap.c:467-493 -> cholmod_solve2). The
+// factorization here is P JtJ P' = L D L' with P = I, D = I and L the Cholesky factor: A and LDLt solve the
+// whole system, LD and L solve L x = b, DLt and Lt solve L' x = b, D, P and Pt copy. CHOLMOD's own P and D
+// differ, the identities between the systems (what mrcal/model_analysis.py:837-841 relies on) hold
+enum { MRCAL_B200_SYS_A = 0, MRCAL_B200_SYS_LDLt, MRCAL_B200_SYS_LD, MRCAL_B200_SYS_DLt, MRCAL_B200_SYS_L,
+       MRCAL_B200_SYS_Lt, MRCAL_B200_SYS_D, MRCAL_B200_SYS_P, MRCAL_B200_SYS_Pt };
+bool mrcal_b200_factorization_solve_sys(mrcal_b200_factorization_t* factorization,
+                                        double* out, const double* bt, int Nrhs, int sys);
 // Reciprocal condition-number estimate from the diagonal of the factor, as
 // cholmod_rcond() defines it (mrcal-pywrap.c:580-593)
 double mrcal_b200_factorization_rcond(mrcal_b200_factorization_t* factorization);

@@ -111,7 +111,7 @@ EXPORTED_SYMBOLS = (
     "mrcal_b200_nccl_get_unique_id", "mrcal_b200_nccl_comm_init", "mrcal_b200_nccl_comm_destroy",
     "mrcal_b200_problem_set_sharding",
     "mrcal_b200_factorization_create", "mrcal_b200_factorization_destroy",
-    "mrcal_b200_factorization_solve_xt_JtJ_bt", "mrcal_b200_factorization_rcond",
+    "mrcal_b200_factorization_solve_xt_JtJ_bt", "mrcal_b200_factorization_solve_sys", "mrcal_b200_factorization_rcond",
 )
 
 if not os.path.exists(LIBPATH):
@@ -132,7 +132,7 @@ for _n in ["mrcal_lensmodel_from_name", "mrcal_lensmodel_name", "mrcal_knots_for
            "mrcal_b200_problem_reset", "mrcal_b200_problem_upload", "mrcal_b200_problem_callback",
            "mrcal_b200_problem_optimize", "mrcal_b200_problem_download", "mrcal_b200_problem_reduced_system",
            "mrcal_b200_nccl_get_unique_id", "mrcal_b200_nccl_comm_init", "mrcal_b200_problem_set_sharding",
-           "mrcal_b200_factorization_solve_xt_JtJ_bt", "mrcal_project", "mrcal_unproject"]:
+           "mrcal_b200_factorization_solve_xt_JtJ_bt", "mrcal_b200_factorization_solve_sys", "mrcal_project", "mrcal_unproject"]:
     getattr(lib, _n).restype = C.c_bool
 lib.mrcal_lensmodel_metadata.restype = Metadata
 lib.mrcal_lensmodel_name_unconfigured.restype = C.c_char_p

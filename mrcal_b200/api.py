@@ -536,16 +536,23 @@ class CHOLMOD_factorization:
             lib.mrcal_b200_factorization_destroy(self._h)
             self._h = None
 
+    _SYS = ("A", "LDLt", "LD", "DLt", "L", "Lt", "D", "P", "Pt")   # mrcal-pywrap.c:467-476; codes of mrcal_b200.h
+
     def solve_xt_JtJ_bt(self, bt, sys="A"):
-        if sys != "A":
-            raise RuntimeError(f"solve_xt_JtJ_bt(sys='{sys}'): only sys='A' is implemented in the CUDA backend")
+        """sys as in the reference (mrcal-pywrap.c:425-578, optionally spelled "CHOLMOD_..."). The factorization
+        here is P JtJ Pt = L D Lt with P = I, D = I: "P","Pt","D" return bt, "L"/"LD" solve L x = b, "Lt"/"DLt"
+        solve Lt x = b. CHOLMOD's own P and D differ; the identities between the systems hold."""
+        name = sys[len("CHOLMOD_"):] if isinstance(sys, str) and sys.startswith("CHOLMOD_") else sys
+        if name not in self._SYS:
+            raise RuntimeError(f"Unknown sys '{sys}' given. Known values of sys: ({','.join(self._SYS)},)")
+        code = self._SYS.index(name)
         bt = np.asarray(bt, dtype=np.float64)
         if bt.ndim < 1 or bt.shape[-1] != self.shape[1]:
             raise RuntimeError(f"bt must have shape (...,Nstate={self.shape[1]}); got {bt.shape}")
         flat = np.ascontiguousarray(bt.reshape(-1, self.shape[1]))
         out = np.empty_like(flat)
         if flat.shape[0]:
-            if not lib.mrcal_b200_factorization_solve_xt_JtJ_bt(self._h, _ptr(out), _ptr(flat), flat.shape[0]):
+            if not lib.mrcal_b200_factorization_solve_sys(self._h, _ptr(out), _ptr(flat), flat.shape[0], code):
                 raise RuntimeError("solve_xt_JtJ_bt: " + _capi.last_error())
         return out.reshape(bt.shape)
 

@@ -267,7 +267,7 @@ static bool syrk_update(double* A, int ld, int n, int c0, int c1, int k0, int k1
 }
 
 static bool chol_factor_enqueue(double* A, int npad, int nreal, double* invL, int* d_info, cudaStream_t s, int* nlaunch, int kinds = 7);
-static bool chol_solve_enqueue(const double* L, int npad, const double* invL, double* B, int ldb, int nrhs, cudaStream_t s, int* nlaunch);
+static bool chol_solve_enqueue(const double* L, int npad, const double* invL, double* B, int ldb, int nrhs, cudaStream_t s, int* nlaunch, int parts = 3);
 
 // The factorization is ~3 short kernels per 64-column block, all with launch-time-constant
 // arguments: replaying a captured CUDA graph takes the host out of the loop (the host would
@@ -330,11 +330,11 @@ bool chol_factor(double* A, int npad, int nreal, double* invL, int* d_info, cuda
                        [&](int* n) { return chol_factor_enqueue(A, npad, nreal, invL, d_info, s, n); });
 }
 
-bool chol_solve(const double* L, int npad, const double* invL, double* B, int ldb, int nrhs, cudaStream_t s, int* nlaunch)
+bool chol_solve(const double* L, int npad, const double* invL, double* B, int ldb, int nrhs, cudaStream_t s, int* nlaunch, int parts)
 {
-    if(nrhs != 1) return chol_solve_enqueue(L, npad, invL, B, ldb, nrhs, s, nlaunch);
-    return run_graphed(GraphKey{L, B, npad, ldb, 1}, s, nlaunch,
-                       [&](int* n) { return chol_solve_enqueue(L, npad, invL, B, ldb, 1, s, n); });
+    if(nrhs != 1) return chol_solve_enqueue(L, npad, invL, B, ldb, nrhs, s, nlaunch, parts);
+    return run_graphed(GraphKey{L, B, npad, ldb, 1 + 16 * parts}, s, nlaunch,
+                       [&](int* n) { return chol_solve_enqueue(L, npad, invL, B, ldb, 1, s, n, parts); });
 }
 
 static bool chol_solve_bwd_enqueue(const double* L, int npad, const double* invL, double* B, int ldb, cudaStream_t s, int* nlaunch);
@@ -437,10 +437,10 @@ solve_update_bwd_kernel(const double* __restrict__ L, int ld, double* __restrict
     }
 }
 
-static bool chol_solve_enqueue(const double* L, int npad, const double* invL, double* B, int ldb, int nrhs, cudaStream_t s, int* nlaunch)
+static bool chol_solve_enqueue(const double* L, int npad, const double* invL, double* B, int ldb, int nrhs, cudaStream_t s, int* nlaunch, int parts)
 {
     const int nblk = npad / NB;
-    for(int k = 0; k < nblk; k++)
+    for(int k = 0; k < nblk && (parts & 1); k++)
     {
         const int k0 = k * NB;
         solve_diag_kernel<<<nrhs, NB, 0, s>>>(invL + (size_t)k * NB * NB, B, ldb, k0, false);
@@ -452,7 +452,7 @@ static bool chol_solve_enqueue(const double* L, int npad, const double* invL, do
             if(nlaunch) (*nlaunch)++;
         }
     }
-    for(int k = nblk - 1; k >= 0; k--)
+    for(int k = nblk - 1; k >= 0 && (parts & 2); k--)
     {
         const int k0 = k * NB;
         solve_diag_kernel<<<nrhs, NB, 0, s>>>(invL + (size_t)k * NB * NB, B, ldb, k0, true);

@@ -13,8 +13,9 @@ inline int chol_padded(int n) { return ((n + kCholBlock - 1) / kCholBlock) * kCh
 // d_info: device int; 0 if positive definite, else 1 + index of the first bad pivot.
 bool chol_factor(double* A, int npad, int nreal, double* invL, int* d_info, cudaStream_t s, int* nlaunch);
 
-// Solve L L' X = B in place for nrhs right-hand sides stored as rows B[r][0..npad)
-bool chol_solve(const double* L, int npad, const double* invL, double* B, int ldb, int nrhs, cudaStream_t s, int* nlaunch);
+// Solve L L' X = B in place for nrhs right-hand sides stored as rows B[r][0..npad).
+// parts: 1 = only L Y = B, 2 = only L' X = B, 3 = both
+bool chol_solve(const double* L, int npad, const double* invL, double* B, int ldb, int nrhs, cudaStream_t s, int* nlaunch, int parts = 3);
 
 // Only the backward half, L' Z = B in place, one right-hand side. d_info (may be the factorization's): set to -9
 // if the persistent kernel gave up waiting (never expected; the alternative would be to hang the GPU)

@@ -110,14 +110,37 @@ extern "C" void mrcal_b200_factorization_destroy(mrcal_b200_factorization_t* F)
 
 extern "C" bool mrcal_b200_factorization_solve_xt_JtJ_bt(mrcal_b200_factorization_t* F, double* out, const double* bt, int Nrhs)
 {
+    return mrcal_b200_factorization_solve_sys(F, out, bt, Nrhs, MRCAL_B200_SYS_A);
+}
+
+// The factorization is P JtJ P' = L D L' with P = I (no fill-reducing permutation: the matrix is dense here),
+// L the Cholesky factor and D = I. The reference's CHOLMOD has its own P and a genuine D (simplicial LDL'), so
+// the individual pieces differ from CHOLMOD's -- but every identity between them holds, which is what callers
+// use (mrcal/model_analysis.py:837-841: sys='P', then 'L', then 'D')
+extern "C" bool mrcal_b200_factorization_solve_sys(mrcal_b200_factorization_t* F, double* out, const double* bt, int Nrhs, int sys)
+{
     if(Nrhs <= 0) return true;
+    int parts;
+    switch(sys)
+    {
+    case MRCAL_B200_SYS_A: case MRCAL_B200_SYS_LDLt: parts = 3; break;
+    case MRCAL_B200_SYS_LD: case MRCAL_B200_SYS_L:   parts = 1; break;
+    case MRCAL_B200_SYS_DLt: case MRCAL_B200_SYS_Lt: parts = 2; break;
+    case MRCAL_B200_SYS_D: case MRCAL_B200_SYS_P: case MRCAL_B200_SYS_Pt: parts = 0; break;
+    default: set_error("Unknown sys %d given", sys); return false;
+    }
+    if(parts == 0)
+    {
+        if(out != bt) memcpy(out, bt, (size_t)Nrhs * F->n * sizeof(double));
+        return true;
+    }
     DeviceArena tmp;
     double* d_b;
     if(!tmp.alloc(&d_b, (size_t)Nrhs * F->npad, true)) return false;
     cudaStream_t s = F->stream;
     MB200_CUDA_CHECK(cudaMemcpy2DAsync(d_b, (size_t)F->npad * sizeof(double), bt, (size_t)F->n * sizeof(double),
                                        (size_t)F->n * sizeof(double), Nrhs, cudaMemcpyHostToDevice, s));
-    if(!chol_solve(F->H, F->npad, F->invL, d_b, F->npad, Nrhs, s, nullptr)) return false;
+    if(!chol_solve(F->H, F->npad, F->invL, d_b, F->npad, Nrhs, s, nullptr, parts)) return false;
     MB200_CUDA_CHECK(cudaMemcpy2DAsync(out, (size_t)F->n * sizeof(double), d_b, (size_t)F->npad * sizeof(double),
                                        (size_t)F->n * sizeof(double), Nrhs, cudaMemcpyDeviceToHost, s));
     MB200_CUDA_CHECK(cudaStreamSynchronize(s));

@@ -33,8 +33,7 @@ def test_reference_known_answer():
     L = np.linalg.cholesky(JtJ)
     d = np.diag(L)
     assert np.isclose(F.rcond(), (d.min() / d.max()) ** 2, rtol=1e-10)
-    with pytest.raises(RuntimeError, match="sys="):
-        F.solve_xt_JtJ_bt(bt, sys="L")
+    assert np.allclose(F.solve_xt_JtJ_bt(bt, sys="L"), np.linalg.solve(L, bt.T).T, rtol=1e-12)
 
 
 @pytest.mark.parametrize("n,m,density", [(50, 200, 0.2), (64, 300, 0.1), (200, 1500, 0.05), (700, 6000, 0.02),
@@ -70,3 +69,37 @@ def test_optimizer_callback_returns_factorization():
     g = Jd.T @ x
     d = F.solve_xt_JtJ_bt(g)
     assert np.abs(Jd.T @ (Jd @ d) - g).max() / np.abs(g).max() < 1e-9
+
+
+def test_solve_systems():
+    """solve_xt_JtJ_bt(sys=...) (mrcal-pywrap.c:467-493). With P = I and D = I the factor L is THE Cholesky factor
+    of JtJ (unique), so 'L' and 'Lt' are pinned by numpy; the identities the reference's callers rely on
+    (mrcal/model_analysis.py:837-841: P, then L, then D, and A2 A3' = b' inv(JtJ) b) are checked as such."""
+    rng = np.random.default_rng(5)
+    J = scipy.sparse.random(400, 150, density=0.08, random_state=7, format="csr") + \
+        scipy.sparse.vstack((scipy.sparse.eye(150), scipy.sparse.csr_matrix((250, 150))))
+    F = mrcal_b200.CHOLMOD_factorization(J)
+    JtJ = (J.T @ J).toarray()
+    L = np.linalg.cholesky(JtJ)
+    bt = rng.normal(size=(7, 150))
+    tol = dict(rtol=0, atol=1e-9 * np.abs(bt).max())
+    xA = F.solve_xt_JtJ_bt(bt)
+    assert np.allclose(xA, np.linalg.solve(JtJ, bt.T).T, **tol)
+    assert np.allclose(F.solve_xt_JtJ_bt(bt, sys="LDLt"), xA, **tol)
+    for name in ("L", "LD", "CHOLMOD_L"):
+        assert np.allclose(F.solve_xt_JtJ_bt(bt, sys=name), np.linalg.solve(L, bt.T).T, **tol)
+    for name in ("Lt", "DLt"):
+        assert np.allclose(F.solve_xt_JtJ_bt(bt, sys=name), np.linalg.solve(L.T, bt.T).T, **tol)
+    for name in ("D", "P", "Pt"):
+        assert np.array_equal(F.solve_xt_JtJ_bt(bt, sys=name), bt)
+    # the chain the reference's uncertainty code runs
+    A1 = F.solve_xt_JtJ_bt(bt, sys="P")
+    A2 = F.solve_xt_JtJ_bt(A1, sys="L")
+    A3 = F.solve_xt_JtJ_bt(A2, sys="D")
+    assert np.allclose(A2 @ A3.T, bt @ np.linalg.solve(JtJ, bt.T), rtol=1e-9, atol=1e-12)
+    # and Lt after L is A (after undoing P)
+    assert np.allclose(F.solve_xt_JtJ_bt(F.solve_xt_JtJ_bt(F.solve_xt_JtJ_bt(A2, sys="D"), sys="Lt"), sys="Pt"), xA, **tol)
+    with pytest.raises(RuntimeError, match="Unknown sys"):
+        F.solve_xt_JtJ_bt(bt, sys="LL")
+    # a single right-hand side takes the graph path
+    assert np.allclose(F.solve_xt_JtJ_bt(bt[0], sys="L"), np.linalg.solve(L, bt[0]), **tol)
