@@ -553,8 +553,18 @@ bool solver_run(mrcal_b200_problem* P, const mrcal_b200_solver_parameters_t* par
     info.Nkernel_launches = P->launches - launches0;
     if(stats)
     {
-        // mrcal.c:6607-6612
-        stats->rms_reproj_error__pixels = sqrt(norm2 / (double)L.Nmeas);
+        // mrcal.c:6607-6612. Sharded: the measurement count of the whole problem (regularization counted once)
+        double nmeas = (double)L.Nmeas;
+        if(comm_active())
+        {
+            ws->h_scal[31] = (double)(P->dp.reg_owner ? L.Nmeas : P->dp.m_reg0);
+            MB200_CUDA_CHECK(cudaMemcpyAsync(ws->scal + 31, ws->h_scal + 31, sizeof(double), cudaMemcpyHostToDevice, s));
+            if(!comm_allreduce_sum(ws->scal + 31, 1, s)) return false;
+            MB200_CUDA_CHECK(cudaMemcpyAsync(ws->h_scal + 31, ws->scal + 31, sizeof(double), cudaMemcpyDeviceToHost, s));
+            MB200_CUDA_CHECK(cudaStreamSynchronize(s));
+            nmeas = ws->h_scal[31];
+        }
+        stats->rms_reproj_error__pixels = sqrt(norm2 / nmeas);
         stats->Noutliers_board = Noutliers;
         stats->Noutliers_triangulated_point = P->Noutliers_tri;
     }
