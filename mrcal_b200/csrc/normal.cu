@@ -692,7 +692,7 @@ __device__ bool spd_inverse(double* Dinv, const double* D, int n)
 // One CTA per elimination group (a frame, or a point): S -= B' D^-1 B over all
 // pairs of the group's items, g' = gs - B' D^-1 gf
 __global__ void __launch_bounds__(256)
-schur_groups_kernel(NormalBuffers N, double lambda)
+schur_groups_kernel(NormalBuffers N, double lambda, int ldc)
 {
     extern __shared__ __align__(16) double dsm[];   // C1[6][cap]
     __shared__ double s_Dinv[36], s_h[6], s_D[36], s_gf[6];
@@ -739,7 +739,11 @@ schur_groups_kernel(NormalBuffers N, double lambda)
         if(tid < 6)  N.grp_gf[(size_t)grp * 6 + tid] = s_gf[tid];
     }
 
-    double* C1 = dsm;   // [6][cap]: Dinv B1
+    // shared memory is sized by the widest item actually present (ldc), not by the capacity N.cap: more CTAs per SM,
+    // and this kernel lives on having many atomics in flight
+    double* C1 = dsm;                                      // [6][ldc]: Dinv B1
+    int* r1 = reinterpret_cast<int*>(dsm + 6 * ldc);       // [ldc] compact index of item 1's columns
+    int* r2 = r1 + ldc;                                    // [ldc] ... of item 2's
     // blockIdx.y picks the pairs (a1, a2 <= a1) with a1 = i0 + blockIdx.y, + gridDim.y, ...: more CTAs than groups
     for(int a1 = i0 + blockIdx.y; a1 < i1; a1 += gridDim.y)
     {
@@ -753,31 +757,35 @@ schur_groups_kernel(NormalBuffers N, double lambda)
             const int p = e / n1, l = e - p * n1;
             double t = 0.;
             for(int q = 0; q < nelim; q++) t += s_Dinv[p * 6 + q] * B1[(size_t)q * N.cap + l];
-            C1[p * N.cap + l] = t;
+            C1[p * ldc + l] = t;
         }
+        for(int l = tid; l < n1; l += 256) r1[l] = N.cidx[c1[l]];
         __syncthreads();
         // reduced gradient
         for(int l = tid; l < n1; l += 256)
         {
             double t = 0.;
             for(int p = 0; p < nelim; p++) t += B1[(size_t)p * N.cap + l] * s_h[p];
-            if(t != 0.) atomicAdd(&N.gs[N.cidx[c1[l]]], -t);
+            if(t != 0.) atomicAdd(&N.gs[r1[l]], -t);
         }
         for(int a2 = i0; a2 <= a1; a2++)
         {
             const int w2 = N.grp_items[a2];
             const int n2 = N.wi_nsh[w2];
-            const double* B2 = N.wi_B + (size_t)w2 * 6 * N.cap;
+            const double* __restrict__ B2 = N.wi_B + (size_t)w2 * 6 * N.cap;
             const int* c2 = N.wi_cols + (size_t)w2 * N.cap;
             const bool same = a1 == a2;
+            __syncthreads();
+            for(int l = tid; l < n2; l += 256) r2[l] = N.cidx[c2[l]];
+            __syncthreads();
             for(int e = tid; e < n1 * n2; e += 256)
             {
                 const int a = e / n2, b = e - a * n2;
                 if(same && b > a) continue;
                 double v = 0.;
-                for(int p = 0; p < nelim; p++) v += C1[p * N.cap + a] * B2[(size_t)p * N.cap + b];
+                for(int p = 0; p < nelim; p++) v += C1[p * ldc + a] * B2[(size_t)p * N.cap + b];
                 if(v == 0.) continue;
-                const int r = N.cidx[c1[a]], c = N.cidx[c2[b]];
+                const int r = r1[a], c = r2[b];
                 if(r > c)       atomicAdd(&N.S[(size_t)r * N.ldS + c], -v);
                 else if(r < c)  atomicAdd(&N.S[(size_t)c * N.ldS + r], -v);
                 else            atomicAdd(&N.S[(size_t)r * N.ldS + r], same ? -v : -2. * v);
@@ -856,8 +864,8 @@ bool normal_assemble(const DevProblem& dp, NormalBuffers& N, const EvalBuffers& 
     }
     const size_t lmap_bytes = ((size_t)dp.Nintr_state * sizeof(short) + 7) / 8 * 8;
     const size_t ccol_bytes = ((size_t)N.cap * sizeof(int) + 7) / 8 * 8;
-    const size_t smem_schur = (size_t)6 * N.cap * sizeof(double);
-    if(lmap_bytes + ccol_bytes + (size_t)7 * (N.cap + 6) * sizeof(double) > 200 * 1024 || smem_schur > 100 * 1024)
+    if(lmap_bytes + ccol_bytes + (size_t)7 * (N.cap + 6) * sizeof(double) > 200 * 1024 ||
+       (size_t)(N.cap + 8) * (6 * sizeof(double) + 2 * sizeof(int)) > 100 * 1024)
     {
         set_error("lens model with %d intrinsics per camera is too large for the assembly kernels", dp.Nintr_state);
         return false;
@@ -880,6 +888,8 @@ bool normal_assemble(const DevProblem& dp, NormalBuffers& N, const EvalBuffers& 
     // one padding row is always there: it carries the right-hand side through the factorization
     N.ldS = chol_padded(N.n_c + 1);
     const int max_ntot = N.h_stat[1];
+    const int ldc_schur = ((max_ntot > 0 ? max_ntot : 1) + 7) & ~7;   // widest item present (nsh + nelim >= nsh)
+    const size_t smem_schur = (size_t)ldc_schur * (6 * sizeof(double) + 2 * sizeof(int));
 
     // ---- pass 2: Gram matrices -> S, g', B, D
     const int gram_cap = max_ntot < kGramMax ? (max_ntot > 8 ? max_ntot : 8) : kGramMax;
@@ -936,7 +946,7 @@ bool normal_assemble(const DevProblem& dp, NormalBuffers& N, const EvalBuffers& 
     }
     if(N.Ngroups > 0)
     {
-        schur_groups_kernel<<<dim3(N.Ngroups, N.schur_split), 256, smem_schur, s>>>(N, lambda);
+        schur_groups_kernel<<<dim3(N.Ngroups, N.schur_split), 256, smem_schur, s>>>(N, lambda, ldc_schur);
         (*nlaunch)++;
     }
     if(comm_active())
