@@ -913,19 +913,43 @@ bool normal_assemble(const DevProblem& dp, NormalBuffers& N, const EvalBuffers& 
             auto ld_for = [](int T) { int ld = 8 * T; while(ld % 16 != 4) ld++; return ld; };
             auto smem_for = [&](int T) { return lmap_bytes + ccol_bytes + (size_t)DCH * ld_for(T) * sizeof(double); };
             (void)ldD;
+            // The size classes touch disjoint items (and add into S with atomics): they run side by side on forked
+            // streams, so that the CTAs of one fill the tails of the other
+            static cudaStream_t s_side[2] = {nullptr, nullptr};
+            static cudaEvent_t ev_fork = nullptr, ev_join[2] = {nullptr, nullptr};
+            if(ev_fork == nullptr)
+            {
+                MB200_CUDA_CHECK(cudaEventCreateWithFlags(&ev_fork, cudaEventDisableTiming));
+                for(int k = 0; k < 2; k++)
+                {
+                    MB200_CUDA_CHECK(cudaStreamCreateWithFlags(&s_side[k], cudaStreamNonBlocking));
+                    MB200_CUDA_CHECK(cudaEventCreateWithFlags(&ev_join[k], cudaEventDisableTiming));
+                }
+            }
+            const bool c1 = Tmax > kDmmaClassT[0], c2 = Tmax > kDmmaClassT[1];
+            if(c1 || c2)
+            {
+                MB200_CUDA_CHECK(cudaEventRecord(ev_fork, s));
+                if(c1) MB200_CUDA_CHECK(cudaStreamWaitEvent(s_side[0], ev_fork, 0));
+                if(c2) MB200_CUDA_CHECK(cudaStreamWaitEvent(s_side[1], ev_fork, 0));
+            }
             {
                 const int T0 = Tmax < kDmmaClassT[0] ? Tmax : kDmmaClassT[0];
                 assemble_items_dmma_kernel<kDmmaClassTiles[0], 0, kDmmaClassT[0]><<<Nwi, 256, smem_for(T0), s>>>(dp, N, ld_for(T0), op.x, op.Jval, op.Jcol);
             }
-            if(Tmax > kDmmaClassT[0])
+            if(c1)
             {
                 const int T1 = Tmax < kDmmaClassT[1] ? Tmax : kDmmaClassT[1];
-                assemble_items_dmma_kernel<kDmmaClassTiles[1], kDmmaClassT[0], kDmmaClassT[1]><<<Nwi, 256, smem_for(T1), s>>>(dp, N, ld_for(T1), op.x, op.Jval, op.Jcol);
+                assemble_items_dmma_kernel<kDmmaClassTiles[1], kDmmaClassT[0], kDmmaClassT[1]><<<Nwi, 256, smem_for(T1), s_side[0]>>>(dp, N, ld_for(T1), op.x, op.Jval, op.Jcol);
+                MB200_CUDA_CHECK(cudaEventRecord(ev_join[0], s_side[0]));
+                MB200_CUDA_CHECK(cudaStreamWaitEvent(s, ev_join[0], 0));
                 (*nlaunch)++;
             }
-            if(Tmax > kDmmaClassT[1])
+            if(c2)
             {
-                assemble_items_dmma_kernel<kDmmaClassTiles[2], kDmmaClassT[1], kDmmaClassT[2]><<<Nwi, 256, smem_for(Tmax), s>>>(dp, N, ld_for(Tmax), op.x, op.Jval, op.Jcol);
+                assemble_items_dmma_kernel<kDmmaClassTiles[2], kDmmaClassT[1], kDmmaClassT[2]><<<Nwi, 256, smem_for(Tmax), s_side[1]>>>(dp, N, ld_for(Tmax), op.x, op.Jval, op.Jcol);
+                MB200_CUDA_CHECK(cudaEventRecord(ev_join[1], s_side[1]));
+                MB200_CUDA_CHECK(cudaStreamWaitEvent(s, ev_join[1], 0));
                 (*nlaunch)++;
             }
         }
