@@ -314,7 +314,7 @@ def main():
     ###### roofline of the dominant kernel family
     # DRAM traffic per launch of the kernels named below, from the committed ncu capture (null if absent)
     try:
-        traffic = json.load(open(os.path.join(ROOT, "profiles", "r01b_dram_traffic.json")))
+        traffic = json.load(open(os.path.join(ROOT, "profiles", "r01c_dram_traffic.json")))
     except Exception:
         traffic = {}
     last = infos[-1]
