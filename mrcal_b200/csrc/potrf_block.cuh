@@ -92,6 +92,7 @@ __device__ __forceinline__ void potrf_block(PotrfSmem& sm, int* __restrict__ inf
             int firstbad = PSB;
 #pragma unroll
             for(int k = 0; k < PSB; k++) a[k] = k <= li ? sm.L[(c0 + li) * PLD + c0 + k] : 0.;
+            __syncwarp();   // (the loads above may touch the strictly upper part, which the loop below overwrites)
 #pragma unroll
             for(int j = 0; j < PSB; j++)
             {
