@@ -145,45 +145,43 @@ __device__ __forceinline__ void potrf_block(PotrfSmem& sm, int* __restrict__ inf
             const int c0 = p * PSB;
             const int m = PB - PSB - c0;   // rows below this panel
             if(warp == 1) PB_STAMP(33 + 6 * p);
-            // ---- B1: rows below D_p, X = A inv(D_p)', a row per thread, one group of 4 columns behind warp 0
-            // (the role split is per WARP: the named barriers inside must be reached by whole warps)
-            if(bw * 32 < m)
+            // ---- B1: rows below D_p, X = A inv(D_p)', a row per thread, one group of 4 columns behind warp 0; warp 7
+            // inverts D_p the same way (column `lane` of inv(D_p) = diag(1/L_jj) inv(Lt); lanes 16..31 shadow).
+            // The roles are per WARP, and every warp of the group waits at the SAME four barrier instructions
+            const bool consumer = bw * 32 < m;
+            const bool inverter = !consumer && warp == 7;
+            const bool mine = consumer && bt < m;
+            const int row = mine ? c0 + PSB + bt : PB - 1;
+            const int li = lane & 15;
+            double v[PSB];   // consumer: the row being solved;  inverter: column li of inv(Lt)
+#pragma unroll
+            for(int k = 0; k < PSB; k++) v[k] = consumer ? sm.L[row * PLD + c0 + k] : (k == li ? 1. : 0.);
+#pragma unroll
+            for(int jg = 0; jg < PSB / 4; jg++)
             {
-                const bool mine = bt < m;
-                const int row = mine ? c0 + PSB + bt : PB - 1;
-                double x[PSB];
-#pragma unroll
-                for(int k = 0; k < PSB; k++) x[k] = sm.L[row * PLD + c0 + k];
-#pragma unroll
-                for(int j = 0; j < PSB; j++)
+                pb_bar_sync(4 + jg, 256);   // columns 4 jg .. 4 jg + 3 of Lt and of R are in shared memory
+                if(consumer)
                 {
-                    if((j & 3) == 0) pb_bar_sync(4 + (j >> 2), 256);
-                    if(mine) sm.L[row * PLD + c0 + j] = x[j] * sm.R[c0 + j];   // x_j is final
 #pragma unroll
-                    for(int k = j + 1; k < PSB; k++) x[k] = fma(-x[j], sm.L[(c0 + j) * PLD + c0 + k], x[k]);
+                    for(int j = 4 * jg; j < 4 * jg + 4; j++)
+                    {
+                        if(mine) sm.L[row * PLD + c0 + j] = v[j] * sm.R[c0 + j];   // x_j is final
+#pragma unroll
+                        for(int k = j + 1; k < PSB; k++) v[k] = fma(-v[j], sm.L[(c0 + j) * PLD + c0 + k], v[k]);
+                    }
+                }
+                else if(inverter)
+                {
+#pragma unroll
+                    for(int k = 4 * jg; k < 4 * jg + 4; k++)
+#pragma unroll
+                        for(int i = k + 1; i < PSB; i++) v[i] = fma(-v[k], sm.L[(c0 + k) * PLD + c0 + i], v[i]);
                 }
             }
-            else if(warp == 7)
-            {
-                // column `lane` of inv(D_p) = diag(1/L_jj) inv(Lt)   (lanes 16..31 shadow)
-                const int li = lane & 15;
-                double y[PSB];
-#pragma unroll
-                for(int k = 0; k < PSB; k++) y[k] = k == li ? 1. : 0.;
-#pragma unroll
-                for(int k = 0; k < PSB; k++)
-                {
-                    if((k & 3) == 0) pb_bar_sync(4 + (k >> 2), 256);
-#pragma unroll
-                    for(int i = k + 1; i < PSB; i++) y[i] = fma(-y[k], sm.L[(c0 + k) * PLD + c0 + i], y[i]);
-                }
-#pragma unroll
-                for(int i = 0; i < PSB; i++) if(lane < PSB) sm.X[(c0 + i) * PLD + c0 + li] = i >= li ? y[i] * sm.R[c0 + i] : 0.;
-            }
-            else
+            if(inverter && lane < PSB)
             {
 #pragma unroll
-                for(int q = 0; q < PSB / 4; q++) pb_bar_sync(4 + q, 256);
+                for(int i = 0; i < PSB; i++) sm.X[(c0 + i) * PLD + c0 + li] = i >= li ? v[i] * sm.R[c0 + i] : 0.;
             }
             if(warp == 1) PB_STAMP(34 + 6 * p);
             pb_bar_sync(3, 224);
