@@ -691,7 +691,7 @@ __device__ bool spd_inverse(double* Dinv, const double* D, int n)
 
 // One CTA per elimination group (a frame, or a point): S -= B' D^-1 B over all
 // pairs of the group's items, g' = gs - B' D^-1 gf
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, 4)
 schur_groups_kernel(NormalBuffers N, double lambda, int ldc)
 {
     extern __shared__ __align__(16) double dsm[];   // C1[6][cap]
