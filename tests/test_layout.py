@@ -152,3 +152,43 @@ def test_corresponding_icam_extrinsics():
     kw = dict(problems.golden_cases())["splined3_3cam_all"]   # 3 cameras, camera 0 at the reference
     assert mrcal_b200.corresponding_icam_extrinsics(0, **kw) == -1
     assert mrcal_b200.corresponding_icam_extrinsics(2, **kw) == 1
+
+
+def test_triangulated_layout_and_validation(ref):
+    """The layout functions with triangulated points need the SETS only (no rays, no GPU): compare with the
+    compiled reference, and check the wrapper's complaints (mrcal-pywrap.c:1207-1240, 1406-1440)."""
+    cases = dict(problems.golden_cases())
+    for name in ("tri_pinhole_only", "tri_opencv4_boards_points", "tri_stereographic_unity"):
+        kw = cases[name]
+        P = ref.Problem(kw)
+        assert mrcal_b200.num_measurements(**kw) == P.num_measurements()
+        assert mrcal_b200.api._Inputs(dict(kw), for_layout_only=True).num_j_nonzero() == P.num_j_nonzero()
+        Ntri = mrcal_b200.num_measurements_points_triangulated(**kw)
+        idx = kw["indices_point_triangulated_camintrinsics_camextrinsics"]
+        assert Ntri == sum(n * (n - 1) // 2 for n in np.bincount(idx[:, 0]))
+        m0 = mrcal_b200.measurement_index_points_triangulated(0, **kw)
+        assert m0 == mrcal_b200.num_measurements_boards(**kw) + mrcal_b200.num_measurements_points(**kw)
+        assert mrcal_b200.measurement_index_regularization(**kw) in (None, m0 + Ntri)
+    kw = cases["tri_pinhole_only"]
+    idx = kw["indices_point_triangulated_camintrinsics_camextrinsics"]
+
+    def broken(f):
+        bad = idx.copy()
+        f(bad)
+        return dict(kw, indices_point_triangulated_camintrinsics_camextrinsics=bad)
+
+    # (the checks run where optimize()/optimizer_callback() parse their arguments; no GPU is touched before they pass)
+    check = lambda k: mrcal_b200.api._Inputs(dict(k))
+    check(kw)
+    with pytest.raises(RuntimeError, match="consecutive and monotonic"):
+        check(broken(lambda a: a.__setitem__((slice(None), 0), a[::-1, 0].copy())))
+    with pytest.raises(RuntimeError, match="icam_intrinsics MUST be"):
+        check(broken(lambda a: a.__setitem__((0, 1), 99)))
+    with pytest.raises(RuntimeError, match="icam_extrinsics MUST be"):
+        check(broken(lambda a: a.__setitem__((0, 2), 99)))
+    lonely = np.concatenate((idx, np.array(((idx[-1, 0] + 1, 0, -1),), np.int32)))
+    obs = np.concatenate((kw["observations_point_triangulated"], np.array(((1., 2., 1.),))))
+    with pytest.raises(RuntimeError, match="at least 2 times"):
+        check(dict(kw, indices_point_triangulated_camintrinsics_camextrinsics=lonely, observations_point_triangulated=obs))
+    with pytest.raises(RuntimeError, match="Inconsistent Nobservations_point_triangulated"):
+        check(dict(kw, observations_point_triangulated=obs))
