@@ -15,6 +15,7 @@ from .api import (  # noqa: F401
     num_measurements_points_triangulated, num_measurements_regularization,
     corresponding_icam_extrinsics, pack_state, unpack_state, project, unproject,
 )
+from .cameramodel import cameramodel, CameramodelParseException  # noqa: F401
 from ._capi import lib as _lib
 
 

@@ -82,6 +82,10 @@ class _Inputs:
         if unknown:
             raise RuntimeError(f"Unknown keyword argument(s): {sorted(unknown)}")
         for old, new in (("extrinsics_rt_fromref", "rt_cam_ref"), ("frames_rt_toref", "rt_ref_frame")):
+            # optimization_inputs read from a .cameramodel carry the old names as a poison string, which the reference's
+            # argument converter takes for "not given" (PyArray_Converter_checkrenamed_leaveNone, mrcal-pywrap.c:840-880)
+            if isinstance(kw.get(old), str) and kw[old].startswith("ERROR:"):
+                del kw[old]
             if old in kw:
                 if new in kw:
                     raise RuntimeError(f"Both '{old}' and '{new}' were given; use '{new}' only")
