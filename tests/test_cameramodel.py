@@ -8,9 +8,13 @@ import os
 import numpy as np
 import pytest
 
+import importlib
+
 import mrcal_b200
 import problems
-from mrcal_b200 import cameramodel as cm
+
+# mrcal_b200.cameramodel is the CLASS (as mrcal.cameramodel is); the module holds the helpers too
+cm = importlib.import_module("mrcal_b200.cameramodel")
 
 REFDATA = "/root/reference/test/data"
 
