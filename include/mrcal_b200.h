@@ -144,6 +144,19 @@ typedef struct
 // Part 1b. Lens-model description (host only)
 ////////////////////////////////////////////////////////////////////////////////
 
+// replaces internal.h:30-49, 85 (mrcal.c:1904-1965): quantities derived from the model configuration, computed
+// once. Only the splined model has one: segments_per_u = (Nx - 1 - margin) / (2 * 2 tan(fov_x/4)), margin 2 (cubic)
+// or 1 (quadratic)
+typedef struct
+{
+    bool ready;
+    union
+    {
+        struct { double segments_per_u; } LENSMODEL_SPLINED_STEREOGRAPHIC__precomputed;
+    };
+} mrcal_projection_precomputed_t;
+void _mrcal_precompute_lensmodel_data(mrcal_projection_precomputed_t* precomputed, const mrcal_lensmodel_t* lensmodel);
+
 // replaces mrcal.h:98-102 (mrcal.c:156-214)
 bool mrcal_lensmodel_from_name(mrcal_lensmodel_t* lensmodel, const char* name);
 // replaces mrcal.h:87 (mrcal.c:219-250)

@@ -81,7 +81,7 @@ SELECTION_BITS = ("do_optimize_intrinsics_core",
 
 # every symbol include/mrcal_b200.h declares; tests check the .so exports each
 EXPORTED_SYMBOLS = (
-    "mrcal_project", "mrcal_unproject", "mrcal_b200_problem_create_triangulated",
+    "_mrcal_precompute_lensmodel_data", "mrcal_project", "mrcal_unproject", "mrcal_b200_problem_create_triangulated",
     "mrcal_lensmodel_from_name", "mrcal_lensmodel_type_from_name", "mrcal_lensmodel_name",
     "mrcal_lensmodel_name_unconfigured", "mrcal_lensmodel_metadata", "mrcal_lensmodel_num_params",
     "mrcal_supported_lensmodel_names", "mrcal_knots_for_splined_models",
@@ -150,6 +150,7 @@ lib.mrcal_b200_factorization_rcond.restype = C.c_double
 lib.mrcal_b200_default_solver_parameters.restype = None
 lib.mrcal_b200_nccl_comm_destroy.restype = None
 lib.mrcal_pack_solver_state_vector.restype = None
+lib._mrcal_precompute_lensmodel_data.restype = None
 lib.mrcal_unpack_solver_state_vector.restype = None
 
 

@@ -311,6 +311,18 @@ bool spline_segments_per_u(double* out, const mrcal_lensmodel_t* lm)
 }
 }  // namespace mb200
 
+// replaces internal.h:85 / mrcal.c:1904-1965: the one derived quantity a lens model caches
+extern "C" void _mrcal_precompute_lensmodel_data(mrcal_projection_precomputed_t* precomputed, const mrcal_lensmodel_t* lensmodel)
+{
+    if(lensmodel->type == MRCAL_LENSMODEL_SPLINED_STEREOGRAPHIC)
+    {
+        double v = 0.;
+        if(!mb200::spline_segments_per_u(&v, lensmodel)) v = 0.;
+        precomputed->LENSMODEL_SPLINED_STEREOGRAPHIC__precomputed.segments_per_u = v;
+    }
+    precomputed->ready = true;
+}
+
 extern "C" bool mrcal_knots_for_splined_models(double* ux, double* uy, const mrcal_lensmodel_t* lensmodel)
 {
     if(lensmodel->type != MRCAL_LENSMODEL_SPLINED_STEREOGRAPHIC)

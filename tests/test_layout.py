@@ -42,6 +42,18 @@ def test_lensmodel_parsing_matches_reference(ref):
             _capi.lib.mrcal_lensmodel_type_from_name(bad.encode())
 
 
+def test_precomputed_lensmodel_data_matches_reference(ref):
+    class Pre(C.Structure):
+        _fields_ = [("ready", C.c_bool), ("segments_per_u", C.c_double)]
+    for name in (problems.SPL3, problems.SPL2, problems.SPL3_BIG, "LENSMODEL_OPENCV8"):
+        a, b = Pre(), Pre()
+        ref.lib()._mrcal_precompute_lensmodel_data(C.byref(a), C.byref(ref.lensmodel_from_name(name)))
+        _capi.lib._mrcal_precompute_lensmodel_data(C.byref(b), C.byref(mrcal_b200.api._lensmodel(name)))
+        assert a.ready and b.ready
+        if "SPLINED" in name:
+            assert a.segments_per_u == b.segments_per_u and a.segments_per_u > 0
+
+
 def test_knots_match_reference(ref):
     for name in (problems.SPL3, problems.SPL2, problems.SPL3_BIG):
         ux, uy = mrcal_b200.knots_for_splined_models(name)
