@@ -14,9 +14,10 @@ line (rank 0). See DESIGN.md "Measurement" for what every field means.
   e2e     the same metric through the reference-facing call mrcal_b200.optimize(**inputs)
           (C-ABI mrcal_optimize) with HOST buffers: H2D of every input and D2H of every
           output inside the timed region
-  --impl reference   the CPU path on this box's host cores: the compiled reference's own
-          optimizer_callback (oracle/_ref) driven by the restated libdogleg loop with a CPU
-          sparse factorization (oracle/dogleg_np.py); libdogleg/CHOLMOD are not in the image
+  --impl reference   the CPU path on this box's host cores: the reference's own compiled
+          mrcal_optimize() (oracle/_ref: mrcal.c unmodified) on top of a C restatement of
+          libdogleg + a simplicial sparse Cholesky (oracle/port/dogleg_port.c); libdogleg and
+          CHOLMOD themselves are not in the image. Single-threaded, like the reference.
 """
 import argparse
 import json
@@ -83,7 +84,11 @@ class ClockSampler:
 
 
 def problem_inputs(config):
-    from mrcal_b200 import synthetic
+    # loaded by path: importing the package would dlopen libmrcal_b200.so, which the reference arm must not touch
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("_mrcal_b200_synthetic", os.path.join(ROOT, "mrcal_b200", "synthetic.py"))
+    synthetic = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(synthetic)
     kw, truth = synthetic.baseline_config(config, pixel_noise=0.3)
     return kw
 
@@ -100,27 +105,30 @@ def describe(config, kw):
                    "126 MB L2; additionally a 256 MB buffer is written between timed steps")
 
 
-def cpu_reference_run(kw, iterations, verbose=False):
-    """`iterations` trust-region iterations of the CPU path from the seed; returns (iterations done, seconds, split)."""
-    from oracle import dogleg_np, ref
+def cpu_reference_run(kw, iterations):
+    """`iterations` trust-region iterations of the CPU path from the seed: the reference's compiled mrcal_optimize()
+    (oracle/_ref) with the iteration cap of the restated libdogleg set. Returns (iterations done, seconds, split)."""
+    from oracle import ref
     if not ref.available():
         return None
-    t_cb = [0.0]
-    t_fac = [0.0]
-    fac0 = dogleg_np.factor_solve
-
-    def timed_factor(A, rhs):
-        t = time.perf_counter()
-        out = fac0(A, rhs)
-        t_fac[0] += time.perf_counter() - t
-        return out
-
     kw2 = {k: (v.copy() if isinstance(v, np.ndarray) else v) for k, v in kw.items()}
+    kw2["do_apply_outlier_rejection"] = False   # a bounded sample: one pass
+    P = ref.Problem(kw2)
     t0 = time.perf_counter()
-    r = dogleg_np.optimize(kw2, factor=timed_factor, max_iterations=iterations)
+    r = P.optimize(iteration_cap=iterations)
     dt = time.perf_counter() - t0
-    return r["iterations"], dt, dict(factor_solve_s=t_fac[0], evaluations=r["evaluations"],
-                                     factorizations=r["factorizations"])
+    inside = r["t_callback"] + r["t_factor"] + r["t_products"]
+    return r["iterations"], dt, dict(callback_s=r["t_callback"], factor_solve_s=r["t_factor"], products_s=r["t_products"],
+                                     outside_callback_and_factor_frac=(dt - r["t_callback"] - r["t_factor"]) / dt,
+                                     solver_total_s=r["t_total"], wall_s=dt, accounted_frac=inside / dt,
+                                     evaluations=r["evaluations"], factorizations=r["factorizations"],
+                                     symbolic_analyses=r["symbolic"], nnz_L=r["Lnnz"])
+
+
+CPU_SAMPLE = ("first {n} trust-region iterations of the same problem from the same seed: the reference's own compiled "
+              "mrcal_optimize() (oracle/_ref; mrcal.c, its callback, pack/unpack and statistics unmodified) on a C "
+              "restatement of libdogleg with a simplicial sparse Cholesky (minimum-degree ordering, up-looking LL'), "
+              "oracle/port/dogleg_port.c; libdogleg/CHOLMOD themselves are absent from the image. 1 thread, as the reference")
 
 
 def measure_fp64_peak():
@@ -170,8 +178,8 @@ def main():
     if args.impl == "reference":
         if rank != 0:
             return 0
-        # a step = a bounded sample of the workload: the first 2 trust-region iterations from the seed
-        iters_per_step = 2
+        # a step = a bounded sample of the workload: the first 4 trust-region iterations from the seed
+        iters_per_step = 4
         ncores = os.cpu_count()
         for _ in range(min(args.warmup, 1)):
             cpu_reference_run(kw, 1)
@@ -183,9 +191,7 @@ def main():
                 return 0
             tot_it += r[0]; tot_s += r[1]; split = r[2]
         v = tot_it / tot_s
-        sample = (f"first {iters_per_step} trust-region iterations from the seed per step: compiled reference "
-                  "optimizer_callback (oracle/_ref) + restated libdogleg loop + scipy SuperLU symmetric-mode "
-                  "factorization of JtJ (libdogleg/CHOLMOD absent from the image); single-threaded like the reference")
+        sample = CPU_SAMPLE.format(n=iters_per_step) + " (per step)"
         print(json.dumps({"impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus,
                           "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * tot_s / args.steps,
                           "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64",
@@ -348,12 +354,10 @@ def main():
     ###### CPU baseline on this box's host cores: a bounded sample
     cpu = None
     if world == 1 and not args.no_cpu_baseline:
-        r = cpu_reference_run(kw, 2)
+        r = cpu_reference_run(kw, 6)
         if r is not None:
             cpu = {"value": r[0] / r[1], "unit": UNIT, "cores": 1, "kind": "port",
-                   "sample": "first 2 trust-region iterations of the same problem from the same seed: compiled reference "
-                             "optimizer_callback (oracle/_ref) + restated libdogleg loop + scipy SuperLU symmetric-mode "
-                             "factorization (libdogleg/CHOLMOD absent from the image)",
+                   "sample": CPU_SAMPLE.format(n=6),
                    "host_cores_available": os.cpu_count(), "split": r[2], "seconds": r[1]}
 
     out = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,

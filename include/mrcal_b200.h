@@ -512,6 +512,11 @@ bool mrcal_b200_problem_download(mrcal_b200_problem_t* problem,
                                  mrcal_calobject_warp_t* calobject_warp,
                                  mrcal_point3_t* observations_board_pool);
 
+// Outlier flags of the triangulated-point observations as they stand on the device (outlier rejection
+// adds to the flags the caller passed; the reference writes them into its input array,
+// mrcal.c:4231-4232,4370-4371). flags: [N] ints, may be NULL. Returns the number of observations; <0 on error
+int mrcal_b200_problem_triangulated_outliers(mrcal_b200_problem_t* problem, int* flags, int N);
+
 // Timing hook for benchmarks: run N cost-function evaluations (residuals +
 // Jacobian) at the current state back to back, return the mean device time per
 // evaluation in milliseconds (CUDA events on the library's stream); <0 on error

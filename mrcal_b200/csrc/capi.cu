@@ -198,5 +198,15 @@ extern "C" mrcal_stats_t mrcal_optimize(double* b_packed_final, int buffer_size_
     if(!mrcal_b200_problem_download(g.p, b_packed_final, x_final, intrinsics, rt_cam_ref, rt_ref_frame, points,
                                     calobject_warp, observations_board_pool))
         return bad;
+    if(observations_point_triangulated != nullptr && Nobservations_point_triangulated > 0 &&
+       problem_selections.do_apply_outlier_rejection)
+    {
+        // the reference marks new triangulated outliers in its (nominally const) input array
+        // (mrcal.c:4231-4232,4370-4371 through the cast at mrcal.c:6463): so does this
+        std::vector<int> flags(Nobservations_point_triangulated);
+        if(mrcal_b200_problem_triangulated_outliers(g.p, flags.data(), Nobservations_point_triangulated) < 0) return bad;
+        mrcal_observation_point_triangulated_t* o = (mrcal_observation_point_triangulated_t*)observations_point_triangulated;
+        for(int i = 0; i < Nobservations_point_triangulated; i++) if(flags[i]) o[i].outlier = 1;
+    }
     return stats;
 }

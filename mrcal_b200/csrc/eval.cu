@@ -725,11 +725,15 @@ static bool launch_kind(const DevProblem& dp, const EvalBuffers& out, bool with_
             // widest row: extrinsics present
             const int row2 = 2 * (dp.nnz_row_intr + (dp.opt_extr ? 6 : 0) + dp.nnz_row_board_geom);
             const size_t smem = (size_t)threads * (row2 + 1) * (sizeof(double) + sizeof(int)) + 16;
-            static bool configured[LENS_NKINDS] = {};
-            if(!configured[KIND])
+            // cudaFuncSetAttribute is per device: one flag per (device, lens kind)
+            static bool configured[kMaxDevices][LENS_NKINDS] = {};
+            int dev = 0;
+            MB200_CUDA_CHECK(cudaGetDevice(&dev));
+            if(dev < 0 || dev >= kMaxDevices) { set_error("device index %d out of range", dev); return false; }
+            if(!configured[dev][KIND])
             {
                 MB200_CUDA_CHECK(cudaFuncSetAttribute(eval_boards_kernel<KIND, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-                configured[KIND] = true;
+                configured[dev][KIND] = true;
             }
             if(smem > 200 * 1024) { set_error("Jacobian rows of %d entries are too wide for the staging buffer", row2 / 2); return false; }
             eval_boards_kernel<KIND, true ><<<dp.Nobs_board, threads, smem, stream>>>(dp, out.x, out.Jval, out.Jcol, out.norm2);
@@ -737,6 +741,7 @@ static bool launch_kind(const DevProblem& dp, const EvalBuffers& out, bool with_
         else
             eval_boards_kernel<KIND, false><<<dp.Nobs_board, threads, 0, stream>>>(dp, out.x, out.Jval, out.Jcol, out.norm2);
         (*nlaunch)++;
+        MB200_CUDA_CHECK(cudaGetLastError());
     }
     if(dp.Nobs_point > 0)
     {
@@ -771,18 +776,18 @@ bool launch_evaluate(const DevProblem& dp, const EvalBuffers& out, bool with_jac
     if(!launch_unpack_state(dp, out.p, stream, nlaunch)) return false;
     switch(dp.lens_kind)
     {
-    case LENS_PINHOLE:       launch_kind<LENS_PINHOLE>(dp, out, with_jacobian, stream, nlaunch); break;
-    case LENS_STEREOGRAPHIC: launch_kind<LENS_STEREOGRAPHIC>(dp, out, with_jacobian, stream, nlaunch); break;
-    case LENS_LONLAT:        launch_kind<LENS_LONLAT>(dp, out, with_jacobian, stream, nlaunch); break;
-    case LENS_LATLON:        launch_kind<LENS_LATLON>(dp, out, with_jacobian, stream, nlaunch); break;
-    case LENS_OPENCV4:       launch_kind<LENS_OPENCV4>(dp, out, with_jacobian, stream, nlaunch); break;
-    case LENS_OPENCV5:       launch_kind<LENS_OPENCV5>(dp, out, with_jacobian, stream, nlaunch); break;
-    case LENS_OPENCV8:       launch_kind<LENS_OPENCV8>(dp, out, with_jacobian, stream, nlaunch); break;
-    case LENS_OPENCV12:      launch_kind<LENS_OPENCV12>(dp, out, with_jacobian, stream, nlaunch); break;
-    case LENS_SPLINED3:      launch_kind<LENS_SPLINED3>(dp, out, with_jacobian, stream, nlaunch); break;
-    case LENS_SPLINED2:      launch_kind<LENS_SPLINED2>(dp, out, with_jacobian, stream, nlaunch); break;
-    case LENS_CAHVOR:        launch_kind<LENS_CAHVOR>(dp, out, with_jacobian, stream, nlaunch); break;
-    case LENS_CAHVORE:       launch_kind<LENS_CAHVORE>(dp, out, with_jacobian, stream, nlaunch); break;
+    case LENS_PINHOLE:       if(!launch_kind<LENS_PINHOLE>(dp, out, with_jacobian, stream, nlaunch)) return false; break;
+    case LENS_STEREOGRAPHIC: if(!launch_kind<LENS_STEREOGRAPHIC>(dp, out, with_jacobian, stream, nlaunch)) return false; break;
+    case LENS_LONLAT:        if(!launch_kind<LENS_LONLAT>(dp, out, with_jacobian, stream, nlaunch)) return false; break;
+    case LENS_LATLON:        if(!launch_kind<LENS_LATLON>(dp, out, with_jacobian, stream, nlaunch)) return false; break;
+    case LENS_OPENCV4:       if(!launch_kind<LENS_OPENCV4>(dp, out, with_jacobian, stream, nlaunch)) return false; break;
+    case LENS_OPENCV5:       if(!launch_kind<LENS_OPENCV5>(dp, out, with_jacobian, stream, nlaunch)) return false; break;
+    case LENS_OPENCV8:       if(!launch_kind<LENS_OPENCV8>(dp, out, with_jacobian, stream, nlaunch)) return false; break;
+    case LENS_OPENCV12:      if(!launch_kind<LENS_OPENCV12>(dp, out, with_jacobian, stream, nlaunch)) return false; break;
+    case LENS_SPLINED3:      if(!launch_kind<LENS_SPLINED3>(dp, out, with_jacobian, stream, nlaunch)) return false; break;
+    case LENS_SPLINED2:      if(!launch_kind<LENS_SPLINED2>(dp, out, with_jacobian, stream, nlaunch)) return false; break;
+    case LENS_CAHVOR:        if(!launch_kind<LENS_CAHVOR>(dp, out, with_jacobian, stream, nlaunch)) return false; break;
+    case LENS_CAHVORE:       if(!launch_kind<LENS_CAHVORE>(dp, out, with_jacobian, stream, nlaunch)) return false; break;
     default: set_error("lens model kind %d has no CUDA implementation", dp.lens_kind); return false;
     }
     if(dp.Ntri > 0)

@@ -154,7 +154,7 @@ mrcal_b200_problem_create_triangulated(const double* intrinsics, const mrcal_pos
     }
 
     // triangulated points: pairs within each set of consecutive observations (mrcal.c:5197-5290)
-    std::vector<int> tri_pairs, tri_cam_e, tri_outlier;
+    std::vector<int> tri_pairs, tri_cam_e, tri_outlier, tri_set_obs0, tri_set_m0;
     std::vector<double> tri_px;
     if(observations_point_triangulated == nullptr || Nobservations_point_triangulated < 0) Nobservations_point_triangulated = 0;
     if(Nobservations_point_triangulated > 0)
@@ -173,6 +173,11 @@ mrcal_b200_problem_create_triangulated(const double* intrinsics, const mrcal_pos
             const auto& o = observations_point_triangulated[i];
             if(o.icam.intrinsics < 0 || o.icam.intrinsics >= Ncameras_intrinsics || o.icam.extrinsics >= Ncameras_extrinsics)
             { set_error("triangulated observation %d has out-of-range indices", i); return nullptr; }
+            if(i == 0 || observations_point_triangulated[i - 1].last_in_set)
+            {
+                tri_set_obs0.push_back(i);
+                tri_set_m0.push_back((int)(tri_pairs.size() / 2));
+            }
             tri_cam_e.push_back(o.icam.extrinsics < 0 ? -1 : o.icam.extrinsics);
             tri_outlier.push_back(o.outlier ? 1 : 0);
             tri_px.push_back(o.px.x); tri_px.push_back(o.px.y); tri_px.push_back(o.px.z);
@@ -185,6 +190,7 @@ mrcal_b200_problem_create_triangulated(const double* intrinsics, const mrcal_pos
         }
     }
 
+    tri_set_obs0.push_back(Nobservations_point_triangulated);
     std::unique_ptr<mrcal_b200_problem> P(new mrcal_b200_problem());
     Dims d;
     d.Nmeas_tri = (int)(tri_pairs.size() / 2);
@@ -262,9 +268,12 @@ mrcal_b200_problem_create_triangulated(const double* intrinsics, const mrcal_pos
     const size_t nfeat = (size_t)d.Nobs_board * d.W * d.H;
     int *d_obs_board, *d_obs_point, *d_board_j0, *d_point_j0, *d_imagersizes;
     int *d_tri_pairs = nullptr, *d_tri_cam_e = nullptr, *d_tri_outlier = nullptr, *d_tri_j0 = nullptr;
+    int *d_tri_set_obs0 = nullptr, *d_tri_set_m0 = nullptr;
     double* d_tri_px = nullptr;
     bool ok = A.alloc(&d_tri_pairs, tri_pairs.size()) && A.alloc(&d_tri_cam_e, tri_cam_e.size()) && A.alloc(&d_tri_outlier, tri_outlier.size()) &&
               A.alloc(&d_tri_j0, tri_j0.size()) && A.alloc(&d_tri_px, tri_px.size()) &&
+              A.alloc(&d_tri_set_obs0, tri_set_obs0.size()) && A.alloc(&d_tri_set_m0, tri_set_m0.size()) &&
+              A.alloc(&P->d_tri_outlier_seed, tri_outlier.size()) &&
               A.alloc(&P->d_seed_intr, (size_t)d.Ncam_i * L.Nintr) && A.alloc(&P->d_seed_rtcam, 6 * (size_t)d.Ncam_e) &&
               A.alloc(&P->d_seed_rtframe, 6 * (size_t)d.Nframes) && A.alloc(&P->d_seed_points, 3 * (size_t)d.Npoints) &&
               A.alloc(&P->d_seed_warp, 2, true) &&
@@ -293,7 +302,9 @@ mrcal_b200_problem_create_triangulated(const double* intrinsics, const mrcal_pos
          upload(P->d_scale, scale.data(), scale.size(), s) &&
          upload(d_tri_pairs, tri_pairs.data(), tri_pairs.size(), s) && upload(d_tri_cam_e, tri_cam_e.data(), tri_cam_e.size(), s) &&
          upload(d_tri_outlier, tri_outlier.data(), tri_outlier.size(), s) && upload(d_tri_j0, tri_j0.data(), tri_j0.size(), s) &&
-         upload(d_tri_px, tri_px.data(), tri_px.size(), s);
+         upload(d_tri_px, tri_px.data(), tri_px.size(), s) &&
+         upload(d_tri_set_obs0, tri_set_obs0.data(), tri_set_obs0.size(), s) && upload(d_tri_set_m0, tri_set_m0.data(), tri_set_m0.size(), s) &&
+         upload(P->d_tri_outlier_seed, tri_outlier.data(), tri_outlier.size(), s);
     if(!ok) return nullptr;
     if(cudaStreamSynchronize(s) != cudaSuccess) { set_error("upload failed"); return nullptr; }   // the staging vectors go out of scope
 
@@ -322,8 +333,8 @@ mrcal_b200_problem_create_triangulated(const double* intrinsics, const mrcal_pos
     dp.board_j0 = d_board_j0; dp.point_j0 = d_point_j0; dp.reg_j0 = reg_j0;
     dp.m_tri0 = L.m_tri0; dp.Ntri = d.Nmeas_tri;
     dp.tri_px = d_tri_px; dp.tri_cam_e = d_tri_cam_e; dp.tri_outlier = d_tri_outlier; dp.tri_pairs = d_tri_pairs; dp.tri_j0 = d_tri_j0;
-    P->Noutliers_tri = 0;
-    for(int v : tri_outlier) P->Noutliers_tri += v;
+    dp.Ntri_sets = (int)tri_set_m0.size(); dp.tri_set_obs0 = d_tri_set_obs0; dp.tri_set_m0 = d_tri_set_m0;
+    P->Nobs_tri = Nobservations_point_triangulated;
     // the extrinsics regularization needs the frames off/extrinsics on case to see u_rtcam: always unpacked
 
     P->Nframes_global = d.Nframes;
@@ -417,6 +428,9 @@ extern "C" bool mrcal_b200_problem_reset(mrcal_b200_problem_t* P, const double* 
     if(nfeat)
         MB200_CUDA_CHECK(cudaMemcpyAsync(P->d_pool_board, P->d_pool_board_seed, 3 * nfeat * sizeof(double),
                                          cudaMemcpyDeviceToDevice, s));
+    if(P->Nobs_tri > 0)
+        MB200_CUDA_CHECK(cudaMemcpyAsync(P->dp.tri_outlier, P->d_tri_outlier_seed, (size_t)P->Nobs_tri * sizeof(int),
+                                         cudaMemcpyDeviceToDevice, s));
     MB200_CUDA_CHECK(cudaStreamSynchronize(s));
     return true;
 }
@@ -461,6 +475,19 @@ extern "C" bool mrcal_b200_problem_download(mrcal_b200_problem_t* P, double* b_p
 #undef D2H
     MB200_CUDA_CHECK(cudaStreamSynchronize(s));
     return true;
+}
+
+extern "C" int mrcal_b200_problem_triangulated_outliers(mrcal_b200_problem_t* P, int* flags, int N)
+{
+    if(flags == nullptr || N <= 0) return P->Nobs_tri;
+    if(N > P->Nobs_tri) N = P->Nobs_tri;
+    if(N > 0)
+    {
+        if(cudaMemcpyAsync(flags, P->dp.tri_outlier, (size_t)N * sizeof(int), cudaMemcpyDeviceToHost, P->stream) != cudaSuccess ||
+           cudaStreamSynchronize(P->stream) != cudaSuccess)
+        { set_error("triangulated_outliers: %s", cudaGetErrorString(cudaGetLastError())); return -1; }
+    }
+    return P->Nobs_tri;
 }
 
 extern "C" double mrcal_b200_problem_time_callback(mrcal_b200_problem_t* P, int N, bool with_jacobian)

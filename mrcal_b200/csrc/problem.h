@@ -17,6 +17,8 @@ namespace mb200 {
         }                                                                                 \
     } while(0)
 
+constexpr int kMaxDevices = 64;   // per-device one-time kernel configuration flags
+
 // Read-only description handed to every kernel BY VALUE (lives in the constant
 // bank; ~300 bytes). All pointers are device pointers.
 struct DevProblem
@@ -58,9 +60,12 @@ struct DevProblem
     int           m_tri0, Ntri;    // first measurement, number of measurements (= pairs)
     const double* tri_px;          // [Nobs_tri][3]
     const int*    tri_cam_e;       // [Nobs_tri] icam_extrinsics (-1: at the reference)
-    const int*    tri_outlier;     // [Nobs_tri]
+    int*          tri_outlier;     // [Nobs_tri] flags; outlier rejection adds to them (outliers.cu)
     const int*    tri_pairs;       // [Ntri][2] observation indices i0 < i1
     const int*    tri_j0;          // [Ntri+1] first Jacobian entry of each pair's row
+    int           Ntri_sets;       // triangulated points (sets of consecutive observations)
+    const int*    tri_set_obs0;    // [Ntri_sets+1] first observation of each set
+    const int*    tri_set_m0;      // [Ntri_sets] first measurement (pair) of each set, relative to m_tri0
 
     // the current state, unpacked (written by unpack_state_kernel each evaluation)
     double* u_intr;      // [Ncam_i][Nintr]

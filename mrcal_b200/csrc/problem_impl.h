@@ -34,7 +34,8 @@ struct DeviceArena
     }
 };
 
-struct SolverWorkspace;   // solver.cu
+struct SolverWorkspace;    // solver.cu
+struct OutlierWorkspace;   // outliers.cu
 
 }  // namespace mb200
 
@@ -63,9 +64,11 @@ struct mrcal_b200_problem
     std::vector<int> h_board_j0, h_point_j0;
     std::vector<int> h_obs_board;         // [Nobs][3] icam_i, icam_e, iframe
     std::vector<int> h_obs_point;
-    int Noutliers_tri = 0;                // triangulated observations flagged as outliers by the caller
+    int Nobs_tri = 0;                     // triangulated observations
+    int* d_tri_outlier_seed = nullptr;    // their outlier flags as given (reset() restores them)
 
     std::unique_ptr<mb200::SolverWorkspace, void (*)(mb200::SolverWorkspace*)> ws{nullptr, nullptr};
+    std::unique_ptr<mb200::OutlierWorkspace, void (*)(mb200::OutlierWorkspace*)> ows{nullptr, nullptr};
     int launches = 0;                     // kernel launches so far (this library's kernels only)
 
     // multi-GPU sharding (identity when single GPU)
@@ -78,6 +81,7 @@ bool problem_pack_seed(mrcal_b200_problem* P);                 // seed -> op[cur
 bool problem_evaluate(mrcal_b200_problem* P, int which, bool with_jacobian, bool with_rowptr);
 bool problem_unpack_to_seed_layout(mrcal_b200_problem* P, int which, double* d_intr, double* d_rtcam,
                                    double* d_rtframe, double* d_points, double* d_warp);
+bool outliers_mark(mrcal_b200_problem* P, bool* found, int* Noutliers_board, int* Noutliers_tri);   // outliers.cu
 bool solver_run(mrcal_b200_problem* P, const mrcal_b200_solver_parameters_t* params,
                 mrcal_stats_t* stats, mrcal_b200_solve_info_t* info);
 }  // namespace mb200

@@ -144,6 +144,16 @@ __global__ void scatter_shared_kernel(NormalBuffers N, const double* __restrict_
     if(r < N.n_r) step_full[N.state_index(r)] = ds[r];
 }
 
+// number of board corners with weight < 0 (mrcal.c:6420-6425). Integer atomics: order-independent
+__global__ void count_negative_kernel(const double* __restrict__ pool, long n, int* __restrict__ out)
+{
+    int c = 0;
+    for(long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long)gridDim.x * blockDim.x)
+        if(pool[3 * i + 2] < 0.0) c++;
+    for(int o = 16; o > 0; o >>= 1) c += __shfl_xor_sync(0xffffffffu, c, o);
+    if((threadIdx.x & 31) == 0 && c) atomicAdd(out, c);
+}
+
 ////////////////////////////////////////////////////////////////////////////////
 // workspace
 ////////////////////////////////////////////////////////////////////////////////
@@ -215,52 +225,26 @@ static bool build_workspace(mrcal_b200_problem* P)
     return true;
 }
 
-// Outlier marking on the host, exactly the board part of the reference's
-// markOutliers() (mrcal.c:4105-4357): sigma^2 from the inlier residuals; if any
-// |x| > 5 sigma, every |x| > 4 sigma is marked by negating its weight
-static bool mark_outliers_host(std::vector<double>& pool, const std::vector<double>& x, int Nobs, int WH,
-                               const int* obs /*icam_i,icam_e,iframe*/, int* Noutliers)
+static bool count_negative_weights(mrcal_b200_problem* P, int* count)
 {
-    const double k0 = 4.0, k1 = 5.0;
-    const size_t Nfeat = (size_t)Nobs * WH;
-    *Noutliers = 0;
-    long Ninliers = 0;
-    double var = 0.;
-    for(size_t i = 0; i < Nfeat; i++)
+    SolverWorkspace* ws = P->ws.get();
+    const Layout& L = P->L;
+    const long n = (long)L.d.Nobs_board * L.d.W * L.d.H;
+    int* d_cnt = ws->N.stat + 2;
+    MB200_CUDA_CHECK(cudaMemsetAsync(d_cnt, 0, sizeof(int), P->stream));
+    count_negative_kernel<<<296, 256, 0, P->stream>>>(P->d_pool_board, n, d_cnt);
+    P->launches++;
+    MB200_CUDA_CHECK(cudaMemcpyAsync(ws->h_info + 2, d_cnt, sizeof(int), cudaMemcpyDeviceToHost, P->stream));
+    MB200_CUDA_CHECK(cudaStreamSynchronize(P->stream));
+    *count = ws->h_info[2];
+    if(comm_active())
     {
-        if(pool[3 * i + 2] <= 0.0) { (*Noutliers)++; continue; }
-        var += x[2 * i] * x[2 * i] + x[2 * i + 1] * x[2 * i + 1];
-        Ninliers++;
-    }
-    var /= (double)(Ninliers * 2);
-    bool found = false;
-    for(size_t i = 0; i < Nfeat && !found; i++)
-    {
-        if(pool[3 * i + 2] <= 0.0) continue;
-        const double dx = x[2 * i], dy = x[2 * i + 1];
-        if(dx * dx > k1 * k1 * var || dy * dy > k1 * k1 * var) found = true;
-    }
-    if(!found) return false;
-    for(int o = 0; o < Nobs; o++)
-    {
-        int Nin = 0, Nout = 0;
-        for(int k = 0; k < WH; k++)
-        {
-            const size_t i = (size_t)o * WH + k;
-            if(pool[3 * i + 2] <= 0.0) { Nout++; continue; }
-            Nin++;
-            const double dx = x[2 * i], dy = x[2 * i + 1];
-            if(dx * dx > k0 * k0 * var || dy * dy > k0 * k0 * var)
-            {
-                pool[3 * i + 2] *= -1.0;
-                (*Noutliers)++;
-            }
-        }
-        if(Nin < 3)
-            fprintf(stderr, "mrcal_b200: WARNING: Board observation %d (icam_intrinsics=%d, icam_extrinsics=%d, iframe=%d) had almost "
-                            "all of its points thrown out as outliers: only %d/%d remain. The normal equations are about to "
-                            "become singular. Something is wrong with this observation\n",
-                    o, obs[3 * o], obs[3 * o + 1], obs[3 * o + 2], Nin, Nin + Nout);
+        ws->h_scal[31] = (double)*count;
+        MB200_CUDA_CHECK(cudaMemcpyAsync(ws->scal + 31, ws->h_scal + 31, sizeof(double), cudaMemcpyHostToDevice, P->stream));
+        if(!comm_allreduce_sum(ws->scal + 31, 1, P->stream)) return false;
+        MB200_CUDA_CHECK(cudaMemcpyAsync(ws->h_scal + 31, ws->scal + 31, sizeof(double), cudaMemcpyDeviceToHost, P->stream));
+        MB200_CUDA_CHECK(cudaStreamSynchronize(P->stream));
+        *count = (int)ws->h_scal[31];
     }
     return true;
 }
@@ -412,6 +396,11 @@ static bool dogleg_pass(mrcal_b200_problem* P, const mrcal_b200_solver_parameter
                             if(ws->h_scal[30] != 0. && ws->h_info[0] == 0 && ws->h_info[1] == 0) ws->h_info[0] = -1;
                         }
                         if(ws->h_info[0] == 0 && ws->h_info[1] == 0) break;
+                        if(ws->h_info[1] == -9)
+                        {
+                            set_error("the persistent factorization kernel gave up waiting for a tile (code -9): not a property of the matrix");
+                            return false;
+                        }
                         // singular JtJ: add lambda I "from now on", as libdogleg does (1e-10, then x10)
                         *lambda = (*lambda == 0.) ? 1e-10 : *lambda * 10.;
                         if(!std::isfinite(*lambda) || *lambda > 1e30) { set_error("the normal equations stay singular even with lambda=%g", *lambda); return false; }
@@ -513,28 +502,25 @@ bool solver_run(mrcal_b200_problem* P, const mrcal_b200_solver_parameters_t* par
     PhaseTimer T{ws, s};
     const int t0 = T.mark();
     const size_t Nfeat = (size_t)L.d.Nobs_board * L.d.W * L.d.H;
-    std::vector<double> h_pool, h_x;
-    int Noutliers = 0;
+    // stats as mrcal_optimize() initialises them (mrcal.c:6416-6425): board corners with weight < 0; the
+    // triangulated count stays 0 unless markOutliers() runs
+    int Noutliers = 0, Noutliers_tri = 0;
     if(Nfeat)
     {
-        h_pool.resize(3 * Nfeat);
-        MB200_CUDA_CHECK(cudaMemcpyAsync(h_pool.data(), P->d_pool_board, 3 * Nfeat * sizeof(double), cudaMemcpyDeviceToHost, s));
-        MB200_CUDA_CHECK(cudaStreamSynchronize(s));
-        for(size_t i = 0; i < Nfeat; i++) if(h_pool[3 * i + 2] < 0.0) Noutliers++;   // mrcal.c:6420-6425
+        if(!count_negative_weights(P, &Noutliers)) return false;
     }
     double lambda = 0., norm2 = -1.;
     while(true)
     {
         info.Nouter++;
+        // every pass is a fresh dogleg_optimize2() call in the reference (mrcal.c:6432-6439): lambda and the
+        // trust region start over
+        lambda = 0.;
         if(!dogleg_pass(P, par, &lambda, &info, &T, &norm2)) return false;
-        if(!(L.sel.do_apply_outlier_rejection && Nfeat)) break;
-        if(comm_active()) { set_error("outlier rejection is not implemented for sharded (multi-GPU) solves yet: pass do_apply_outlier_rejection=False"); return false; }
-        h_x.resize(L.Nmeas_board);
-        MB200_CUDA_CHECK(cudaMemcpyAsync(h_x.data(), P->op[P->cur].x, (size_t)L.Nmeas_board * sizeof(double), cudaMemcpyDeviceToHost, s));
-        MB200_CUDA_CHECK(cudaMemcpyAsync(h_pool.data(), P->d_pool_board, 3 * Nfeat * sizeof(double), cudaMemcpyDeviceToHost, s));
-        MB200_CUDA_CHECK(cudaStreamSynchronize(s));
-        if(!mark_outliers_host(h_pool, h_x, L.d.Nobs_board, L.d.W * L.d.H, P->h_obs_board.data(), &Noutliers)) break;
-        MB200_CUDA_CHECK(cudaMemcpyAsync(P->d_pool_board, h_pool.data(), 3 * Nfeat * sizeof(double), cudaMemcpyHostToDevice, s));
+        if(!L.sel.do_apply_outlier_rejection) break;
+        bool found = false;
+        if(!outliers_mark(P, &found, &Noutliers, &Noutliers_tri)) return false;
+        if(!found) break;
         fprintf(stderr, "mrcal_b200: Threw out some outliers. New count = %d/%d (%.1f%%). Going again\n",
                 Noutliers, L.Nmeas_board, (double)(Noutliers * 100) / (double)L.Nmeas_board);
     }
@@ -566,7 +552,7 @@ bool solver_run(mrcal_b200_problem* P, const mrcal_b200_solver_parameters_t* par
         }
         stats->rms_reproj_error__pixels = sqrt(norm2 / nmeas);
         stats->Noutliers_board = Noutliers;
-        stats->Noutliers_triangulated_point = P->Noutliers_tri;
+        stats->Noutliers_triangulated_point = Noutliers_tri;
     }
     if(info_out) *info_out = info;
     return true;

@@ -88,7 +88,10 @@ def shard_inputs(kw, rank, world):
                           ("do_optimize_calobject_warp", kw.get("observations_board") is not None)):
         if out.get(name) is None:
             out[name] = default
-    out["do_apply_outlier_rejection"] = False
+    # outlier rejection works sharded (the statistics and the "found" flag are all-reduced, outliers.cu); the
+    # default must be spelled out so that every rank takes the same path
+    if out.get("do_apply_outlier_rejection") is None:
+        out["do_apply_outlier_rejection"] = True
     for k in ("intrinsics", "rt_cam_ref", "calobject_warp"):
         if out.get(k) is not None:
             out[k] = out[k].copy()

@@ -5,7 +5,10 @@ poseutils*.c/.cc, triangulation.cc, cahvore.cc) compiled by oracle/Makefile from
 the sources where they lie under /root/reference. It is the ground truth for the
 callback half of the hot path: x, the CSR Jacobian, the state/measurement
 layout and pack/unpack. The solver half (libdogleg+CHOLMOD) is NOT in the
-reference tree; see oracle/dogleg_np.py for its restatement.
+reference tree: oracle/port/dogleg_port.c restates libdogleg behind its own
+interface and is linked into libmrcal_ref.so, so the reference's own
+mrcal_optimize() (markOutliers, outer loop, unpack, statistics) runs:
+Problem.optimize(). (oracle/dogleg_np.py is the same restatement in numpy.)
 
 Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline/reference legs
 may import this module. The product (mrcal_b200/) never does.
@@ -41,6 +44,12 @@ class Lensmodel(C.Structure):
 
 class Selections(C.Structure):
     _fields_ = [("bits", C.c_uint8)]
+
+
+class Stats(C.Structure):
+    """mrcal_stats_t (types.h:319-344)"""
+    _fields_ = [("rms_reproj_error__pixels", C.c_double), ("Noutliers_board", C.c_int),
+                ("Noutliers_triangulated_point", C.c_int)]
 
 
 class CholmodSparse(C.Structure):
@@ -333,6 +342,46 @@ class Problem:
             P, I, X = keep
             J = scipy.sparse.csr_matrix((X, I, P), shape=(Nmeas, Nstate))
         return b, x, J
+
+    def optimize(self, verbose=False, iteration_cap=0):
+        """The reference's own mrcal_optimize() (mrcal.c:6179) on top of the restated libdogleg
+        (oracle/port/dogleg_port.c). Modifies this Problem's state arrays and observation weights in
+        place, as the reference does. iteration_cap > 0 bounds the steps of each dogleg_optimize2() call
+        (benchmark samples). Returns dict(b_packed, x, rms_reproj_error__pixels, Noutliers_board,
+        Noutliers_triangulated_point, + the solver's counters and timers)."""
+        L = lib()
+        L.mrcal_optimize.restype = Stats
+        L.dogleg_port_set_iteration_cap(C.c_int(int(iteration_cap)))
+        L.dogleg_port_reset_stats()
+        Nstate, Nmeas = self.num_states(), self.num_measurements()
+        b = np.zeros(Nstate)
+        x = np.zeros(Nmeas)
+        st = L.mrcal_optimize(
+            _dp(b), C.c_int(b.nbytes), _dp(x), C.c_int(x.nbytes),
+            _dp(self.intrinsics), _dp(self.rt_cam_ref), _dp(self.rt_ref_frame), _dp(self.points),
+            _dp(self.calobject_warp) if self.calobject_warp is not None else None,
+            self.Ncam_i, self.Ncam_e, self.Nframes, self.Npoints, self.Npoints_fixed,
+            _dp(self.c_obs_board), _dp(self.c_obs_point), self.Nobs_board, self.Nobs_point,
+            self.c_tri, self.Nobs_tri,
+            _dp(self.observations_board), _dp(self.observations_point),
+            C.byref(self.lensmodel), _dp(self.imagersizes),
+            self.selections, None,
+            C.c_double(self.spacing), self.W, self.H, C.c_bool(bool(verbose)), C.c_bool(False))
+        L.dogleg_port_set_iteration_cap(C.c_int(0))
+        if st.rms_reproj_error__pixels < 0:
+            raise RuntimeError("reference mrcal_optimize() failed")
+        o = (C.c_double * 16)()
+        L.dogleg_port_get_stats(o)
+        if self.c_tri is not None:
+            self.tri_outlier = np.array([(self.c_tri[i].bits >> 1) & 1 for i in range(self.Nobs_tri)], np.int32)
+        return dict(b_packed=b, x=x, rms_reproj_error__pixels=float(st.rms_reproj_error__pixels),
+                    Noutliers_board=int(st.Noutliers_board),
+                    Noutliers_triangulated_point=int(st.Noutliers_triangulated_point),
+                    norm2_x=float(x @ x),
+                    iterations=int(o[0]), evaluations=int(o[1]), factorizations=int(o[2]),
+                    symbolic=int(o[3]), Lnnz=int(o[4]), passes=int(o[5]),
+                    t_callback=o[6], t_factor=o[7], t_products=o[8], t_total=o[9], lambda_=o[10],
+                    iterations_last_pass=int(o[12]))
 
     def pack_vector(self, b):
         b = np.ascontiguousarray(b, dtype=np.float64)

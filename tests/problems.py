@@ -135,3 +135,61 @@ def layout_numbers(P):
     for what in ("boards", "points", "regularization"):
         out.append(P.num_measurements_of(what))
     return out
+
+
+def inject_gross_outliers(inp, fraction, seed, shift=25.):
+    """Moves a fraction of the board corners by `shift` pixels (as test-basic-calibration.py:91-100 does with its
+    x20 noise), so that outlier rejection has something to find."""
+    rng = np.random.default_rng(seed)
+    flat = inp["observations_board"].reshape(-1, 3)
+    n = max(1, int(fraction * flat.shape[0]))
+    i = rng.choice(flat.shape[0], n, replace=False)
+    ang = rng.uniform(0, 2 * np.pi, n)
+    flat[i, 0] += shift * np.cos(ang)
+    flat[i, 1] += shift * np.sin(ang)
+    return inp
+
+
+def solve_cases():
+    """(name, optimization_inputs) whose SOLUTIONS by the reference's own mrcal_optimize() (on the restated
+    libdogleg, oracle/port/dogleg_port.c) are stored in tests/golden/solve_cases.npz by
+    tests/golden/make_solve_golden.py. BASELINE configs 1-3 exactly as bench.py builds them, the same with
+    gross outliers and outlier rejection on, and small problems that exercise points and triangulated
+    points in the outer loop."""
+    cases = []
+    for cfg in (1, 2, 3):
+        kw, _ = synthetic.baseline_config(cfg, pixel_noise=0.3)
+        cases.append((f"baseline{cfg}", kw))
+    for cfg, frac in ((1, 0.01), (2, 0.005)):
+        kw, _ = synthetic.baseline_config(cfg, pixel_noise=0.3)
+        inject_gross_outliers(kw, frac, 100 + cfg)
+        kw["do_apply_outlier_rejection"] = True
+        cases.append((f"baseline{cfg}_outliers", kw))
+    kw, _ = synthetic.make_problem(lensmodel=SPL3, Ncameras=2, Nframes=30, W=6, H=5, seed=11, pixel_noise=0.2)
+    inject_gross_outliers(kw, 0.01, 7)
+    kw["do_apply_outlier_rejection"] = True
+    cases.append(("splined3_outliers", kw))
+    kw, _ = synthetic.make_problem(lensmodel="LENSMODEL_OPENCV4", Ncameras=3, Nframes=8, W=6, H=5, seed=4,
+                                   pixel_noise=0.2, Npoints=12, Npoints_fixed=3, which="some")
+    inject_gross_outliers(kw, 0.02, 8)
+    kw["do_apply_outlier_rejection"] = True
+    cases.append(("opencv4_points_outliers", kw))
+    # triangulated points (intrinsics locked): the outlier loop has a triangulated branch too (mrcal.c:4150-4400)
+    for name in ("tri_pinhole_unity_only", "tri_opencv4_boards_points", "tri_stereographic_unity"):
+        kw = dict(dict(golden_cases())[name])
+        kw = {k: (v.copy() if isinstance(v, np.ndarray) else v) for k, v in kw.items()}
+        kw["do_apply_outlier_rejection"] = True
+        cases.append((name + "_rejection", kw))
+    # ... and one where that branch has work to do: two observations moved far enough that their rays diverge or
+    # their residual is many sigma out
+    inp, truth = synthetic.make_problem(lensmodel="LENSMODEL_PINHOLE", Ncameras=3, Nframes=2, W=6, H=5, seed=5, pixel_noise=0.3)
+    inp.update(_sel(False, False, True, False, False, unity=True))   # the scale of a points-only solve is free otherwise
+    add_triangulated_points(inp, truth, 40, 77, outliers=0)
+    for k in ("observations_board", "indices_frame_camintrinsics_camextrinsics", "rt_ref_frame", "calobject_warp"):
+        inp.pop(k, None)
+    inp["do_optimize_calobject_warp"] = False
+    o = inp["observations_point_triangulated"]
+    o[5, 0] += 900.; o[17, 1] -= 40.; o[60, 0] -= 25.
+    inp["do_apply_outlier_rejection"] = True
+    cases.append(("tri_divergent_rejection", inp))
+    return cases
