@@ -16,7 +16,7 @@
 // only the reduced result goes to global memory. For splined models the touched
 // knot columns are data-dependent (mrcal.c:2171-2185), so each CTA discovers
 // its own local column set every time.
-#include "normal.h"
+#include "normal_items.cuh"
 #include "chol.h"
 
 namespace mb200 {
@@ -32,60 +32,6 @@ bool comm_allreduce_max_int(int* d_buf, size_t count, cudaStream_t s);
 // built and factored over those alone; the untouched ones are solved from their regularization rows
 // directly (inactive_step_kernel). The reference gets the same saving from CHOLMOD's sparse
 // factorization.
-constexpr int kMaxRowNnz = 40;     // widest row: 16 intrinsics + 6 + 6 + 2 (any model here <= 30)
-constexpr int kGramMax   = 200;
-constexpr int RCH        = 16;     // rows staged per chunk in assemble_items_kernel (RCH*kMaxRowNnz <= 3*256)    // largest local column count whose Gram matrix lives in shared memory
-
-struct ItemDesc
-{
-    int rows, nnz_row, nI, j0, m0;
-    int cbase, clen;       // the camera's intrinsics block in the state vector
-    int cam0;              // first extrinsics column, or -1
-    int elim0, nelim;      // first eliminated column, count (6 frame / 3 point / 0)
-    int warp0;             // first warp column or -1
-    int group;             // elimination group or -1
-};
-
-__device__ __forceinline__ ItemDesc describe_item(const DevProblem& P, int w, int Nframe_groups)
-{
-    ItemDesc d;
-    d.nI = P.nnz_row_intr;
-    d.clen = P.Nintr_state;
-    if(w < P.Nobs_board)
-    {
-        const int icam_i = P.obs_board[3 * w + 0], icam_e = P.obs_board[3 * w + 1], iframe = P.obs_board[3 * w + 2];
-        d.rows = 2 * P.W * P.H;
-        d.j0 = P.board_j0[w];
-        d.nnz_row = (P.board_j0[w + 1] - d.j0) / d.rows;
-        d.m0 = d.rows * w;
-        d.cbase = P.i_intr0 + icam_i * P.Nintr_state;
-        d.cam0 = (P.opt_extr && icam_e >= 0) ? P.i_extr0 + 6 * icam_e : -1;
-        d.nelim = P.opt_frames ? 6 : 0;
-        d.elim0 = P.opt_frames ? P.i_frame0 + 6 * iframe : -1;
-        d.warp0 = P.opt_warp ? P.i_warp0 : -1;
-        d.group = P.opt_frames ? iframe : -1;
-    }
-    else
-    {
-        const int o = w - P.Nobs_board;
-        const int icam_i = P.obs_point[3 * o + 0], icam_e = P.obs_point[3 * o + 1], ipt = P.obs_point[3 * o + 2];
-        const bool in_state = P.opt_frames && ipt < P.Npoints_variable;
-        d.rows = 2;
-        d.j0 = P.point_j0[o];
-        d.nnz_row = (P.point_j0[o + 1] - d.j0) / 2;
-        d.m0 = P.m_point0 + 2 * o;
-        d.cbase = P.i_intr0 + icam_i * P.Nintr_state;
-        d.cam0 = (P.opt_extr && icam_e >= 0) ? P.i_extr0 + 6 * icam_e : -1;
-        d.nelim = in_state ? 3 : 0;
-        d.elim0 = in_state ? P.i_point0 + 3 * ipt : -1;
-        d.warp0 = -1;
-        d.group = in_state ? Nframe_groups + ipt : -1;
-    }
-    return d;
-}
-
-__device__ __forceinline__ int tri(int a, int b) { return a * (a + 1) / 2 + b; }   // a >= b
-
 // Pass 1, one CTA per work item: which shared columns does the item touch? Writes the item's column
 // list (reduced numbering, increasing) and marks those unknowns active.
 __global__ void __launch_bounds__(256)
@@ -366,13 +312,8 @@ constexpr int DCH = 32;                                 // rows per chunk
 constexpr int kDmmaClassT[3]     = {10, 16, 20};
 constexpr int kDmmaClassTiles[3] = {7, 17, 27};
 
-__device__ __forceinline__ void dmma884(double& c0, double& c1, double a, double b)
-{
-    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n"
-                 : "+d"(c0), "+d"(c1) : "d"(a), "d"(b));
-}
 
-template <int kDmmaMaxTiles, int TMIN, int TMAX>
+template <int kDmmaMaxTiles, int TMIN, int TMAX, bool DET>
 __global__ void __launch_bounds__(256)
 assemble_items_dmma_kernel(DevProblem P, NormalBuffers N, int ldD, const double* __restrict__ x,
                            const double* __restrict__ Jval, const int* __restrict__ Jcol)
@@ -516,6 +457,10 @@ assemble_items_dmma_kernel(DevProblem P, NormalBuffers N, int ldD, const double*
 
     // ---- write out from the accumulators. Lane holds G[8 ti + g][8 tj + 2t + {0,1}]
     double* B = N.wi_B + (size_t)w * 6 * N.cap;
+    // DET: the shared x shared block and the gradient go to this item's own block of the pool (every entry of
+    // the lower triangle exactly once, zeros included); normal_det.cu sums the blocks into S in a fixed order
+    double* Aw = DET ? N.wi_A + N.wi_Aoff[w] : nullptr;
+    const int lda = DET ? N.wi_lda[w] : 0;
 #pragma unroll
     for(int i = 0; i < kDmmaMaxTiles; i++)
     {
@@ -531,7 +476,8 @@ assemble_items_dmma_kernel(DevProblem P, NormalBuffers N, int ldD, const double*
             if(row > ntot || col > row || col >= ntot) continue;
             if(row < nsh)
             {
-                if(v != 0.) atomicAdd(&N.S[(size_t)ccol[row] * N.ldS + ccol[col]], v);        // shared x shared
+                if constexpr(DET) Aw[(size_t)row * lda + col] = v;
+                else if(v != 0.) atomicAdd(&N.S[(size_t)ccol[row] * N.ldS + ccol[col]], v);   // shared x shared
             }
             else if(row < ntot)
             {
@@ -548,7 +494,14 @@ assemble_items_dmma_kernel(DevProblem P, NormalBuffers N, int ldD, const double*
             {
                 if(col < nsh)
                 {
-                    if(v != 0.)
+                    if constexpr(DET)
+                    {
+                        // rows nsh and nsh+1 of the block: -J'x (the right-hand side rides through the factorization
+                        // as row n_c of S; row n_c+1 collects the plain gradient)
+                        Aw[(size_t)nsh * lda + col] = -v;
+                        Aw[(size_t)(nsh + 1) * lda + col] = -v;
+                    }
+                    else if(v != 0.)
                     {
                         atomicAdd(&N.gs[ccol[col]], v);
                         atomicAdd(&N.g_full[N.state_index(cols[col])], v);
@@ -569,9 +522,11 @@ assemble_items_dmma_kernel(DevProblem P, NormalBuffers N, int ldD, const double*
 // Regularization rows touch shared unknowns only: one thread per row. A row whose unknowns are
 // inactive (touched by no observation) stays out of S: inactive_step_kernel deals with it
 // (Also used for the triangulated-point rows [m_begin, m_end) = [m_tri0, m_reg0): extrinsics only.)
+// det_nc >= 0 (the atomics-free path, triangulated rows only): the gradients go to rows det_nc, det_nc+1 of S, which is
+// where that path keeps g' and the plain gradient
 __global__ void assemble_reg_kernel(DevProblem P, NormalBuffers N, const double* __restrict__ x,
                                     const double* __restrict__ Jval, const int* __restrict__ Jcol,
-                                    const int* __restrict__ rowptr, int m_begin, int m_end)
+                                    const int* __restrict__ rowptr, int m_begin, int m_end, int det_nc)
 {
     const int m = m_begin + blockIdx.x * blockDim.x + threadIdx.x;
     if(m >= m_end || !P.reg_owner) return;
@@ -580,7 +535,7 @@ __global__ void assemble_reg_kernel(DevProblem P, NormalBuffers N, const double*
     bool all_active = true;
     for(int a = j0; a < j1; a++)
     {
-        atomicAdd(&N.g_full[Jcol[a]], Jval[a] * xm);
+        if(det_nc < 0) atomicAdd(&N.g_full[Jcol[a]], Jval[a] * xm);
         if(N.cidx[N.reduced_index(Jcol[a])] < 0) all_active = false;
     }
     if(!all_active) return;
@@ -588,7 +543,12 @@ __global__ void assemble_reg_kernel(DevProblem P, NormalBuffers N, const double*
     {
         const int ca = N.cidx[N.reduced_index(Jcol[a])];
         const double va = Jval[a];
-        atomicAdd(&N.gs[ca], va * xm);
+        if(det_nc < 0) atomicAdd(&N.gs[ca], va * xm);
+        else
+        {
+            atomicAdd(&N.S[(size_t)det_nc * N.ldS + ca], -va * xm);
+            atomicAdd(&N.S[(size_t)(det_nc + 1) * N.ldS + ca], -va * xm);
+        }
         for(int b = j0; b <= a; b++)
         {
             const int cb = N.cidx[N.reduced_index(Jcol[b])];
@@ -849,19 +809,73 @@ __global__ void augment_rhs_kernel(NormalBuffers N)
     if(c < N.n_c) N.S[(size_t)N.n_c * N.ldS + c] = -N.gs[c];
 }
 
+// One-time, per-device kernel attributes
+static bool configure_kernels()
+{
+    static bool configured[kMaxDevices] = {};
+    int dev = 0;
+    MB200_CUDA_CHECK(cudaGetDevice(&dev));
+    if(dev < 0 || dev >= kMaxDevices) { set_error("device index %d out of range", dev); return false; }
+    if(configured[dev]) return true;
+    MB200_CUDA_CHECK(cudaFuncSetAttribute(assemble_items_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    MB200_CUDA_CHECK(cudaFuncSetAttribute(schur_groups_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
+#define MB200_CFG(DET)                                                                                                        \
+    MB200_CUDA_CHECK(cudaFuncSetAttribute((assemble_items_dmma_kernel<kDmmaClassTiles[0], 0, kDmmaClassT[0], DET>), cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024)); \
+    MB200_CUDA_CHECK(cudaFuncSetAttribute((assemble_items_dmma_kernel<kDmmaClassTiles[1], kDmmaClassT[0], kDmmaClassT[1], DET>), cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024)); \
+    MB200_CUDA_CHECK(cudaFuncSetAttribute((assemble_items_dmma_kernel<kDmmaClassTiles[2], kDmmaClassT[1], kDmmaClassT[2], DET>), cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
+    MB200_CFG(false)
+    MB200_CFG(true)
+#undef MB200_CFG
+    configured[dev] = true;
+    return true;
+}
+
+template <bool DET>
+static bool launch_gram_dmma(const DevProblem& dp, NormalBuffers& N, const EvalBuffers& op, int Nwi, int max_ntot,
+                             size_t lmap_bytes, size_t ccol_bytes, cudaStream_t s, int* nlaunch)
+{
+    // the tensor-pipe kernel: D chunk [32][ldD], ldD = 4 (mod 16) for conflict-free fragment loads
+    const int ncols_pad = ((max_ntot + 1 + 7) / 8) * 8;
+    const int Tmax = ncols_pad / 8;
+    auto ld_for = [](int T) { int ld = 8 * T; while(ld % 16 != 4) ld++; return ld; };
+    auto smem_for = [&](int T) { return lmap_bytes + ccol_bytes + (size_t)DCH * ld_for(T) * sizeof(double); };
+    // The size classes touch disjoint items: they run side by side on forked streams (owned by the workspace),
+    // so that the CTAs of one fill the tails of the other
+    const bool c1 = Tmax > kDmmaClassT[0], c2 = Tmax > kDmmaClassT[1];
+    if(c1 || c2)
+    {
+        MB200_CUDA_CHECK(cudaEventRecord(N.ev_fork, s));
+        if(c1) MB200_CUDA_CHECK(cudaStreamWaitEvent(N.s_side[0], N.ev_fork, 0));
+        if(c2) MB200_CUDA_CHECK(cudaStreamWaitEvent(N.s_side[1], N.ev_fork, 0));
+    }
+    {
+        const int T0 = Tmax < kDmmaClassT[0] ? Tmax : kDmmaClassT[0];
+        assemble_items_dmma_kernel<kDmmaClassTiles[0], 0, kDmmaClassT[0], DET><<<Nwi, 256, smem_for(T0), s>>>(dp, N, ld_for(T0), op.x, op.Jval, op.Jcol);
+        (*nlaunch)++;
+    }
+    if(c1)
+    {
+        const int T1 = Tmax < kDmmaClassT[1] ? Tmax : kDmmaClassT[1];
+        assemble_items_dmma_kernel<kDmmaClassTiles[1], kDmmaClassT[0], kDmmaClassT[1], DET><<<Nwi, 256, smem_for(T1), N.s_side[0]>>>(dp, N, ld_for(T1), op.x, op.Jval, op.Jcol);
+        MB200_CUDA_CHECK(cudaEventRecord(N.ev_join[0], N.s_side[0]));
+        MB200_CUDA_CHECK(cudaStreamWaitEvent(s, N.ev_join[0], 0));
+        (*nlaunch)++;
+    }
+    if(c2)
+    {
+        assemble_items_dmma_kernel<kDmmaClassTiles[2], kDmmaClassT[1], kDmmaClassT[2], DET><<<Nwi, 256, smem_for(Tmax), N.s_side[1]>>>(dp, N, ld_for(Tmax), op.x, op.Jval, op.Jcol);
+        MB200_CUDA_CHECK(cudaEventRecord(N.ev_join[1], N.s_side[1]));
+        MB200_CUDA_CHECK(cudaStreamWaitEvent(s, N.ev_join[1], 0));
+        (*nlaunch)++;
+    }
+    MB200_CUDA_CHECK(cudaGetLastError());
+    return true;
+}
+
 bool normal_assemble(const DevProblem& dp, NormalBuffers& N, const EvalBuffers& op, const int* d_rowptr,
                      double lambda, cudaStream_t s, int* nlaunch)
 {
-    static bool configured = false;
-    if(!configured)
-    {
-        MB200_CUDA_CHECK(cudaFuncSetAttribute(assemble_items_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-        MB200_CUDA_CHECK(cudaFuncSetAttribute(schur_groups_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
-        MB200_CUDA_CHECK(cudaFuncSetAttribute((assemble_items_dmma_kernel<kDmmaClassTiles[0], 0, kDmmaClassT[0]>), cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
-        MB200_CUDA_CHECK(cudaFuncSetAttribute((assemble_items_dmma_kernel<kDmmaClassTiles[1], kDmmaClassT[0], kDmmaClassT[1]>), cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
-        MB200_CUDA_CHECK(cudaFuncSetAttribute((assemble_items_dmma_kernel<kDmmaClassTiles[2], kDmmaClassT[1], kDmmaClassT[2]>), cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
-        configured = true;
-    }
+    if(!configure_kernels()) return false;
     const size_t lmap_bytes = ((size_t)dp.Nintr_state * sizeof(short) + 7) / 8 * 8;
     const size_t ccol_bytes = ((size_t)N.cap * sizeof(int) + 7) / 8 * 8;
     if(lmap_bytes + ccol_bytes + (size_t)7 * (N.cap + 6) * sizeof(double) > 200 * 1024 ||
@@ -875,6 +889,7 @@ bool normal_assemble(const DevProblem& dp, NormalBuffers& N, const EvalBuffers& 
     // ---- pass 1: who touches what; compact numbering of the coupled shared unknowns
     MB200_CUDA_CHECK(cudaMemsetAsync(N.active, 0, (size_t)(N.n_r > 0 ? N.n_r : 1) * sizeof(int), s));
     MB200_CUDA_CHECK(cudaMemsetAsync(N.stat, 0, 4 * sizeof(int), s));
+    MB200_CUDA_CHECK(cudaMemsetAsync(N.info, 0, sizeof(int), s));
     if(Nwi > 0) { item_columns_kernel<<<Nwi, 256, lmap_bytes, s>>>(dp, N, op.Jcol); (*nlaunch)++; }
     if(dp.reg_unity) { mark_reg_active_kernel<<<1, 32, 0, s>>>(dp, N); (*nlaunch)++; }
     if(dp.Ntri > 0) { mark_tri_active_kernel<<<(2 * dp.Ntri + 127) / 128, 128, 0, s>>>(dp, N); (*nlaunch)++; }
@@ -882,12 +897,38 @@ bool normal_assemble(const DevProblem& dp, NormalBuffers& N, const EvalBuffers& 
     if(comm_active() && N.n_r > 0 && !comm_allreduce_max_int(N.active, (size_t)N.n_r, s)) return false;
     compact_scan_kernel<<<1, 1024, 0, s>>>(N);
     (*nlaunch)++;
+    if(N.det_available && !normal_det_item_offsets(dp, N, s, nlaunch)) return false;
     MB200_CUDA_CHECK(cudaMemcpyAsync(N.h_stat, N.stat, 2 * sizeof(int), cudaMemcpyDeviceToHost, s));
     MB200_CUDA_CHECK(cudaStreamSynchronize(s));
     N.n_c = N.h_stat[0];
-    // one padding row is always there: it carries the right-hand side through the factorization
-    N.ldS = chol_padded(N.n_c + 1);
     const int max_ntot = N.h_stat[1];
+    const int ncols_pad = ((max_ntot + 1 + 7) / 8) * 8;
+    // The atomics-free path needs every item within the tensor-pipe Gram kernel's width and within its block of the pool
+    N.det = N.det_available && Nwi > 0 && ncols_pad <= kDmmaMaxCols && max_ntot + 2 <= N.capA;
+    // padding rows: one carries the right-hand side through the factorization; the atomics-free path keeps the plain
+    // gradient in a second one
+    N.ldS = chol_padded(N.n_c + (N.det ? 2 : 1));
+    if(N.ldS > N.ldS_max) N.ldS = N.ldS_max;
+    MB200_CUDA_CHECK(cudaMemsetAsync(N.g_full, 0, (size_t)dp.Nstate * sizeof(double), s));
+
+    if(N.det)
+    {
+        if(!normal_det_item_prepare(dp, N, s, nlaunch)) return false;
+        if(!launch_gram_dmma<true>(dp, N, op, Nwi, max_ntot, lmap_bytes, ccol_bytes, s, nlaunch)) return false;
+        if(!normal_det_finish(dp, N, op, d_rowptr, lambda, s, nlaunch)) return false;
+        if(dp.Ntri > 0)
+        {
+            assemble_reg_kernel<<<(dp.Ntri + 127) / 128, 128, 0, s>>>(dp, N, op.x, op.Jval, op.Jcol, d_rowptr, dp.m_tri0, dp.m_reg0, N.n_c);
+            (*nlaunch)++;
+        }
+        // THE collective of the algorithm: the reduced normal equations (with g' and the gradient as rows n_c, n_c+1),
+        // summed over the frame shards
+        if(comm_active() && !comm_allreduce_sum(N.S, (size_t)N.ldS * N.ldS, s)) return false;
+        if(!normal_det_rhs(N, s, nlaunch)) return false;
+        MB200_CUDA_CHECK(cudaGetLastError());
+        return true;
+    }
+
     const int ldc_schur = ((max_ntot > 0 ? max_ntot : 1) + 7) & ~7;   // widest item present (nsh + nelim >= nsh)
     const size_t smem_schur = (size_t)ldc_schur * (6 * sizeof(double) + 2 * sizeof(int));
 
@@ -899,73 +940,27 @@ bool normal_assemble(const DevProblem& dp, NormalBuffers& N, const EvalBuffers& 
 
     MB200_CUDA_CHECK(cudaMemsetAsync(N.S, 0, (size_t)N.ldS * N.ldS * sizeof(double), s));
     MB200_CUDA_CHECK(cudaMemsetAsync(N.gs, 0, (size_t)N.ldS_max * sizeof(double), s));
-    MB200_CUDA_CHECK(cudaMemsetAsync(N.g_full, 0, (size_t)dp.Nstate * sizeof(double), s));
-    MB200_CUDA_CHECK(cudaMemsetAsync(N.info, 0, sizeof(int), s));
     if(Nwi > 0)
     {
-        const int ncols_pad = ((max_ntot + 1 + 7) / 8) * 8;
         if(ncols_pad <= kDmmaMaxCols)
         {
-            // the tensor-pipe kernel: D chunk [32][ldD], ldD = 4 (mod 16) for conflict-free fragment loads
-            int ldD = ncols_pad;
-            while(ldD % 16 != 4) ldD++;
-            const int Tmax = ncols_pad / 8;
-            auto ld_for = [](int T) { int ld = 8 * T; while(ld % 16 != 4) ld++; return ld; };
-            auto smem_for = [&](int T) { return lmap_bytes + ccol_bytes + (size_t)DCH * ld_for(T) * sizeof(double); };
-            (void)ldD;
-            // The size classes touch disjoint items (and add into S with atomics): they run side by side on forked
-            // streams, so that the CTAs of one fill the tails of the other
-            static cudaStream_t s_side[2] = {nullptr, nullptr};
-            static cudaEvent_t ev_fork = nullptr, ev_join[2] = {nullptr, nullptr};
-            if(ev_fork == nullptr)
-            {
-                MB200_CUDA_CHECK(cudaEventCreateWithFlags(&ev_fork, cudaEventDisableTiming));
-                for(int k = 0; k < 2; k++)
-                {
-                    MB200_CUDA_CHECK(cudaStreamCreateWithFlags(&s_side[k], cudaStreamNonBlocking));
-                    MB200_CUDA_CHECK(cudaEventCreateWithFlags(&ev_join[k], cudaEventDisableTiming));
-                }
-            }
-            const bool c1 = Tmax > kDmmaClassT[0], c2 = Tmax > kDmmaClassT[1];
-            if(c1 || c2)
-            {
-                MB200_CUDA_CHECK(cudaEventRecord(ev_fork, s));
-                if(c1) MB200_CUDA_CHECK(cudaStreamWaitEvent(s_side[0], ev_fork, 0));
-                if(c2) MB200_CUDA_CHECK(cudaStreamWaitEvent(s_side[1], ev_fork, 0));
-            }
-            {
-                const int T0 = Tmax < kDmmaClassT[0] ? Tmax : kDmmaClassT[0];
-                assemble_items_dmma_kernel<kDmmaClassTiles[0], 0, kDmmaClassT[0]><<<Nwi, 256, smem_for(T0), s>>>(dp, N, ld_for(T0), op.x, op.Jval, op.Jcol);
-            }
-            if(c1)
-            {
-                const int T1 = Tmax < kDmmaClassT[1] ? Tmax : kDmmaClassT[1];
-                assemble_items_dmma_kernel<kDmmaClassTiles[1], kDmmaClassT[0], kDmmaClassT[1]><<<Nwi, 256, smem_for(T1), s_side[0]>>>(dp, N, ld_for(T1), op.x, op.Jval, op.Jcol);
-                MB200_CUDA_CHECK(cudaEventRecord(ev_join[0], s_side[0]));
-                MB200_CUDA_CHECK(cudaStreamWaitEvent(s, ev_join[0], 0));
-                (*nlaunch)++;
-            }
-            if(c2)
-            {
-                assemble_items_dmma_kernel<kDmmaClassTiles[2], kDmmaClassT[1], kDmmaClassT[2]><<<Nwi, 256, smem_for(Tmax), s_side[1]>>>(dp, N, ld_for(Tmax), op.x, op.Jval, op.Jcol);
-                MB200_CUDA_CHECK(cudaEventRecord(ev_join[1], s_side[1]));
-                MB200_CUDA_CHECK(cudaStreamWaitEvent(s, ev_join[1], 0));
-                (*nlaunch)++;
-            }
+            if(!launch_gram_dmma<false>(dp, N, op, Nwi, max_ntot, lmap_bytes, ccol_bytes, s, nlaunch)) return false;
         }
         else
+        {
             assemble_items_kernel<<<Nwi, 256, smem_items, s>>>(dp, N, gram_cap, op.x, op.Jval, op.Jcol);
-        (*nlaunch)++;
+            (*nlaunch)++;
+        }
     }
     const int Nreg = dp.Nmeas - dp.m_reg0;
     if(Nreg > 0)
     {
-        assemble_reg_kernel<<<(Nreg + 127) / 128, 128, 0, s>>>(dp, N, op.x, op.Jval, op.Jcol, d_rowptr, dp.m_reg0, dp.Nmeas);
+        assemble_reg_kernel<<<(Nreg + 127) / 128, 128, 0, s>>>(dp, N, op.x, op.Jval, op.Jcol, d_rowptr, dp.m_reg0, dp.Nmeas, -1);
         (*nlaunch)++;
     }
     if(dp.Ntri > 0)
     {
-        assemble_reg_kernel<<<(dp.Ntri + 127) / 128, 128, 0, s>>>(dp, N, op.x, op.Jval, op.Jcol, d_rowptr, dp.m_tri0, dp.m_reg0);
+        assemble_reg_kernel<<<(dp.Ntri + 127) / 128, 128, 0, s>>>(dp, N, op.x, op.Jval, op.Jcol, d_rowptr, dp.m_tri0, dp.m_reg0, -1);
         (*nlaunch)++;
     }
     if(N.Ngroups > 0)
@@ -1058,8 +1053,12 @@ bool normal_expand_step(const DevProblem& dp, const NormalBuffers& N, const Eval
     }
     if(N.Ngroups > 0)
     {
-        backsub_groups_kernel<<<(N.Ngroups * 32 + 255) / 256, 256, 0, s>>>(N, ds_r, step_full, N.e0);
-        (*nlaunch)++;
+        if(N.det) { if(!normal_det_backsub(N, sol, step_full, s, nlaunch)) return false; }
+        else
+        {
+            backsub_groups_kernel<<<(N.Ngroups * 32 + 255) / 256, 256, 0, s>>>(N, ds_r, step_full, N.e0);
+            (*nlaunch)++;
+        }
     }
     MB200_CUDA_CHECK(cudaGetLastError());
     return true;

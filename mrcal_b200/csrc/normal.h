@@ -41,6 +41,27 @@ struct NormalBuffers
     double* grp_Dinv;   // [Ngroups][36]
     double* grp_gf;     // [Ngroups][6]
 
+    // ---- the atomics-free assembly (normal_det.cu): every entry of S is summed by ONE thread in a fixed order
+    bool    det_available;   // the buffers below exist (MRCAL_B200_ATOMIC_ASSEMBLY=1 turns the path off)
+    bool    det;          // in use for this assembly
+    cudaStream_t s_side[2];               // forked streams of the Gram kernel's size classes (owned by the workspace)
+    cudaEvent_t  ev_fork, ev_join[2];
+    int     capA;         // most local columns (incl. the two gradient rows) an item may have in the A pool
+    double* wi_A;         // pool of per-item Gram blocks over the shared columns, [lda][lda] row-major, lower triangle
+    long long* wi_Aoff;   // [Nwi] offset of each item's block in the pool (doubles)
+    long long  A_pool;    // pool size (doubles)
+    int*    wi_lda;       // [Nwi] nsh + 2 rounded up to even; rows nsh, nsh+1: -J'x over the item's shared columns
+    unsigned short* wi_ccol;    // [Nwi][capA] compact index of each local column (increasing); then n_c, n_c+1
+    unsigned char*  wi_segoff;  // [Nwi][nblk_max+1] first local column of each 64-column block of S
+    int     nblk_max;     // ldS_max / 64
+    double* Ypan;         // [Ngroups][nblk_max][6][64] inv(L_D) B of each group, dense per 64-column block (present blocks only)
+    unsigned* grp_present;   // [nblk_max][gwords] bit g: group g has columns in this block
+    unsigned* wi_present;    // [nblk_max][wwords]
+    unsigned* grp_blkmask;   // [Ngroups][bwords] the blocks a group is present in
+    int     gwords, wwords, bwords;
+    double* grp_Linv;     // [Ngroups][36] inverse of the Cholesky factor of D (lower)
+    double* grp_h;        // [Ngroups][6]  inv(L_D) gf
+
     __host__ __device__ int reduced_index(int c) const { return c < e0 ? c : c - (e1 - e0); }
     __host__ __device__ int state_index(int r) const { return r < e0 ? r : r + (e1 - e0); }
 };
@@ -58,5 +79,13 @@ bool normal_rhs(const NormalBuffers& N, double* rhs, cudaStream_t s, int* nlaunc
 // ds_r: scratch, n_r doubles
 bool normal_expand_step(const DevProblem& dp, const NormalBuffers& N, const EvalBuffers& op, double lambda,
                         const double* sol, double* ds_r, double* step_full, cudaStream_t s, int* nlaunch);
+
+// normal_det.cu: the stages after the per-item Gram matrices, without atomics
+bool normal_det_finish(const DevProblem& dp, NormalBuffers& N, const EvalBuffers& op, const int* d_rowptr,
+                       double lambda, cudaStream_t s, int* nlaunch);
+bool normal_det_item_prepare(const DevProblem& dp, NormalBuffers& N, cudaStream_t s, int* nlaunch);   // after the compaction
+bool normal_det_item_offsets(const DevProblem& dp, NormalBuffers& N, cudaStream_t s, int* nlaunch);   // before it
+bool normal_det_rhs(const NormalBuffers& N, cudaStream_t s, int* nlaunch);   // after the cross-rank reduction of S
+bool normal_det_backsub(const NormalBuffers& N, const double* sol_compact, double* step_full, cudaStream_t s, int* nlaunch);
 
 }  // namespace mb200

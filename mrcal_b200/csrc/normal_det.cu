@@ -1,0 +1,676 @@
+// Kernel family 2b: the reduced normal equations WITHOUT atomics.
+//
+// normal.cu leaves, per work item (a board or point observation), the Gram matrix of its
+// rows over the shared unknowns it touches (wi_A), and the blocks B, D, gf that couple it
+// to its eliminated group (a frame or a point). Here
+//
+//     S = sum_items A_w  -  sum_groups Y_g' Y_g ,      Y_g = inv(L_Dg) B_g ,  D_g = L_Dg L_Dg'
+//
+// is formed by OWNER-COMPUTES: one CTA per 64x64 tile of the lower triangle of S adds up
+// everything that lands in its tile, in a fixed order, and writes the tile once. No fp64
+// atomics, so the result -- and with it the iteration count of a solve -- is the same from
+// run to run, as the reference's is.
+//
+//   item_offsets / item_prepare   where each item's block lives; compact column index of each of its
+//                                 local columns; which 64-column blocks of S it reaches
+//   groups_panels_kernel          one CTA per group: D, its Cholesky factor, Y_g written as dense
+//                                 6x64 panels per 64-column block the group reaches (zeros where it does
+//                                 not), -inv(L_D) gf as the column that forms the right-hand side
+//   schur_tiles_kernel            one CTA per tile. Phase A: the items' Gram blocks, each warp owning the
+//                                 tile rows = its number (mod 8). Phase S: the panels of the groups that
+//                                 reach both block r and block c, stacked along K, through DMMA 8x8x4;
+//                                 operands staged with cp.async, double buffered.
+//   reg_blocks_kernel             the regularization rows: one thread per knot (or per unknown), the
+//                                 single owner of the entries it adds to
+//
+// The right-hand side travels as row n_c of S (forward substitution for free, as before), the plain
+// gradient J'x of the shared unknowns as row n_c+1.
+//
+// Replaces what the reference gets from libdogleg's Jt*x and CHOLMOD's A*A' + factorization of the full
+// sparse JtJ (call site mrcal.c:6435).
+#include "normal_items.cuh"
+#include "chol.h"
+
+namespace mb200 {
+
+bool comm_active();
+
+namespace {
+
+constexpr int TB = 64;          // tile
+constexpr int TLD = 68;         // row stride of tiles and panels in shared memory (conflict-free DMMA fragment loads)
+constexpr int kChunkItems = 64; // phase A: items staged per chunk
+constexpr int kChunkGroups = 6; // phase S: groups per K chunk (36 rows); two CTAs of ~88 KB per SM
+
+__device__ __forceinline__ void cp16(void* smem, const void* gmem)
+{
+    const unsigned s = (unsigned)__cvta_generic_to_shared(smem);
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(s), "l"(gmem));
+}
+__device__ __forceinline__ void cp_commit() { asm volatile("cp.async.commit_group;\n" ::); }
+__device__ __forceinline__ void cp_wait_all() { asm volatile("cp.async.wait_group 0;\n" ::); }
+__device__ __forceinline__ void cp_wait_one() { asm volatile("cp.async.wait_group 1;\n" ::); }
+
+}  // namespace
+
+// exclusive scan of lda^2 over the items: one CTA
+__global__ void __launch_bounds__(1024)
+item_offsets_kernel(NormalBuffers N, int Nwi)
+{
+    __shared__ long long s_scan[1024];
+    const int tid = threadIdx.x;
+    const int per = (Nwi + 1023) / 1024;
+    const int lo = tid * per, hi = min(lo + per, Nwi);
+    long long cnt = 0;
+    for(int w = lo; w < hi; w++)
+    {
+        const int lda = (N.wi_nsh[w] + 2 + 1) & ~1;
+        N.wi_lda[w] = lda;
+        cnt += (long long)lda * lda;
+    }
+    s_scan[tid] = cnt;
+    __syncthreads();
+    for(int o = 1; o < 1024; o <<= 1)
+    {
+        const long long v = tid >= o ? s_scan[tid - o] : 0;
+        __syncthreads();
+        s_scan[tid] += v;
+        __syncthreads();
+    }
+    long long base = s_scan[tid] - cnt;
+    for(int w = lo; w < hi; w++)
+    {
+        N.wi_Aoff[w] = base;
+        base += (long long)N.wi_lda[w] * N.wi_lda[w];
+    }
+    if(tid == 1023 && s_scan[1023] > N.A_pool) atomicCAS(N.info, 0, 2000000000);   // pool too small: reported by the host
+}
+
+// After the compaction: compact column of each local column, the two gradient rows, the first local column of
+// every 64-column block, the block presence bits. One warp per item
+__global__ void __launch_bounds__(256)
+item_prepare_kernel(NormalBuffers N, int Nwi, int n_c, int nblk)
+{
+    const int w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    if(w >= Nwi) return;
+    const int nsh = N.wi_nsh[w];
+    const int* cols = N.wi_cols + (size_t)w * N.cap;
+    unsigned short* cc = N.wi_ccol + (size_t)w * N.capA;
+    unsigned char* seg = N.wi_segoff + (size_t)w * (N.nblk_max + 1);
+    const int n = nsh + 2;
+    for(int l = lane; l < n; l += 32)
+    {
+        const int c = l < nsh ? N.cidx[cols[l]] : n_c + (l - nsh);
+        cc[l] = (unsigned short)c;
+        const int blk = c >> 6;
+        const int prev = l == 0 ? -1 : ((l - 1 < nsh ? N.cidx[cols[l - 1]] : n_c + (l - 1 - nsh)) >> 6);
+        // blocks (prev, blk] start at local column l
+        for(int b = prev + 1; b <= blk; b++) seg[b] = (unsigned char)l;
+        if(blk != prev) atomicOr(&N.wi_present[(size_t)blk * N.wwords + (w >> 5)], 1u << (w & 31));
+        if(l == n - 1) for(int b = blk + 1; b <= nblk; b++) seg[b] = (unsigned char)n;
+    }
+}
+
+// 6x6 (or 3x3) Cholesky factor and its inverse, in registers of one thread. False if not positive definite
+__device__ bool chol6_inverse(double* Linv, const double* D, int n)
+{
+    double L[6][6] = {};
+    for(int j = 0; j < n; j++)
+    {
+        double s = D[j * 6 + j];
+        for(int k = 0; k < j; k++) s -= L[j][k] * L[j][k];
+        if(!(s > 0.)) return false;
+        L[j][j] = sqrt(s);
+        for(int i = j + 1; i < n; i++)
+        {
+            double t = D[i * 6 + j];
+            for(int k = 0; k < j; k++) t -= L[i][k] * L[j][k];
+            L[i][j] = t / L[j][j];
+        }
+    }
+    for(int i = 0; i < 36; i++) Linv[i] = 0.;
+    for(int c = 0; c < n; c++)
+    {
+        Linv[c * 6 + c] = 1. / L[c][c];
+        for(int i = c + 1; i < n; i++)
+        {
+            double t = 0.;
+            for(int k = c; k < i; k++) t += L[i][k] * Linv[k * 6 + c];
+            Linv[i * 6 + c] = -t / L[i][i];
+        }
+    }
+    return true;
+}
+
+// One CTA per elimination group
+__global__ void __launch_bounds__(256)
+groups_panels_kernel(NormalBuffers N, double lambda, int n_c, int nblk)
+{
+    __shared__ double s_D[36], s_gf[6], s_Linv[36], s_h[6];
+    __shared__ unsigned s_blk[8];   // up to 256 blocks
+    const int grp = blockIdx.x, tid = threadIdx.x;
+    const int i0 = N.grp_ptr[grp], i1 = N.grp_ptr[grp + 1];
+    const int nelim = grp < N.Nframe_groups ? 6 : 3;
+    if(tid < 36)
+    {
+        double v = 0.;
+        for(int i = i0; i < i1; i++) v += N.wi_D[(size_t)N.grp_items[i] * 36 + tid];
+        const int p = tid / 6, q = tid % 6;
+        if(p == q && p < nelim) v += lambda;
+        s_D[tid] = v;
+    }
+    if(tid >= 64 && tid < 70)
+    {
+        double v = 0.;
+        for(int i = i0; i < i1; i++) v += N.wi_gf[(size_t)N.grp_items[i] * 6 + (tid - 64)];
+        s_gf[tid - 64] = v;
+    }
+    if(tid >= 96 && tid < 104) s_blk[tid - 96] = 0u;
+    __syncthreads();
+    if(tid == 0)
+    {
+        double Linv[36];
+        // a group nobody observes (or all of whose observations are outliers) has D = 0: the reference would hand
+        // CHOLMOD a singular matrix here (mrcal.c:4826-4833); report it
+        if(!chol6_inverse(Linv, s_D, nelim))
+        {
+            atomicCAS(N.info, 0, 1000000000 + grp);
+            for(int i = 0; i < 36; i++) Linv[i] = 0.;
+        }
+        const int e0 = N.e0 + (grp < N.Nframe_groups ? 6 * grp : 6 * N.Nframe_groups + 3 * (grp - N.Nframe_groups));
+        for(int p = 0; p < 6; p++)
+        {
+            double t = 0.;
+            for(int q = 0; q <= p; q++) t += Linv[p * 6 + q] * s_gf[q];
+            s_h[p] = t;
+            N.grp_h[(size_t)grp * 6 + p] = t;
+            if(p < nelim) N.g_full[e0 + p] = s_gf[p];    // the eliminated part of the full gradient
+        }
+        for(int i = 0; i < 36; i++) { s_Linv[i] = Linv[i]; N.grp_Linv[(size_t)grp * 36 + i] = Linv[i]; }
+    }
+    // the blocks this group reaches (the block of column n_c always: the right-hand side)
+    for(int i = i0; i < i1; i++)
+    {
+        const int w = N.grp_items[i];
+        const int nsh = N.wi_nsh[w];
+        const unsigned short* cc = N.wi_ccol + (size_t)w * N.capA;
+        for(int l = tid; l < nsh; l += 256) { const int b = cc[l] >> 6; atomicOr(&s_blk[b >> 5], 1u << (b & 31)); }
+    }
+    if(tid == 0) { const int b = n_c >> 6; atomicOr(&s_blk[b >> 5], 1u << (b & 31)); }
+    __syncthreads();
+    double* Yg = N.Ypan + (size_t)grp * N.nblk_max * (6 * TB);
+    for(int b = 0; b < nblk; b++)
+    {
+        if(!((s_blk[b >> 5] >> (b & 31)) & 1u)) continue;   // uniform
+        for(int e = tid; e < 6 * TB; e += 256) Yg[(size_t)b * (6 * TB) + e] = 0.;
+        if(tid == 0) atomicOr(&N.grp_present[(size_t)b * N.gwords + (grp >> 5)], 1u << (grp & 31));
+    }
+    if(tid < N.bwords) N.grp_blkmask[(size_t)grp * N.bwords + tid] = s_blk[tid];
+    __syncthreads();
+    // Y = inv(L) B, item after item: items of one group may share columns (the board warp; the intrinsics of a
+    // camera seen twice), and the order of the additions is part of the result
+    for(int i = i0; i < i1; i++)
+    {
+        const int w = N.grp_items[i];
+        const int nsh = N.wi_nsh[w];
+        const unsigned short* cc = N.wi_ccol + (size_t)w * N.capA;
+        const double* B = N.wi_B + (size_t)w * 6 * N.cap;
+        for(int l = tid; l < nsh; l += 256)
+        {
+            const int c = cc[l];
+            double* y = Yg + (size_t)(c >> 6) * (6 * TB) + (c & 63);
+            double bq[6];
+#pragma unroll
+            for(int q = 0; q < 6; q++) bq[q] = q < nelim ? B[(size_t)q * N.cap + l] : 0.;
+#pragma unroll
+            for(int p = 0; p < 6; p++)
+            {
+                double t = 0.;
+#pragma unroll
+                for(int q = 0; q < 6; q++) if(q <= p) t += s_Linv[p * 6 + q] * bq[q];
+                if(p < nelim) y[p * TB] += t;
+            }
+        }
+        __syncthreads();
+    }
+    if(tid < 6) Yg[(size_t)(n_c >> 6) * (6 * TB) + tid * TB + (n_c & 63)] = -s_h[tid];
+}
+
+struct TileCommon
+{
+    int wl[2048];      // items (or groups) that reach both blocks of the tile
+    int scan[256];
+    int count;
+    int pad;
+};
+struct TileSmemA
+{
+    double tile[TB * TLD];
+    int    meta[kChunkItems][4];           // a0 | na<<8,  b0 | nb<<8,  lda, (unused)
+    long long base[kChunkItems];
+    unsigned char rl[kChunkItems][TB + 4]; // tile row of each local row
+    unsigned char cl[kChunkItems][TB + 4]; // tile column of each local column
+};
+struct TileSmemS
+{
+    double R[2][6 * kChunkGroups][TLD];
+    double C[2][6 * kChunkGroups][TLD];
+};
+constexpr size_t kTileSmemBody = sizeof(TileSmemA) > sizeof(TileSmemS) ? sizeof(TileSmemA) : sizeof(TileSmemS);
+constexpr size_t kTileSmem = sizeof(TileCommon) + kTileSmemBody;
+
+// worklist of the set bits of (rowA[w] & rowB[w]), w in [w0, w1), at most 64 words: ids -> sm.wl, count -> sm.count
+__device__ __forceinline__ void build_worklist(TileCommon& sm, const unsigned* rowA, const unsigned* rowB, int w0, int w1)
+{
+    const int tid = threadIdx.x;
+    unsigned m = 0;
+    if(tid < w1 - w0) m = rowA[w0 + tid] & rowB[w0 + tid];
+    const int cnt = __popc(m);
+    sm.scan[tid] = cnt;
+    __syncthreads();
+    for(int o = 1; o < 256; o <<= 1)
+    {
+        const int v = tid >= o ? sm.scan[tid - o] : 0;
+        __syncthreads();
+        sm.scan[tid] += v;
+        __syncthreads();
+    }
+    int pos = sm.scan[tid] - cnt;
+    while(m) { const int b = __ffs(m) - 1; m &= m - 1; sm.wl[pos++] = 32 * (w0 + tid) + b; }
+    if(tid == 255) sm.count = sm.scan[255];
+    __syncthreads();
+}
+
+// One CTA per 64x64 tile of the lower triangle of S
+__global__ void __launch_bounds__(256, 2)
+schur_tiles_kernel(NormalBuffers N, double lambda, int n_c, int nblk, bool add_lambda)
+{
+    extern __shared__ __align__(16) unsigned char dsm_raw[];
+    TileCommon& sc = *reinterpret_cast<TileCommon*>(dsm_raw);
+    TileSmemA& sa = *reinterpret_cast<TileSmemA*>(dsm_raw + sizeof(TileCommon));
+    TileSmemS& ss = *reinterpret_cast<TileSmemS*>(dsm_raw + sizeof(TileCommon));
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    // tile number -> (r >= c), the late rows first: they carry the most work
+    int r, c;
+    {
+        const int q = (nblk * (nblk + 1) / 2 - 1) - (int)blockIdx.x;
+        r = (int)((sqrtf(8.f * q + 1.f) - 1.f) * 0.5f);
+        while(r * (r + 1) / 2 > q) r--;
+        while((r + 1) * (r + 2) / 2 <= q) r++;
+        c = q - r * (r + 1) / 2;
+    }
+    const bool diag = r == c;
+
+    ////////////////////////////// phase A: the items' Gram blocks
+    for(int e = tid; e < TB * TLD; e += 256) sa.tile[e] = 0.;
+    __syncthreads();
+    for(int w0 = 0; w0 < N.wwords; w0 += 64)
+    {
+        build_worklist(sc, N.wi_present + (size_t)r * N.wwords, N.wi_present + (size_t)c * N.wwords, w0, min(w0 + 64, N.wwords));
+        const int nwl = sc.count;
+        for(int ch = 0; ch < nwl; ch += kChunkItems)
+        {
+            const int nch = min(kChunkItems, nwl - ch);
+            // ---- stage: where the item's rows and columns of this tile sit
+            if(tid < nch)
+            {
+                const int w = sc.wl[ch + tid];
+                const unsigned char* seg = N.wi_segoff + (size_t)w * (N.nblk_max + 1);
+                const int nsh = N.wi_nsh[w];
+                const int a0 = seg[r], a1 = seg[r + 1];
+                int b0 = seg[c], b1 = seg[c + 1];
+                if(b1 > nsh) b1 = nsh;              // the gradient rows are rows only
+                if(b0 > b1) b0 = b1;
+                sa.meta[tid][0] = a0 | ((a1 - a0) << 8);
+                sa.meta[tid][1] = b0 | ((b1 - b0) << 8);
+                sa.meta[tid][2] = N.wi_lda[w];
+                sa.base[tid] = N.wi_Aoff[w];
+            }
+            __syncthreads();
+            for(int e = tid; e < nch * 2 * TB; e += 256)
+            {
+                const int i = e / (2 * TB), k = e - i * (2 * TB);
+                const int w = sc.wl[ch + i];
+                const unsigned short* cc = N.wi_ccol + (size_t)w * N.capA;
+                if(k < TB)
+                {
+                    const int a0 = sa.meta[i][0] & 255, na = sa.meta[i][0] >> 8;
+                    if(k < na) sa.rl[i][k] = (unsigned char)(cc[a0 + k] - TB * r);
+                }
+                else
+                {
+                    const int kk = k - TB;
+                    const int b0 = sa.meta[i][1] & 255, nb = sa.meta[i][1] >> 8;
+                    if(kk < nb) sa.cl[i][kk] = (unsigned char)(cc[b0 + kk] - TB * c);
+                }
+            }
+            __syncthreads();
+            // ---- accumulate: warp `warp` owns the tile rows = warp (mod 8), so no two warps ever touch the same entry,
+            // and every entry sees its contributions in item order
+            for(int i = 0; i < nch; i++)
+            {
+                const int a0 = sa.meta[i][0] & 255, na = sa.meta[i][0] >> 8;
+                const int b0 = sa.meta[i][1] & 255, nb = sa.meta[i][1] >> 8;
+                if(na == 0 || nb == 0) continue;
+                const int lda = sa.meta[i][2];
+                const double* __restrict__ A = N.wi_A + sa.base[i];
+                const unsigned m0 = __ballot_sync(0xffffffffu, lane < na && (sa.rl[i][lane] & 7) == warp);
+                const unsigned m1 = __ballot_sync(0xffffffffu, lane + 32 < na && (sa.rl[i][lane + 32] & 7) == warp);
+                const int cb0 = lane < nb ? sa.cl[i][lane] : 0;
+                const int cb1 = lane + 32 < nb ? sa.cl[i][lane + 32] : 0;
+#pragma unroll
+                for(int half = 0; half < 2; half++)
+                {
+                    unsigned m = half ? m1 : m0;
+                    while(m)
+                    {
+                        // up to 4 rows at a time: their loads go out together
+                        int ar[4];
+                        double v0[4], v1[4];
+#pragma unroll
+                        for(int u = 0; u < 4; u++)
+                        {
+                            ar[u] = -1; v0[u] = v1[u] = 0.;
+                            if(m) { ar[u] = 32 * half + __ffs(m) - 1; m &= m - 1; }
+                        }
+#pragma unroll
+                        for(int u = 0; u < 4; u++)
+                        {
+                            if(ar[u] < 0) continue;
+                            const int a = a0 + ar[u];
+                            // lower triangle of the item's block: local column <= local row (always true off the diagonal tiles)
+                            const double* row = A + (size_t)a * lda + b0;
+                            if(lane < nb && b0 + lane <= a) v0[u] = __ldg(row + lane);
+                            if(lane + 32 < nb && b0 + lane + 32 <= a) v1[u] = __ldg(row + lane + 32);
+                        }
+#pragma unroll
+                        for(int u = 0; u < 4; u++)
+                        {
+                            if(ar[u] < 0) continue;
+                            const int a = a0 + ar[u];
+                            double* trow = sa.tile + (int)sa.rl[i][ar[u]] * TLD;
+                            if(lane < nb && b0 + lane <= a) trow[cb0] += v0[u];
+                            if(lane + 32 < nb && b0 + lane + 32 <= a) trow[cb1] += v1[u];
+                        }
+                    }
+                }
+            }
+            __syncthreads();
+        }
+    }
+
+    ////////////////////////////// phase S: minus the groups' Y'Y, through the tensor pipe
+    // accumulators start at -tile and collect +Y'Y: S = -acc. 8 warps as 4 x 2, warp tile 16 x 32
+    const int wm = warp >> 1, wn = warp & 1, g = lane >> 2, t = lane & 3;
+    double acc[2][4][2];
+#pragma unroll
+    for(int a = 0; a < 2; a++)
+#pragma unroll
+        for(int b = 0; b < 4; b++)
+        {
+            const double2 v = *reinterpret_cast<const double2*>(&sa.tile[(wm * 16 + a * 8 + g) * TLD + wn * 32 + b * 8 + 2 * t]);
+            acc[a][b][0] = -v.x;
+            acc[a][b][1] = -v.y;
+        }
+    __syncthreads();
+    for(int w0 = 0; w0 < N.gwords && N.Ngroups > 0; w0 += 64)
+    {
+        build_worklist(sc, N.grp_present + (size_t)r * N.gwords, N.grp_present + (size_t)c * N.gwords, w0, min(w0 + 64, N.gwords));
+        const int nwl = sc.count;
+        const int nchunks = (nwl + kChunkGroups - 1) / kChunkGroups;
+        // rows 6 i .. 6 i + 5 of the K panel <- group i of the chunk; 32 16-byte pieces per row. Rows up to the next
+        // multiple of 4 past the last group are zeroed
+        auto stage = [&](int chunk, int buf)
+        {
+            const int ng = min(kChunkGroups, nwl - chunk * kChunkGroups);
+            const int krows = (6 * ng + 3) & ~3;
+            const int sides = diag ? 1 : 2;
+            for(int e = tid; e < sides * krows * 32; e += 256)
+            {
+                const int side = e / (krows * 32), rem = e - side * (krows * 32);
+                const int row = rem >> 5, piece = rem & 31;
+                double* dst = side == 0 ? &ss.R[buf][row][2 * piece] : &ss.C[buf][row][2 * piece];
+                if(row < 6 * ng)
+                {
+                    const int gi = row / 6, p = row - gi * 6;
+                    const int grp = sc.wl[chunk * kChunkGroups + gi];
+                    const double* src = N.Ypan + ((size_t)grp * N.nblk_max + (side == 0 ? r : c)) * (6 * TB) + p * TB + 2 * piece;
+                    cp16(dst, src);
+                }
+                else { dst[0] = 0.; dst[1] = 0.; }
+            }
+        };
+        if(nchunks > 0) stage(0, 0);
+        cp_commit();
+        for(int ch = 0; ch < nchunks; ch++)
+        {
+            const int buf = ch & 1;
+            if(ch + 1 < nchunks) { stage(ch + 1, buf ^ 1); cp_commit(); cp_wait_one(); }
+            else cp_wait_all();
+            __syncthreads();
+            const int ng = min(kChunkGroups, nwl - ch * kChunkGroups);
+            const int ksteps = (6 * ng + 3) >> 2;
+            const double* Rb = &ss.R[buf][0][0];
+            const double* Cb = diag ? Rb : &ss.C[buf][0][0];
+            for(int ks = 0; ks < ksteps; ks++)
+            {
+                double af[2], bf[4];
+#pragma unroll
+                for(int a = 0; a < 2; a++) af[a] = Rb[(ks * 4 + t) * TLD + wm * 16 + a * 8 + g];
+#pragma unroll
+                for(int b = 0; b < 4; b++) bf[b] = Cb[(ks * 4 + t) * TLD + wn * 32 + b * 8 + g];
+#pragma unroll
+                for(int a = 0; a < 2; a++)
+#pragma unroll
+                    for(int b = 0; b < 4; b++) dmma884(acc[a][b][0], acc[a][b][1], af[a], bf[b]);
+            }
+            __syncthreads();   // this buffer is staged again two chunks from now
+        }
+    }
+
+    ////////////////////////////// write the tile. Rows >= n_c: the right-hand side (row n_c), the plain gradient (row n_c+1), padding
+#pragma unroll
+    for(int a = 0; a < 2; a++)
+#pragma unroll
+        for(int b = 0; b < 4; b++)
+        {
+            const int i = TB * r + wm * 16 + a * 8 + g;
+            const int j0 = TB * c + wn * 32 + b * 8 + 2 * t;
+            double out[2];
+#pragma unroll
+            for(int h = 0; h < 2; h++)
+            {
+                const int j = j0 + h;
+                const double v = -acc[a][b][h];
+                if(i < n_c)           out[h] = v + ((i == j && add_lambda) ? lambda : 0.);
+                else if(i <= n_c + 1) out[h] = j < n_c ? v : (i == j ? 1. : 0.);
+                else                  out[h] = i == j ? 1. : 0.;
+            }
+            double* dst = &N.S[(size_t)i * N.ldS + j0];
+            if(j0 + 1 <= i) *reinterpret_cast<double2*>(dst) = make_double2(out[0], out[1]);
+            else if(j0 <= i) dst[0] = out[0];
+        }
+}
+
+// The regularization rows (mrcal.c:5655-5955): each touches 1..3 shared unknowns, and the rows of one spline knot
+// (radial, tangential) touch the same two. One thread per knot / per unknown: the single owner of what it adds to.
+// Blocks whose unknowns no observation touches stay out of S (inactive_step_kernel solves them in closed form);
+// their gradient still goes to g_full.
+__global__ void reg_blocks_kernel(DevProblem P, NormalBuffers N, int n_c, const double* __restrict__ x,
+                                  const double* __restrict__ Jval, const int* __restrict__ Jcol)
+{
+    if(!P.reg_owner) return;
+    const int Ndist_rows   = (P.reg && P.opt_dist) ? P.Ncam_i * (P.Nintr - 4) : 0;
+    const int Ncenter_rows = (P.reg && P.opt_core) ? P.Ncam_i * 2 : 0;
+    const int Nunity_rows  = P.reg_unity ? 1 : 0;
+    const int wd = N.splined ? 2 : 1;
+    const int Ndist_blocks = N.splined ? Ndist_rows / 2 : Ndist_rows;
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if(t >= Ndist_blocks + Ncenter_rows + Nunity_rows) return;
+    int m0, nrows, j0, ncol;
+    if(t < Ndist_blocks)
+    {
+        if(N.splined) { m0 = P.m_reg0 + 2 * t; nrows = 2; j0 = P.reg_j0 + 4 * t; ncol = 2; }
+        else          { m0 = P.m_reg0 + t;     nrows = 1; j0 = P.reg_j0 + t;     ncol = 1; }
+    }
+    else if(t < Ndist_blocks + Ncenter_rows)
+    {
+        const int rr = t - Ndist_blocks;
+        m0 = P.m_reg0 + Ndist_rows + rr; nrows = 1; j0 = P.reg_j0 + wd * Ndist_rows + rr; ncol = 1;
+    }
+    else { m0 = P.m_reg0 + Ndist_rows + Ncenter_rows; nrows = 1; j0 = P.reg_j0 + wd * Ndist_rows + Ncenter_rows; ncol = 3; }
+
+    int col[3], ci[3];
+    double gk[3] = {0., 0., 0.}, H[3][3] = {};
+    bool all_active = true;
+    for(int k = 0; k < ncol; k++)
+    {
+        col[k] = Jcol[j0 + k];
+        ci[k] = N.cidx[N.reduced_index(col[k])];
+        if(ci[k] < 0) all_active = false;
+    }
+    for(int rr = 0; rr < nrows; rr++)
+    {
+        const double xm = x[m0 + rr];
+        double v[3];
+        for(int k = 0; k < ncol; k++) { v[k] = Jval[j0 + rr * ncol + k]; gk[k] += v[k] * xm; }
+        for(int k = 0; k < ncol; k++)
+            for(int l = 0; l <= k; l++) H[k][l] += v[k] * v[l];
+    }
+    if(!all_active)
+    {
+        for(int k = 0; k < ncol; k++) N.g_full[col[k]] = gk[k];
+        return;
+    }
+    for(int k = 0; k < ncol; k++)
+    {
+        N.S[(size_t)n_c * N.ldS + ci[k]] -= gk[k];
+        N.S[(size_t)(n_c + 1) * N.ldS + ci[k]] -= gk[k];
+        for(int l = 0; l <= k; l++)
+        {
+            const int hi = ci[k] > ci[l] ? ci[k] : ci[l], lo = ci[k] > ci[l] ? ci[l] : ci[k];
+            N.S[(size_t)hi * N.ldS + lo] += H[k][l];
+        }
+    }
+}
+
+// gs = g' and the shared part of J'x out of rows n_c, n_c+1 of S; row n_c+1 becomes plain padding
+__global__ void finish_rhs_kernel(NormalBuffers N, int n_c)
+{
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if(c >= n_c) return;
+    N.gs[c] = -N.S[(size_t)n_c * N.ldS + c];
+    N.g_full[N.state_index(N.cinv[c])] = -N.S[(size_t)(n_c + 1) * N.ldS + c];
+    N.S[(size_t)(n_c + 1) * N.ldS + c] = 0.;
+}
+
+// df_g = -inv(L_D)' (h + Y ds): one warp per group, over the blocks the group reaches. sol: the compact solution
+__global__ void __launch_bounds__(256)
+backsub_panels_kernel(NormalBuffers N, const double* __restrict__ sol, double* __restrict__ step_full, int nblk)
+{
+    const int grp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    if(grp >= N.Ngroups) return;
+    const int nelim = grp < N.Nframe_groups ? 6 : 3;
+    const double* Yg = N.Ypan + (size_t)grp * N.nblk_max * (6 * TB);
+    double tsum[6] = {0., 0., 0., 0., 0., 0.};
+    for(int b = 0; b < nblk; b++)
+    {
+        if(!((N.grp_blkmask[(size_t)grp * N.bwords + (b >> 5)] >> (b & 31)) & 1u)) continue;
+        const double d0 = sol[TB * b + lane], d1 = sol[TB * b + 32 + lane];
+#pragma unroll
+        for(int p = 0; p < 6; p++)
+            tsum[p] += Yg[(size_t)b * (6 * TB) + p * TB + lane] * d0 + Yg[(size_t)b * (6 * TB) + p * TB + 32 + lane] * d1;
+    }
+#pragma unroll
+    for(int p = 0; p < 6; p++)
+#pragma unroll
+        for(int o = 16; o > 0; o >>= 1) tsum[p] += __shfl_xor_sync(0xffffffffu, tsum[p], o);
+    if(lane < nelim)
+    {
+        double v = 0.;
+        for(int p = lane; p < 6; p++) v += N.grp_Linv[(size_t)grp * 36 + p * 6 + lane] * (N.grp_h[(size_t)grp * 6 + p] + tsum[p]);
+        const int col = grp < N.Nframe_groups ? N.e0 + 6 * grp : N.e0 + 6 * N.Nframe_groups + 3 * (grp - N.Nframe_groups);
+        step_full[col + lane] = -v;
+    }
+}
+
+bool normal_det_item_offsets(const DevProblem& dp, NormalBuffers& N, cudaStream_t s, int* nlaunch)
+{
+    const int Nwi = dp.Nobs_board + dp.Nobs_point;
+    if(Nwi == 0) return true;
+    item_offsets_kernel<<<1, 1024, 0, s>>>(N, Nwi);
+    (*nlaunch)++;
+    MB200_CUDA_CHECK(cudaGetLastError());
+    return true;
+}
+
+bool normal_det_item_prepare(const DevProblem& dp, NormalBuffers& N, cudaStream_t s, int* nlaunch)
+{
+    const int Nwi = dp.Nobs_board + dp.Nobs_point;
+    const int nblk = N.ldS / TB;
+    MB200_CUDA_CHECK(cudaMemsetAsync(N.wi_present, 0, (size_t)nblk * N.wwords * sizeof(unsigned), s));
+    if(N.Ngroups > 0) MB200_CUDA_CHECK(cudaMemsetAsync(N.grp_present, 0, (size_t)nblk * N.gwords * sizeof(unsigned), s));
+    if(Nwi > 0)
+    {
+        item_prepare_kernel<<<(Nwi * 32 + 255) / 256, 256, 0, s>>>(N, Nwi, N.n_c, nblk);
+        (*nlaunch)++;
+    }
+    MB200_CUDA_CHECK(cudaGetLastError());
+    return true;
+}
+
+// groups -> tiles -> regularization -> (all-reduce by the caller) ; finish_rhs afterwards
+bool normal_det_finish(const DevProblem& dp, NormalBuffers& N, const EvalBuffers& op, const int* d_rowptr,
+                       double lambda, cudaStream_t s, int* nlaunch)
+{
+    static bool configured[kMaxDevices] = {};
+    int dev = 0;
+    MB200_CUDA_CHECK(cudaGetDevice(&dev));
+    if(dev < 0 || dev >= kMaxDevices) { set_error("device index %d out of range", dev); return false; }
+    if(!configured[dev])
+    {
+        MB200_CUDA_CHECK(cudaFuncSetAttribute(schur_tiles_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTileSmem));
+        configured[dev] = true;
+    }
+    const int nblk = N.ldS / TB;
+    if(N.Ngroups > 0)
+    {
+        groups_panels_kernel<<<N.Ngroups, 256, 0, s>>>(N, lambda, N.n_c, nblk);
+        (*nlaunch)++;
+    }
+    schur_tiles_kernel<<<nblk * (nblk + 1) / 2, 256, kTileSmem, s>>>(N, lambda, N.n_c, nblk, dp.reg_owner);
+    (*nlaunch)++;
+    const int Ndist_rows   = (dp.reg && dp.opt_dist) ? dp.Ncam_i * (dp.Nintr - 4) : 0;
+    const int Ncenter_rows = (dp.reg && dp.opt_core) ? dp.Ncam_i * 2 : 0;
+    const int Nreg_blocks = (N.splined ? Ndist_rows / 2 : Ndist_rows) + Ncenter_rows + (dp.reg_unity ? 1 : 0);
+    if(Nreg_blocks > 0)
+    {
+        reg_blocks_kernel<<<(Nreg_blocks + 127) / 128, 128, 0, s>>>(dp, N, N.n_c, op.x, op.Jval, op.Jcol);
+        (*nlaunch)++;
+    }
+    (void)d_rowptr;
+    MB200_CUDA_CHECK(cudaGetLastError());
+    return true;
+}
+
+bool normal_det_rhs(const NormalBuffers& N, cudaStream_t s, int* nlaunch)
+{
+    if(N.n_c > 0)
+    {
+        finish_rhs_kernel<<<(N.n_c + 255) / 256, 256, 0, s>>>(N, N.n_c);
+        (*nlaunch)++;
+    }
+    MB200_CUDA_CHECK(cudaGetLastError());
+    return true;
+}
+
+bool normal_det_backsub(const NormalBuffers& N, const double* sol_compact, double* step_full, cudaStream_t s, int* nlaunch)
+{
+    if(N.Ngroups == 0) return true;
+    backsub_panels_kernel<<<(N.Ngroups * 32 + 255) / 256, 256, 0, s>>>(N, sol_compact, step_full, N.ldS / TB);
+    (*nlaunch)++;
+    MB200_CUDA_CHECK(cudaGetLastError());
+    return true;
+}
+
+}  // namespace mb200

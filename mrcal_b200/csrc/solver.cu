@@ -38,6 +38,12 @@ struct SolverWorkspace
     ~SolverWorkspace()
     {
         chol_forget_graphs(N.S);
+        for(int k = 0; k < 2; k++)
+        {
+            if(N.s_side[k]) cudaStreamDestroy(N.s_side[k]);
+            if(N.ev_join[k]) cudaEventDestroy(N.ev_join[k]);
+        }
+        if(N.ev_fork) cudaEventDestroy(N.ev_fork);
         if(h_scal) cudaFreeHost(h_scal);
         if(h_info) cudaFreeHost(h_info);
         for(auto e : ev) cudaEventDestroy(e);
@@ -169,7 +175,7 @@ static bool build_workspace(mrcal_b200_problem* P)
     N.e0 = elim ? (L.i_frame0 >= 0 ? L.i_frame0 : L.i_point0) : L.Nstate;
     N.e1 = elim ? N.e0 + (L.i_frame0 >= 0 ? 6 * L.d.Nframes : 0) + (L.i_point0 >= 0 ? 3 * L.Npoints_variable : 0) : L.Nstate;
     N.n_r = L.Nstate - (N.e1 - N.e0);
-    N.ldS_max = chol_padded(N.n_r + 1);
+    N.ldS_max = chol_padded(N.n_r + 2);
     N.ldS = N.ldS_max;
     N.n_c = N.n_r;
     N.splined = L.splined;
@@ -213,6 +219,33 @@ static bool build_workspace(mrcal_b200_problem* P)
               A.alloc(&ws->invL, (size_t)N.ldS_max * kCholBlock) && A.alloc(&ws->rhs, N.ldS_max, true) &&
               A.alloc(&ws->step_gn, L.Nstate, true) && A.alloc(&ws->step, L.Nstate, true) && A.alloc(&ws->scal, 32, true);
     if(!ok) return false;
+    // the atomics-free assembly (normal_det.cu)
+    N.nblk_max = N.ldS_max / kCholBlock;
+    N.det_available = getenv("MRCAL_B200_ATOMIC_ASSEMBLY") == nullptr && Nwi > 0 && N.nblk_max <= 256;
+    if(N.det_available)
+    {
+        N.capA = N.cap + 2 < 162 ? N.cap + 2 : 162;
+        auto even = [](int v) { return (v + 1) & ~1; };
+        const int lda_board = even(std::min(N.capA, (L.splined ? 160 : L.Nintr_state + 8) + 2));
+        const int lda_point = even(std::min(N.capA, (L.splined ? 2 * 16 + 4 + 6 : L.Nintr_state + 6) + 2));
+        N.A_pool = (long long)L.d.Nobs_board * lda_board * lda_board + (long long)L.d.Nobs_point * lda_point * lda_point;
+        N.gwords = (N.Ngroups + 31) / 32; if(N.gwords < 1) N.gwords = 1;
+        N.wwords = (Nwi + 31) / 32;
+        N.bwords = (N.nblk_max + 31) / 32;
+        ok = A.alloc(&N.wi_A, (size_t)N.A_pool) && A.alloc(&N.wi_Aoff, Nwi, true) && A.alloc(&N.wi_lda, Nwi, true) &&
+             A.alloc(&N.wi_ccol, (size_t)Nwi * N.capA, true) && A.alloc(&N.wi_segoff, (size_t)Nwi * (N.nblk_max + 1), true) &&
+             A.alloc(&N.Ypan, (size_t)(N.Ngroups > 0 ? N.Ngroups : 1) * N.nblk_max * 6 * kCholBlock) &&
+             A.alloc(&N.grp_present, (size_t)N.nblk_max * N.gwords, true) && A.alloc(&N.wi_present, (size_t)N.nblk_max * N.wwords, true) &&
+             A.alloc(&N.grp_blkmask, (size_t)(N.Ngroups > 0 ? N.Ngroups : 1) * N.bwords, true) &&
+             A.alloc(&N.grp_Linv, (size_t)(N.Ngroups > 0 ? N.Ngroups : 1) * 36, true) && A.alloc(&N.grp_h, (size_t)(N.Ngroups > 0 ? N.Ngroups : 1) * 6, true);
+        if(!ok) return false;
+    }
+    MB200_CUDA_CHECK(cudaEventCreateWithFlags(&N.ev_fork, cudaEventDisableTiming));
+    for(int k = 0; k < 2; k++)
+    {
+        MB200_CUDA_CHECK(cudaStreamCreateWithFlags(&N.s_side[k], cudaStreamNonBlocking));
+        MB200_CUDA_CHECK(cudaEventCreateWithFlags(&N.ev_join[k], cudaEventDisableTiming));
+    }
     N.gsh = N.gs + N.ldS_max;
     MB200_CUDA_CHECK(cudaMallocHost(&ws->h_scal, 32 * sizeof(double)));
     MB200_CUDA_CHECK(cudaMallocHost(&ws->h_info, 8 * sizeof(int)));
