@@ -561,6 +561,19 @@ bool mrcal_b200_factorization_solve_sys(mrcal_b200_factorization_t* factorizatio
 // cholmod_rcond() defines it (mrcal-pywrap.c:580-593)
 double mrcal_b200_factorization_rcond(mrcal_b200_factorization_t* factorization);
 
+// A sparse Jacobian held on the GPU, for the consumers downstream of the solve (the reference's
+// projection-uncertainty code, mrcal/model_analysis.py:716-870). J is CSR, shape (Nrows, Ncols), given as the
+// reference gives it: p/i/x = indptr/indices/data of a scipy.sparse.csr_matrix = the arrays of the cholmod_sparse Jt.
+typedef struct mrcal_b200_csr mrcal_b200_csr_t;
+mrcal_b200_csr_t* mrcal_b200_csr_create(const int32_t* Jrowptr, const int32_t* Jcolidx, const double* Jval, int Nrows, int Ncols);
+void mrcal_b200_csr_destroy(mrcal_b200_csr_t* J);
+// out[Ncols] = Jt xt.  replaces _Jt_x, mrcal-genpywrap.py:640-731. Every output sums its column in row order, like
+// the reference's loop: the result is bit-identical to the reference's
+bool mrcal_b200_csr_Jt_x(mrcal_b200_csr_t* J, double* out, const double* xt);
+// out[Nx][Nx] = A Jt J At over the Nleading_rows_J leading rows of J; A is (Nx, Ncols) row-major.
+// replaces _A_Jt_J_At and _A_Jt_J_At__2, mrcal-genpywrap.py:477-638
+bool mrcal_b200_csr_A_Jt_J_At(mrcal_b200_csr_t* J, double* out, const double* A, int Nx, int Nleading_rows_J);
+
 #ifdef __cplusplus
 }
 #endif

@@ -14,6 +14,10 @@ from .api import (  # noqa: F401
     num_measurements, num_measurements_boards, num_measurements_points,
     num_measurements_points_triangulated, num_measurements_regularization,
     corresponding_icam_extrinsics, pack_state, unpack_state, project, unproject,
+    _Jt_x, _A_Jt_J_At, _A_Jt_J_At__2,
+)
+from .seeding import (  # noqa: F401
+    seed_stereographic, estimate_monocular_calobject_poses_Rt_tocam, estimate_joint_frame_poses,
 )
 from .cameramodel import cameramodel, CameramodelParseException  # noqa: F401
 from ._capi import lib as _lib

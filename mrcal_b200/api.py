@@ -565,6 +565,85 @@ class CHOLMOD_factorization:
 
 
 ####################################################################################################
+# consumers of the sparse Jacobian (the reference's _mrcal_npsp._Jt_x / _A_Jt_J_At, mrcal-genpywrap.py:477-731)
+####################################################################################################
+class _DeviceCSR:
+    """A CSR matrix uploaded once; the last one is kept, keyed by the identity of the arrays, because the
+    uncertainty code calls these functions over and over with the same J (mrcal/model_analysis.py:716-870)."""
+    _last = None
+
+    def __init__(self, Jp, Ji, Jx, Ncols):
+        self.key = (Jp.ctypes.data, Ji.ctypes.data, Jx.ctypes.data, Jp.size, Ji.size, Ncols)
+        self.Nrows, self.Ncols = Jp.size - 1, Ncols
+        h = lib.mrcal_b200_csr_create(_ptr(Jp) or Jp.ctypes.data_as(C.c_void_p), _ptr(Ji), _ptr(Jx), self.Nrows, Ncols)
+        if not h:
+            raise RuntimeError(_capi.last_error())
+        self._h = C.c_void_p(h)
+
+    def __del__(self):
+        if getattr(self, "_h", None):
+            lib.mrcal_b200_csr_destroy(self._h)
+            self._h = None
+
+    @classmethod
+    def get(cls, Jp, Ji, Jx, Ncols):
+        _require_gpu()
+        Jp = np.ascontiguousarray(Jp, np.int32)
+        Ji = np.ascontiguousarray(Ji, np.int32)
+        Jx = np.ascontiguousarray(Jx, np.float64)
+        key = (Jp.ctypes.data, Ji.ctypes.data, Jx.ctypes.data, Jp.size, Ji.size, Ncols)
+        if cls._last is None or cls._last.key != key:
+            cls._last = cls(Jp, Ji, Jx, Ncols)
+            cls._last._keep = (Jp, Ji, Jx)   # the key is only meaningful while the arrays live
+        return cls._last
+
+
+def _Jt_x(Jp, Ji, Jx, xt, out=None):
+    """Jt*xt for a sparse J given as the indptr/indices/data of a scipy.sparse.csr_matrix; `out` (shape (Nstate,))
+    must be given, as in the reference (mrcal-genpywrap.py:640-731: its length is the number of columns of J)."""
+    if out is None:
+        raise RuntimeError("_Jt_x(): the output array must be passed in: there is no other way to know the number of columns of J")
+    xt = np.ascontiguousarray(xt, np.float64)
+    if xt.ndim != 1 or xt.shape[0] != np.asarray(Jp).size - 1:
+        raise RuntimeError("len(xt) must match the number of rows in J")
+    if out.dtype != np.float64 or not out.flags.c_contiguous or out.ndim != 1:
+        raise RuntimeError("out must be a contiguous 1-dimensional float64 array")
+    J = _DeviceCSR.get(Jp, Ji, Jx, out.shape[0])
+    if not lib.mrcal_b200_csr_Jt_x(J._h, _ptr(out), _ptr(xt)):
+        raise RuntimeError(_capi.last_error())
+    return out
+
+
+def _A_Jt_J_At(A, Jp, Ji, Jx, Nleading_rows_J=-1, out=None):
+    """matmult(A,Jt,J,At) over the Nleading_rows_J leading rows of a sparse J (mrcal-genpywrap.py:477-567).
+    A: (...,Nx,Nstate), broadcast over the leading dimensions; returns (...,Nx,Nx)."""
+    if Nleading_rows_J is None or Nleading_rows_J <= 0:
+        raise RuntimeError("Nleading_rows_J must be passed, and must be > 0")
+    A = np.asarray(A, np.float64)
+    if A.ndim < 2:
+        raise RuntimeError("A must have shape (...,Nx,Nstate)")
+    Nx, Nstate = A.shape[-2:]
+    J = _DeviceCSR.get(Jp, Ji, Jx, Nstate)
+    flat = np.ascontiguousarray(A.reshape(-1, Nx, Nstate))
+    res = np.zeros((flat.shape[0], Nx, Nx))
+    for k in range(flat.shape[0]):
+        if not lib.mrcal_b200_csr_A_Jt_J_At(J._h, _ptr(res[k]), _ptr(flat[k]), Nx, int(Nleading_rows_J)):
+            raise RuntimeError(_capi.last_error())
+    res = res.reshape(A.shape[:-2] + (Nx, Nx))
+    if out is not None:
+        out[...] = res
+        return out
+    return res
+
+
+def _A_Jt_J_At__2(A, Jp, Ji, Jx, Nleading_rows_J=-1, out=None):
+    """_A_Jt_J_At() for A.shape = (...,2,Nstate) (mrcal-genpywrap.py:569-638)."""
+    if np.asarray(A).shape[-2] != 2:
+        raise RuntimeError("_A_Jt_J_At__2(): A must have shape (...,2,Nstate)")
+    return _A_Jt_J_At(A, Jp, Ji, Jx, Nleading_rows_J, out)
+
+
+####################################################################################################
 # lens models
 ####################################################################################################
 def lensmodel_num_params(lensmodel):
