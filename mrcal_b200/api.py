@@ -359,8 +359,12 @@ def optimizer_callback(no_jacobian=False, no_factorization=False, **kwargs):
         if not no_factorization:
             try:
                 factorization = CHOLMOD_factorization(J)
-            except RuntimeError:
-                factorization = None   # not an error: mrcal-pywrap.c:1981-1988
+            except RuntimeError as e:
+                # "JtJ is not positive definite" is not an error here: mrcal-pywrap.c:1981-1988 returns None.
+                # Anything else (out of memory, a CUDA failure) is one
+                if "not positive definite" not in str(e):
+                    raise
+                factorization = None
     return b, x, J, factorization
 
 

@@ -236,7 +236,12 @@ static const size_t kPotrfSmem = sizeof(PotrfSmem);
 
 static bool configure_kernels()
 {
-    static bool configured = false;
+    // cudaFuncSetAttribute is per device
+    static bool configured_dev[kMaxDevices] = {};
+    int dev = 0;
+    MB200_CUDA_CHECK(cudaGetDevice(&dev));
+    if(dev < 0 || dev >= kMaxDevices) { set_error("device index %d out of range", dev); return false; }
+    bool& configured = configured_dev[dev];
     if(configured) return true;
     MB200_CUDA_CHECK(cudaFuncSetAttribute(syrk_dmma_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSyrkSmem));
     MB200_CUDA_CHECK(cudaFuncSetAttribute(syrk_dmma_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSyrkSmem));
@@ -322,10 +327,12 @@ void chol_forget_graphs(const void* A)
         else i++;
 }
 
-bool chol_factor(double* A, int npad, int nreal, double* invL, int* d_info, cudaStream_t s, int* nlaunch)
+bool chol_factor(double* A, int npad, int nreal, double* invL, int* d_info, cudaStream_t s, int* nlaunch,
+                 CholScratch* scratch, const int* d_run_if)
 {
     if(!configure_kernels()) return false;
-    if(chol_dataflow_usable(npad)) return chol_factor_dataflow(A, npad, nreal, invL, d_info, s, nlaunch);
+    if(chol_dataflow_usable(npad)) return chol_factor_dataflow(A, npad, nreal, invL, d_info, s, nlaunch, scratch, d_run_if);
+    // (the multi-kernel fallback always runs: a factorization nobody asked for costs time, not correctness)
     return run_graphed(GraphKey{A, d_info, npad, nreal, 0}, s, nlaunch,
                        [&](int* n) { return chol_factor_enqueue(A, npad, nreal, invL, d_info, s, n); });
 }
@@ -340,9 +347,10 @@ bool chol_solve(const double* L, int npad, const double* invL, double* B, int ld
 static bool chol_solve_bwd_enqueue(const double* L, int npad, const double* invL, double* B, int ldb, cudaStream_t s, int* nlaunch);
 
 // L' z = y only (the forward half came out of the factorization itself: see normal_assemble's augmented row)
-bool chol_solve_backward(const double* L, int npad, const double* invL, double* B, int ldb, int* d_info, cudaStream_t s, int* nlaunch)
+bool chol_solve_backward(const double* L, int npad, const double* invL, double* B, int ldb, int* d_info, cudaStream_t s, int* nlaunch,
+                         CholScratch* scratch, const int* d_run_if)
 {
-    if(chol_dataflow_usable(npad)) return chol_solve_backward_dataflow(L, npad, invL, B, d_info, s, nlaunch);
+    if(chol_dataflow_usable(npad)) return chol_solve_backward_dataflow(L, npad, invL, B, d_info, s, nlaunch, scratch, d_run_if);
     return run_graphed(GraphKey{L, B, npad, ldb, 2}, s, nlaunch,
                        [&](int* n) { return chol_solve_bwd_enqueue(L, npad, invL, B, ldb, s, n); });
 }

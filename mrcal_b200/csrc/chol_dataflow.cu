@@ -182,8 +182,10 @@ __device__ __forceinline__ int tile_flag(int i, int j, int nb) { return j * nb -
 //   tiles (i,j), i >= j+2.
 __global__ void __launch_bounds__(256, 1)
 chol_dataflow_kernel(double* __restrict__ A, int ld, int nb, int nreal, double* __restrict__ invL, int* __restrict__ info,
-                     int* __restrict__ flags, int* __restrict__ abort_flag)
+                     int* __restrict__ flags, int* __restrict__ abort_flag, const int* __restrict__ run_if)
 {
+    // the trust-region loop decides on the device whether this operating point needs a Gauss-Newton step at all
+    if(run_if != nullptr && *run_if == 0) return;
     extern __shared__ __align__(16) unsigned char dsm_raw[];
     DfSmem& sm = *reinterpret_cast<DfSmem*>(dsm_raw);
     const int tid = threadIdx.x;
@@ -279,8 +281,10 @@ chol_dataflow_kernel(double* __restrict__ A, int ld, int nb, int nreal, double* 
 // the wait.
 __global__ void __launch_bounds__(256, 1)
 chol_backward_dataflow_kernel(const double* __restrict__ L, int ld, int nb, const double* __restrict__ invL,
-                              double* __restrict__ B, double* __restrict__ xbuf, int* __restrict__ abort_flag, int* __restrict__ info)
+                              double* __restrict__ B, double* __restrict__ xbuf, int* __restrict__ abort_flag, int* __restrict__ info,
+                              const int* __restrict__ run_if)
 {
+    if(run_if != nullptr && *run_if == 0) return;
     __shared__ double xs[T];
     __shared__ double red[4][T];
     __shared__ double tv[T];
@@ -341,66 +345,106 @@ chol_backward_dataflow_kernel(const double* __restrict__ L, int ld, int nb, cons
     }
 }
 
-int* g_flags = nullptr;       // [kMaxTiles] tile flags, then [1] abort
-double* g_xbuf = nullptr;     // [kMaxBlocks * 64]
-int g_num_sms = 0;
-bool g_configured = false, g_unavailable = false;
 constexpr int kMaxBlocks = 128;
 constexpr int kMaxTiles = kMaxBlocks * (kMaxBlocks + 1) / 2;
 
-bool configure()
+// per device: kernel attributes, SM count
+struct DeviceCfg { bool configured = false, unavailable = false; int num_sms = 0; };
+DeviceCfg g_cfg[kMaxDevices];
+// scratch of callers that bring none (the timing aids): one per device
+CholScratch g_default_scratch[kMaxDevices];
+
+DeviceCfg* configure()
 {
-    if(g_configured) return true;
-    if(g_unavailable) return false;
-    int dev = 0, coop = 0;
-    if(cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, dev) != cudaSuccess || !coop ||
-       cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess ||
-       cudaFuncSetAttribute(chol_dataflow_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(DfSmem)) != cudaSuccess ||
-       cudaMalloc(&g_flags, (kMaxTiles + 1) * sizeof(int)) != cudaSuccess || cudaMalloc(&g_xbuf, (size_t)kMaxBlocks * T * sizeof(double)) != cudaSuccess)
+    int dev = 0;
+    if(cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= kMaxDevices) { cudaGetLastError(); return nullptr; }
+    DeviceCfg& c = g_cfg[dev];
+    if(c.configured) return &c;
+    if(c.unavailable) return nullptr;
+    int coop = 0;
+    if(cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, dev) != cudaSuccess || !coop ||
+       cudaDeviceGetAttribute(&c.num_sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess ||
+       cudaFuncSetAttribute(chol_dataflow_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(DfSmem)) != cudaSuccess)
     {
         cudaGetLastError();
-        g_unavailable = true;
-        return false;
+        c.unavailable = true;
+        return nullptr;
     }
-    g_configured = true;
-    return true;
+    c.configured = true;
+    return &c;
+}
+
+CholScratch* scratch_or_default(CholScratch* sc)
+{
+    if(sc != nullptr && sc->flags != nullptr) return sc;
+    int dev = 0;
+    if(cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= kMaxDevices) return nullptr;
+    CholScratch& d = g_default_scratch[dev];
+    if(d.flags == nullptr && !chol_scratch_create(&d)) return nullptr;
+    return &d;
 }
 
 }  // namespace
 
+bool chol_scratch_create(CholScratch* sc)
+{
+    sc->flags = nullptr; sc->xbuf = nullptr;
+    if(cudaMalloc(&sc->flags, (kMaxTiles + 1) * sizeof(int)) != cudaSuccess ||
+       cudaMalloc(&sc->xbuf, (size_t)kMaxBlocks * T * sizeof(double)) != cudaSuccess)
+    {
+        set_error("cudaMalloc of the factorization scratch failed: %s", cudaGetErrorString(cudaGetLastError()));
+        chol_scratch_destroy(sc);
+        return false;
+    }
+    return true;
+}
+void chol_scratch_destroy(CholScratch* sc)
+{
+    if(sc->flags) cudaFree(sc->flags);
+    if(sc->xbuf) cudaFree(sc->xbuf);
+    sc->flags = nullptr; sc->xbuf = nullptr;
+}
+
 bool chol_dataflow_usable(int npad)
 {
     static const bool disabled = getenv("MRCAL_B200_CHOL_CLASSIC") != nullptr;
-    return !disabled && npad / T <= kMaxBlocks && configure();
+    return !disabled && npad / T <= kMaxBlocks && configure() != nullptr;
 }
 
-bool chol_factor_dataflow(double* A, int npad, int nreal, double* invL, int* d_info, cudaStream_t s, int* nlaunch)
+bool chol_factor_dataflow(double* A, int npad, int nreal, double* invL, int* d_info, cudaStream_t s, int* nlaunch,
+                          CholScratch* scratch, const int* d_run_if)
 {
-    if(!configure()) { set_error("the persistent Cholesky kernel is not available on this device"); return false; }
+    DeviceCfg* cfg = configure();
+    CholScratch* sc = scratch_or_default(scratch);
+    if(!cfg || !sc) { set_error("the persistent Cholesky kernel is not available on this device"); return false; }
     int nb = npad / T;
     const int ntiles = 1 + (nb - 1) * nb / 2;   // tasks: see the kernel
     MB200_CUDA_CHECK(cudaMemsetAsync(d_info, 0, sizeof(int), s));
-    MB200_CUDA_CHECK(cudaMemsetAsync(g_flags, 0, (kMaxTiles + 1) * sizeof(int), s));
+    MB200_CUDA_CHECK(cudaMemsetAsync(sc->flags, 0, (size_t)(nb * (nb + 1) / 2) * sizeof(int), s));   // one flag per tile of the lower triangle
+    MB200_CUDA_CHECK(cudaMemsetAsync(sc->flags + kMaxTiles, 0, sizeof(int), s));
     int ld = npad;
-    int* flags = g_flags;
-    int* abort_flag = g_flags + kMaxTiles;
-    void* args[] = {&A, &ld, &nb, &nreal, &invL, &d_info, &flags, &abort_flag};
-    const int grid = ntiles < g_num_sms ? ntiles : g_num_sms;
+    int* flags = sc->flags;
+    int* abort_flag = sc->flags + kMaxTiles;
+    void* args[] = {&A, &ld, &nb, &nreal, &invL, &d_info, &flags, &abort_flag, &d_run_if};
+    const int grid = ntiles < cfg->num_sms ? ntiles : cfg->num_sms;
     MB200_CUDA_CHECK(cudaLaunchCooperativeKernel((const void*)chol_dataflow_kernel, dim3(grid), dim3(256), args, sizeof(DfSmem), s));
     if(nlaunch) (*nlaunch)++;
     return true;
 }
 
-bool chol_solve_backward_dataflow(const double* L, int npad, const double* invL, double* B, int* d_info, cudaStream_t s, int* nlaunch)
+bool chol_solve_backward_dataflow(const double* L, int npad, const double* invL, double* B, int* d_info, cudaStream_t s, int* nlaunch,
+                                  CholScratch* scratch, const int* d_run_if)
 {
-    if(!configure()) { set_error("the persistent Cholesky kernel is not available on this device"); return false; }
+    DeviceCfg* cfg = configure();
+    CholScratch* sc = scratch_or_default(scratch);
+    if(!cfg || !sc) { set_error("the persistent Cholesky kernel is not available on this device"); return false; }
     int nb = npad / T, ld = npad;
-    MB200_CUDA_CHECK(cudaMemsetAsync(g_xbuf, 0xff, (size_t)kMaxBlocks * T * sizeof(double), s));
-    MB200_CUDA_CHECK(cudaMemsetAsync(g_flags + kMaxTiles, 0, sizeof(int), s));
-    int* abort_flag = g_flags + kMaxTiles;
-    double* xbuf = g_xbuf;
-    void* args[] = {&L, &ld, &nb, &invL, &B, &xbuf, &abort_flag, &d_info};
-    const int grid = nb < g_num_sms ? nb : g_num_sms;
+    MB200_CUDA_CHECK(cudaMemsetAsync(sc->xbuf, 0xff, (size_t)nb * T * sizeof(double), s));
+    MB200_CUDA_CHECK(cudaMemsetAsync(sc->flags + kMaxTiles, 0, sizeof(int), s));
+    int* abort_flag = sc->flags + kMaxTiles;
+    double* xbuf = sc->xbuf;
+    void* args[] = {&L, &ld, &nb, &invL, &B, &xbuf, &abort_flag, &d_info, &d_run_if};
+    const int grid = nb < cfg->num_sms ? nb : cfg->num_sms;
     MB200_CUDA_CHECK(cudaLaunchCooperativeKernel((const void*)chol_backward_dataflow_kernel, dim3(grid), dim3(256), args, 0, s));
     if(nlaunch) (*nlaunch)++;
     return true;

@@ -18,6 +18,7 @@ struct mrcal_b200_factorization
     double* invL = nullptr;
     int*    info = nullptr;
     double* minmax = nullptr;
+    mb200::CholScratch chol;  // this object's own flags of the persistent kernels
 };
 
 namespace mb200 {
@@ -79,12 +80,13 @@ mrcal_b200_factorization_create(const int32_t* Jrowptr, const int32_t* Jcolidx, 
     if(Nrows > 0) jtj_rows_kernel<<<((size_t)Nrows * 32 + 255) / 256, 256, 0, s>>>(d_p, d_i, d_x, Nrows, F->H, F->npad);
     if(F->npad > F->n) pad_diagonal_kernel<<<(F->npad - F->n + 255) / 256, 256, 0, s>>>(F->H, F->npad, F->n, F->npad);
     int info = -1;
-    bool ok = chol_factor(F->H, F->npad, F->n, F->invL, F->info, s, nullptr) &&
+    bool ok = chol_scratch_create(&F->chol) && chol_factor(F->H, F->npad, F->n, F->invL, F->info, s, nullptr, &F->chol) &&
               cudaMemcpyAsync(&info, F->info, sizeof(int), cudaMemcpyDeviceToHost, s) == cudaSuccess &&
               cudaStreamSynchronize(s) == cudaSuccess;
     if(!ok)
     {
         set_error("factorization failed on the device: %s", cudaGetErrorString(cudaGetLastError()));
+        chol_scratch_destroy(&F->chol);
         cudaStreamDestroy(s);
         return nullptr;
     }
@@ -92,6 +94,7 @@ mrcal_b200_factorization_create(const int32_t* Jrowptr, const int32_t* Jcolidx, 
     {
         // the reference reports this the same way: no object (mrcal-pywrap.c:199-212)
         set_error("JtJ is not positive definite (pivot %d)", info - 1);
+        chol_scratch_destroy(&F->chol);
         cudaStreamDestroy(s);
         return nullptr;
     }
@@ -103,6 +106,7 @@ extern "C" void mrcal_b200_factorization_destroy(mrcal_b200_factorization_t* F)
     if(F == nullptr) return;
     if(F->stream) { cudaStreamSynchronize(F->stream); }
     chol_forget_graphs(F->H);
+    chol_scratch_destroy(&F->chol);
     F->arena.release();
     if(F->stream) cudaStreamDestroy(F->stream);
     delete F;

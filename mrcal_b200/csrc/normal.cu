@@ -872,8 +872,11 @@ static bool launch_gram_dmma(const DevProblem& dp, NormalBuffers& N, const EvalB
     return true;
 }
 
-bool normal_assemble(const DevProblem& dp, NormalBuffers& N, const EvalBuffers& op, const int* d_rowptr,
-                     double lambda, cudaStream_t s, int* nlaunch)
+// Pass 1 of the assembly: which shared unknowns do the rows at `op` touch; their compact numbering; where each
+// item's block goes. Ends with an ASYNCHRONOUS copy of (n_c, widest item) to the host: the caller synchronises
+// the stream when it suits it (the solver does so once per trust-region step, with everything else it reads)
+// and then calls normal_adopt_sizes()
+bool normal_prepare(const DevProblem& dp, NormalBuffers& N, const EvalBuffers& op, cudaStream_t s, int* nlaunch)
 {
     if(!configure_kernels()) return false;
     const size_t lmap_bytes = ((size_t)dp.Nintr_state * sizeof(short) + 7) / 8 * 8;
@@ -885,11 +888,8 @@ bool normal_assemble(const DevProblem& dp, NormalBuffers& N, const EvalBuffers& 
         return false;
     }
     const int Nwi = dp.Nobs_board + dp.Nobs_point;
-
-    // ---- pass 1: who touches what; compact numbering of the coupled shared unknowns
     MB200_CUDA_CHECK(cudaMemsetAsync(N.active, 0, (size_t)(N.n_r > 0 ? N.n_r : 1) * sizeof(int), s));
     MB200_CUDA_CHECK(cudaMemsetAsync(N.stat, 0, 4 * sizeof(int), s));
-    MB200_CUDA_CHECK(cudaMemsetAsync(N.info, 0, sizeof(int), s));
     if(Nwi > 0) { item_columns_kernel<<<Nwi, 256, lmap_bytes, s>>>(dp, N, op.Jcol); (*nlaunch)++; }
     if(dp.reg_unity) { mark_reg_active_kernel<<<1, 32, 0, s>>>(dp, N); (*nlaunch)++; }
     if(dp.Ntri > 0) { mark_tri_active_kernel<<<(2 * dp.Ntri + 127) / 128, 128, 0, s>>>(dp, N); (*nlaunch)++; }
@@ -898,18 +898,48 @@ bool normal_assemble(const DevProblem& dp, NormalBuffers& N, const EvalBuffers& 
     compact_scan_kernel<<<1, 1024, 0, s>>>(N);
     (*nlaunch)++;
     if(N.det_available && !normal_det_item_offsets(dp, N, s, nlaunch)) return false;
-    MB200_CUDA_CHECK(cudaMemcpyAsync(N.h_stat, N.stat, 2 * sizeof(int), cudaMemcpyDeviceToHost, s));
-    MB200_CUDA_CHECK(cudaStreamSynchronize(s));
+    MB200_CUDA_CHECK(cudaMemcpyAsync(N.h_stat, N.stat, 4 * sizeof(int), cudaMemcpyDeviceToHost, s));
+    MB200_CUDA_CHECK(cudaGetLastError());
+    return true;
+}
+
+// After the stream was synchronised: take over what normal_prepare() found
+bool normal_adopt_sizes(NormalBuffers& N)
+{
     N.n_c = N.h_stat[0];
-    const int max_ntot = N.h_stat[1];
-    const int ncols_pad = ((max_ntot + 1 + 7) / 8) * 8;
+    N.max_ntot = N.h_stat[1];
+    const int ncols_pad = ((N.max_ntot + 1 + 7) / 8) * 8;
     // The atomics-free path needs every item within the tensor-pipe Gram kernel's width and within its block of the pool
-    N.det = N.det_available && Nwi > 0 && ncols_pad <= kDmmaMaxCols && max_ntot + 2 <= N.capA;
+    // (h_stat[3]: the items' blocks would not fit the pool -- then this assembly takes the other path)
+    N.det = N.det_available && ncols_pad <= kDmmaMaxCols && N.max_ntot + 2 <= N.capA && N.h_stat[3] == 0;
     // padding rows: one carries the right-hand side through the factorization; the atomics-free path keeps the plain
     // gradient in a second one
     N.ldS = chol_padded(N.n_c + (N.det ? 2 : 1));
     if(N.ldS > N.ldS_max) N.ldS = N.ldS_max;
+    return true;
+}
+
+bool normal_assemble(const DevProblem& dp, NormalBuffers& N, const EvalBuffers& op, const int* d_rowptr,
+                     double lambda, cudaStream_t s, int* nlaunch)
+{
+    if(!normal_prepare(dp, N, op, s, nlaunch)) return false;
+    MB200_CUDA_CHECK(cudaStreamSynchronize(s));
+    return normal_adopt_sizes(N) && normal_finish(dp, N, op, d_rowptr, lambda, s, nlaunch);
+}
+
+// Pass 2: Gram matrices, Schur elimination, regularization, right-hand side: S, g', J'x
+bool normal_finish(const DevProblem& dp, NormalBuffers& N, const EvalBuffers& op, const int* d_rowptr,
+                   double lambda, cudaStream_t s, int* nlaunch)
+{
+    const size_t lmap_bytes = ((size_t)dp.Nintr_state * sizeof(short) + 7) / 8 * 8;
+    const size_t ccol_bytes = ((size_t)N.cap * sizeof(int) + 7) / 8 * 8;
+    const int Nwi = dp.Nobs_board + dp.Nobs_point;
+    const int max_ntot = N.max_ntot;
+    const int ncols_pad = ((max_ntot + 1 + 7) / 8) * 8;
+    if(Nwi == 0) N.det = false;
+    if(!N.det) N.ldS = chol_padded(N.n_c + 1) > N.ldS_max ? N.ldS_max : chol_padded(N.n_c + 1);
     MB200_CUDA_CHECK(cudaMemsetAsync(N.g_full, 0, (size_t)dp.Nstate * sizeof(double), s));
+    MB200_CUDA_CHECK(cudaMemsetAsync(N.info, 0, sizeof(int), s));
 
     if(N.det)
     {

@@ -15,6 +15,7 @@ struct NormalBuffers
     int     ldS_max;  // n_r padded: the allocation
     int     n_r;      // number of shared (non-eliminated) unknowns
     int     n_c;      // ... of which touched by some observation: the coupled ("active") ones
+    int     max_ntot; // widest work item (local columns) at the operating point of the last normal_prepare()
     double* gs;       // [ldS_max] reduced gradient g' (compact numbering)
     double* gsh;      // [ldS_max] staging for the shared part of J'x (reduced numbering); follows gs in memory
     int*    active;   // [n_r] flag
@@ -66,6 +67,12 @@ struct NormalBuffers
     __host__ __device__ int state_index(int r) const { return r < e0 ? r : r + (e1 - e0); }
 };
 
+// The same in pieces, for a caller that wants to pick its own moment to wait for the device:
+// prepare (device work + an async copy of the sizes) -> [synchronise the stream] -> adopt_sizes -> finish
+bool normal_prepare(const DevProblem& dp, NormalBuffers& N, const EvalBuffers& op, cudaStream_t s, int* nlaunch);
+bool normal_adopt_sizes(NormalBuffers& N);
+bool normal_finish(const DevProblem& dp, NormalBuffers& N, const EvalBuffers& op, const int* d_rowptr,
+                   double lambda, cudaStream_t s, int* nlaunch);
 // S, g', g_full at the operating point `op` (needs its x and Jacobian). lambda: diagonal loading.
 // Updates N.n_c / N.ldS (one small device->host read)
 bool normal_assemble(const DevProblem& dp, NormalBuffers& N, const EvalBuffers& op, const int* d_rowptr,

@@ -83,7 +83,7 @@ item_offsets_kernel(NormalBuffers N, int Nwi)
         N.wi_Aoff[w] = base;
         base += (long long)N.wi_lda[w] * N.wi_lda[w];
     }
-    if(tid == 1023 && s_scan[1023] > N.A_pool) atomicCAS(N.info, 0, 2000000000);   // pool too small: reported by the host
+    if(tid == 1023 && s_scan[1023] > N.A_pool) N.stat[3] = 1;   // pool too small: the host takes the other path
 }
 
 // After the compaction: compact column of each local column, the two gradient rows, the first local column of

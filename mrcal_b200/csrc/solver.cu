@@ -21,6 +21,8 @@ namespace mb200 {
 bool comm_active();                                                             // nccl.cu
 bool comm_allreduce_sum(double* d_buf, size_t count, cudaStream_t s);           // nccl.cu
 int  comm_rank();
+// the per-rank partial sums of the Cauchy phase sit in slots [6..8] (eliminated range) and [9..10] (row sums): one call
+static bool comm_allreduce_partial(double* scal, cudaStream_t s) { return comm_allreduce_sum(scal + 6, 5, s); }
 
 struct SolverWorkspace
 {
@@ -34,6 +36,9 @@ struct SolverWorkspace
     double* scal = nullptr;       // [16] device scalars
     double* h_scal = nullptr;     // pinned mirror
     int*    h_info = nullptr;     // pinned
+    int*    ictl = nullptr;       // [8] device control flags of the step logic
+    int*    h_ictl = nullptr;     // pinned
+    CholScratch chol;             // this workspace's own flags of the persistent factorization kernels
     std::vector<cudaEvent_t> ev;
     ~SolverWorkspace()
     {
@@ -46,6 +51,7 @@ struct SolverWorkspace
         if(N.ev_fork) cudaEventDestroy(N.ev_fork);
         if(h_scal) cudaFreeHost(h_scal);
         if(h_info) cudaFreeHost(h_info);
+        chol_scratch_destroy(&chol);
         for(auto e : ev) cudaEventDestroy(e);
     }
 };
@@ -93,14 +99,16 @@ jv_kernel(const int* __restrict__ rowptr, const int* __restrict__ col, const dou
 
 // Block k in {0,1,2} reduces range k of the state vector: [0,e0) shared head, [e0,e1) eliminated
 // (the only part that differs between ranks when the frames are sharded), [e1,n) shared tail.
-// out[3k+0] = a.a, out[3k+1] = b.b, out[3k+2] = a.b  (b may be null)
+// out[3j+0] = a.a, out[3j+1] = b.b, out[3j+2] = a.b  (b may be null); j: see below
 __global__ void __launch_bounds__(1024)
 dots_kernel(const double* __restrict__ a, const double* __restrict__ b, int e0, int e1, int n, double* __restrict__ out)
 {
     __shared__ double r[3][32];
     const int i0 = blockIdx.x == 0 ? 0 : (blockIdx.x == 1 ? e0 : e1);
     const int i1 = blockIdx.x == 0 ? e0 : (blockIdx.x == 1 ? e1 : n);
-    out += 3 * blockIdx.x;
+    // slots: head 0..2, tail 3..5, eliminated 6..8 -- the per-rank partial sums (eliminated range) come last, next to
+    // the row sums the caller keeps behind them, so that ONE cross-rank reduction covers both
+    out += blockIdx.x == 0 ? 0 : (blockIdx.x == 1 ? 6 : 3);
     double s0 = 0., s1 = 0., s2 = 0.;
     for(int i = i0 + threadIdx.x; i < i1; i += blockDim.x)
     {
@@ -217,7 +225,8 @@ static bool build_workspace(mrcal_b200_problem* P)
               A.alloc(&N.grp_ptr, (size_t)N.Ngroups + 1) && A.alloc(&N.grp_items, items.size()) &&
               A.alloc(&N.grp_Dinv, (size_t)N.Ngroups * 36) && A.alloc(&N.grp_gf, (size_t)N.Ngroups * 6) &&
               A.alloc(&ws->invL, (size_t)N.ldS_max * kCholBlock) && A.alloc(&ws->rhs, N.ldS_max, true) &&
-              A.alloc(&ws->step_gn, L.Nstate, true) && A.alloc(&ws->step, L.Nstate, true) && A.alloc(&ws->scal, 32, true);
+              A.alloc(&ws->step_gn, L.Nstate, true) && A.alloc(&ws->step, L.Nstate, true) && A.alloc(&ws->scal, 64, true) &&
+              A.alloc(&ws->ictl, 8, true);
     if(!ok) return false;
     // the atomics-free assembly (normal_det.cu)
     N.nblk_max = N.ldS_max / kCholBlock;
@@ -247,9 +256,11 @@ static bool build_workspace(mrcal_b200_problem* P)
         MB200_CUDA_CHECK(cudaEventCreateWithFlags(&N.ev_join[k], cudaEventDisableTiming));
     }
     N.gsh = N.gs + N.ldS_max;
-    MB200_CUDA_CHECK(cudaMallocHost(&ws->h_scal, 32 * sizeof(double)));
-    MB200_CUDA_CHECK(cudaMallocHost(&ws->h_info, 8 * sizeof(int)));
+    MB200_CUDA_CHECK(cudaMallocHost(&ws->h_scal, 64 * sizeof(double)));
+    MB200_CUDA_CHECK(cudaMallocHost(&ws->h_info, 16 * sizeof(int)));
     N.h_stat = ws->h_info + 4;
+    ws->h_ictl = ws->h_info + 8;
+    if(!chol_scratch_create(&ws->chol)) return false;
     MB200_CUDA_CHECK(cudaMemcpyAsync(N.grp_ptr, ptr.data(), ptr.size() * sizeof(int), cudaMemcpyHostToDevice, P->stream));
     if(!items.empty())
         MB200_CUDA_CHECK(cudaMemcpyAsync(N.grp_items, items.data(), items.size() * sizeof(int), cudaMemcpyHostToDevice, P->stream));
@@ -304,12 +315,77 @@ struct PhaseTimer
     }
 };
 
-static bool read_scalars(mrcal_b200_problem* P, int n)
+// ---- the step logic on the device. scal[] slots:
+//   0..8   dots of g = J'x by range (shared head | eliminated | shared tail): a.a, -, -
+//   9,10   x.(J g), |J g|^2
+//   11..19 dots of (gn, g) by range: gn.gn, g.g, gn.g
+//   20,21  x.(J step), |J step|^2        22  |x|^2 at the trial point
+//   32 cg  33 cn  34 update_lensq  35 edge  36 cauchy_lensq  37 gn_lensq  38 kc
+// ictl[]: 0 need_gn (the factorization kernels run only if set)  1 zero gradient
+enum { SC_CG = 32, SC_CN, SC_UPDATE, SC_EDGE, SC_CAUCHY2, SC_GN2, SC_KC, SC_N = 48 };
+
+__global__ void cauchy_decide_kernel(double* __restrict__ scal, int* __restrict__ ictl, double trustregion)
 {
-    SolverWorkspace* ws = P->ws.get();
-    MB200_CUDA_CHECK(cudaMemcpyAsync(ws->h_scal, ws->scal, n * sizeof(double), cudaMemcpyDeviceToHost, P->stream));
-    MB200_CUDA_CHECK(cudaStreamSynchronize(P->stream));
-    return true;
+    if(threadIdx.x != 0 || blockIdx.x != 0) return;
+    const double g2 = scal[0] + scal[3] + scal[6];
+    const double Jg2 = scal[10];
+    if(!(g2 > 0.) || !(Jg2 > 0.))
+    {
+        // zero gradient: nothing to do (libdogleg's Jt_x_threshold test)
+        ictl[1] = 1; ictl[0] = 0;
+        scal[SC_KC] = 0.; scal[SC_CAUCHY2] = 0.;
+        return;
+    }
+    const double kc = g2 / Jg2;
+    const double c2 = kc * kc * g2;
+    scal[SC_KC] = kc;
+    scal[SC_CAUCHY2] = c2;
+    ictl[1] = 0;
+    ictl[0] = c2 >= trustregion * trustregion ? 0 : 1;   // Cauchy point inside the trust region: go on to Gauss-Newton
+}
+
+// Cauchy step to the edge | Gauss-Newton step | dogleg to the edge (libdogleg's takeStepFrom())
+__global__ void select_step_kernel(double* __restrict__ scal, const int* __restrict__ ictl, double trustregion)
+{
+    if(threadIdx.x != 0 || blockIdx.x != 0) return;
+    const double kc = scal[SC_KC], a2 = scal[SC_CAUCHY2];
+    const double tr2 = trustregion * trustregion;
+    double cg, cn, upd, edge;
+    if(ictl[1]) { cg = 0.; cn = 0.; upd = 0.; edge = 0.; }
+    else if(a2 >= tr2)
+    {
+        cg = -kc * trustregion / sqrt(a2); cn = 0.; upd = tr2; edge = 1.;
+    }
+    else
+    {
+        const double gn2 = scal[11] + scal[14] + scal[17];
+        const double g_dot_gn = scal[13] + scal[16] + scal[19];
+        scal[SC_GN2] = gn2;
+        if(gn2 <= tr2) { cg = 0.; cn = 1.; upd = gn2; edge = 0.; }
+        else
+        {
+            // a + k (b-a) on the boundary; a = Cauchy = -kc g, b = Gauss-Newton
+            const double ab = -kc * g_dot_gn;
+            const double l2 = a2 - 2. * ab + gn2;
+            const double c = ab - a2;
+            const double disc = c * c - l2 * (a2 - tr2);
+            const double k = (-c + sqrt(disc > 0. ? disc : 0.)) / l2;
+            cg = -kc * (1. - k); cn = k; upd = tr2; edge = 1.;
+        }
+    }
+    scal[SC_CG] = cg; scal[SC_CN] = cn; scal[SC_UPDATE] = upd; scal[SC_EDGE] = edge;
+}
+
+// step = cg g + cn gn ; p_new = p + step, with cg, cn read on the device
+__global__ void combine_step_dev_kernel(int n, const double* __restrict__ scal, const double* __restrict__ g, const double* __restrict__ gn,
+                                        const double* __restrict__ p, double* __restrict__ step, double* __restrict__ p_new)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if(i >= n) return;
+    const double cg = scal[SC_CG], cn = scal[SC_CN];
+    const double sv = (cg != 0. ? cg * g[i] : 0.) + (cn != 0. ? cn * gn[i] : 0.);
+    step[i] = sv;
+    p_new[i] = p[i] + sv;
 }
 
 static bool dogleg_pass(mrcal_b200_problem* P, const mrcal_b200_solver_parameters_t& par, double* lambda,
@@ -321,40 +397,52 @@ static bool dogleg_pass(mrcal_b200_problem* P, const mrcal_b200_solver_parameter
     cudaStream_t s = P->stream;
     const int Nstate = L.Nstate, Nmeas = L.Nmeas;
     int* nl = &P->launches;
-    double* const S_NORM2 = nullptr; (void)S_NORM2;
 
+    // evaluate the cost function at op[which] and, in the same breath, find out which shared unknowns its rows touch:
+    // the size of the reduced system then reaches the host with the same read as everything else
     auto evaluate = [&](int which) -> bool
     {
         const int a = T->mark();
         if(!problem_evaluate(P, which, true, false)) return false;
         T->spans[0].push_back({a, T->mark()});
         info->Nevaluations++;
+        const int b = T->mark();
+        if(!normal_prepare(P->dp, N, P->op[which], s, nl)) return false;
+        T->spans[1].push_back({b, T->mark()});
         return true;
     };
     auto assemble = [&](int which) -> bool
     {
         const int a = T->mark();
-        if(!normal_assemble(P->dp, N, P->op[which], P->d_rowptr, *lambda, s, nl)) return false;
+        if(!normal_finish(P->dp, N, P->op[which], P->d_rowptr, *lambda, s, nl)) return false;
         T->spans[1].push_back({a, T->mark()});
         return true;
+    };
+    // ONE device -> host read per iteration: the scalars, the control flags, the factorization codes
+    auto read_back = [&]() -> bool
+    {
+        MB200_CUDA_CHECK(cudaMemcpyAsync(ws->h_scal, ws->scal, SC_N * sizeof(double), cudaMemcpyDeviceToHost, s));
+        MB200_CUDA_CHECK(cudaMemcpyAsync(ws->h_info, N.info, 2 * sizeof(int), cudaMemcpyDeviceToHost, s));
+        MB200_CUDA_CHECK(cudaMemcpyAsync(ws->h_ictl, ws->ictl, 2 * sizeof(int), cudaMemcpyDeviceToHost, s));
+        MB200_CUDA_CHECK(cudaStreamSynchronize(s));
+        info->Nsyncs++;
+        return normal_adopt_sizes(N);   // n_c, widest item: from the prepare() that ran last
     };
 
     // rows whose sums this rank contributes to cross-rank reductions: the regularization rows are
     // replicated on every rank but counted once
     const int Nrows_mine = P->dp.reg_owner ? Nmeas : P->dp.m_reg0;
     const int e0 = N.e0, e1 = N.e1;
-    auto sum3 = [&](const double* h, int k) { return h[k] + h[3 + k] + h[6 + k]; };
 
     if(!evaluate(P->cur)) return false;
     if(comm_active() && !comm_allreduce_sum(P->op[P->cur].norm2, 1, s)) return false;
-    MB200_CUDA_CHECK(cudaMemcpyAsync(ws->h_scal, P->op[P->cur].norm2, sizeof(double), cudaMemcpyDeviceToHost, s));
-    MB200_CUDA_CHECK(cudaStreamSynchronize(s));
-    double norm2_x = ws->h_scal[0];
+    MB200_CUDA_CHECK(cudaMemcpyAsync(ws->scal + 22, P->op[P->cur].norm2, sizeof(double), cudaMemcpyDeviceToDevice, s));
+    if(!read_back()) return false;
+    double norm2_x = ws->h_scal[22];
     if(info->Nevaluations == 1) info->norm2_x_initial = norm2_x;
 
     double trustregion = par.trustregion0;
-    bool have_system = false, have_cauchy = false, have_gn = false;
-    double g2 = 0., Jg2 = 0., kc = 0., cauchy_lensq = 0., gn_lensq = 0., g_dot_gn = 0.;
+    bool have_system = false, have_cauchy = false, have_gn = false, sizes_are_cur = true;
     int stepCount = 0;
     bool done = false;
 
@@ -366,6 +454,13 @@ static bool dogleg_pass(mrcal_b200_problem* P, const mrcal_b200_solver_parameter
             const EvalBuffers& nxt = P->op[1 - P->cur];
             if(!have_system)
             {
+                if(!sizes_are_cur)
+                {
+                    // (only after a failed factorization: the column bookkeeping belongs to the trial point by now)
+                    if(!normal_prepare(P->dp, N, cur, s, nl)) return false;
+                    if(!read_back()) return false;
+                    sizes_are_cur = true;
+                }
                 if(!assemble(P->cur)) return false;
                 have_system = true;
                 have_cauchy = have_gn = false;
@@ -377,121 +472,82 @@ static bool dogleg_pass(mrcal_b200_problem* P, const mrcal_b200_solver_parameter
                 dots_kernel<<<3, 1024, 0, s>>>(N.g_full, nullptr, e0, e1, Nstate, ws->scal + 0);
                 jv_kernel<<<148 * 16, 256, 0, s>>>(P->d_rowptr, cur.Jcol, cur.Jval, N.g_full, cur.x, Nrows_mine, ws->scal + 9);
                 *nl += 2;
-                if(comm_active())
-                {
-                    // eliminated-range dots and the row sums are per-rank partial sums: slots [3..5] and [9..10]
-                    if(!comm_allreduce_sum(ws->scal + 3, 3, s) || !comm_allreduce_sum(ws->scal + 9, 2, s)) return false;
-                }
-                if(!read_scalars(P, 11)) return false;
-                g2 = sum3(ws->h_scal, 0);
-                Jg2 = ws->h_scal[10];
-                if(!(g2 > 0.) || !(Jg2 > 0.))
-                {
-                    // zero gradient: nothing to do (libdogleg's Jt_x_threshold test)
-                    done = true;
-                    break;
-                }
-                kc = g2 / Jg2;
-                cauchy_lensq = kc * kc * g2;
+                // eliminated-range dots and the row sums are per-rank partial sums: slots [6..8] and [9..10] -> one reduction
+                if(comm_active() && !comm_allreduce_partial(ws->scal, s)) return false;
                 have_cauchy = true;
             }
-            double cg, cn, update_lensq;
-            bool edge;
-            if(cauchy_lensq >= trustregion * trustregion)
+            cauchy_decide_kernel<<<1, 32, 0, s>>>(ws->scal, ws->ictl, trustregion);
+            (*nl)++;
+            bool factored_now = false;
+            if(!have_gn)
             {
-                // scaled Cauchy step to the edge of the trust region
-                cg = -kc * trustregion / sqrt(cauchy_lensq);
-                cn = 0.;
-                update_lensq = trustregion * trustregion;
-                edge = true;
-            }
-            else
-            {
-                if(!have_gn)
-                {
-                    // ---- Gauss-Newton step: factor the reduced system (diagonal loading on failure), solve, back-substitute
-                    while(true)
-                    {
-                        const int a = T->mark();
-                        if(!chol_factor(N.S, N.ldS, N.n_c, ws->invL, N.info + 1, s, nl)) return false;
-                        MB200_CUDA_CHECK(cudaMemcpyAsync(ws->h_info, N.info, 2 * sizeof(int), cudaMemcpyDeviceToHost, s));
-                        MB200_CUDA_CHECK(cudaStreamSynchronize(s));
-                        T->spans[2].push_back({a, T->mark()});
-                        info->Nfactorizations++;
-                        if(comm_active())
-                        {
-                            // a frame block that is singular on ONE rank must send every rank down the same path
-                            ws->h_scal[30] = (double)(ws->h_info[0] != 0 || ws->h_info[1] != 0);
-                            MB200_CUDA_CHECK(cudaMemcpyAsync(ws->scal + 30, ws->h_scal + 30, sizeof(double), cudaMemcpyHostToDevice, s));
-                            if(!comm_allreduce_sum(ws->scal + 30, 1, s)) return false;
-                            MB200_CUDA_CHECK(cudaMemcpyAsync(ws->h_scal + 30, ws->scal + 30, sizeof(double), cudaMemcpyDeviceToHost, s));
-                            MB200_CUDA_CHECK(cudaStreamSynchronize(s));
-                            if(ws->h_scal[30] != 0. && ws->h_info[0] == 0 && ws->h_info[1] == 0) ws->h_info[0] = -1;
-                        }
-                        if(ws->h_info[0] == 0 && ws->h_info[1] == 0) break;
-                        if(ws->h_info[1] == -9)
-                        {
-                            set_error("the persistent factorization kernel gave up waiting for a tile (code -9): not a property of the matrix");
-                            return false;
-                        }
-                        // singular JtJ: add lambda I "from now on", as libdogleg does (1e-10, then x10)
-                        *lambda = (*lambda == 0.) ? 1e-10 : *lambda * 10.;
-                        if(!std::isfinite(*lambda) || *lambda > 1e30) { set_error("the normal equations stay singular even with lambda=%g", *lambda); return false; }
-                        fprintf(stderr, "mrcal_b200: singular JtJ (codes %d,%d). Adding %g I from now on\n", ws->h_info[0], ws->h_info[1], *lambda);
-                        if(!assemble(P->cur)) return false;
-                    }
-                    const int a = T->mark();
-                    if(!normal_extract_y(N, ws->rhs, s, nl)) return false;
-                    if(N.n_c > 0 && !chol_solve_backward(N.S, N.ldS, ws->invL, ws->rhs, N.ldS, N.info + 1, s, nl)) return false;
-                    if(!normal_expand_step(P->dp, N, P->op[P->cur], *lambda, ws->rhs, ws->ds_r, ws->step_gn, s, nl)) return false;
-                    dots_kernel<<<3, 1024, 0, s>>>(ws->step_gn, N.g_full, e0, e1, Nstate, ws->scal + 11);
-                    (*nl)++;
-                    if(comm_active() && !comm_allreduce_sum(ws->scal + 14, 3, s)) return false;
-                    T->spans[3].push_back({a, T->mark()});
-                    MB200_CUDA_CHECK(cudaMemcpyAsync(ws->h_scal + 11, ws->scal + 11, 9 * sizeof(double), cudaMemcpyDeviceToHost, s));
-                    MB200_CUDA_CHECK(cudaStreamSynchronize(s));
-                    gn_lensq = sum3(ws->h_scal + 11, 0);
-                    g_dot_gn = sum3(ws->h_scal + 11, 2);
-                    have_gn = true;
-                }
-                if(gn_lensq <= trustregion * trustregion)
-                {
-                    cg = 0.; cn = 1.;
-                    update_lensq = gn_lensq;
-                    edge = false;
-                }
-                else
-                {
-                    // dogleg: a + k (b-a) on the trust-region boundary; a = Cauchy = -kc g, b = GN
-                    const double a2 = cauchy_lensq;
-                    const double ab = -kc * g_dot_gn;                 // a.b
-                    const double l2 = a2 - 2. * ab + gn_lensq;        // |b-a|^2
-                    const double c = ab - a2;                         // a.(b-a)
-                    const double disc = c * c - l2 * (a2 - trustregion * trustregion);
-                    const double k = (-c + sqrt(disc > 0. ? disc : 0.)) / l2;
-                    cg = -kc * (1. - k);
-                    cn = k;
-                    update_lensq = trustregion * trustregion;
-                    edge = true;
-                }
+                // ---- Gauss-Newton step: factor the reduced system, solve, back-substitute. The kernels look at ictl[0] and
+                // do nothing if the Cauchy point is outside the trust region
+                const int a = T->mark();
+                if(!chol_factor(N.S, N.ldS, N.n_c, ws->invL, N.info + 1, s, nl, &ws->chol, ws->ictl)) return false;
+                T->spans[2].push_back({a, T->mark()});
+                const int b = T->mark();
+                if(!normal_extract_y(N, ws->rhs, s, nl)) return false;
+                if(N.n_c > 0 && !chol_solve_backward(N.S, N.ldS, ws->invL, ws->rhs, N.ldS, N.info + 1, s, nl, &ws->chol, ws->ictl)) return false;
+                if(!normal_expand_step(P->dp, N, P->op[P->cur], *lambda, ws->rhs, ws->ds_r, ws->step_gn, s, nl)) return false;
+                dots_kernel<<<3, 1024, 0, s>>>(ws->step_gn, N.g_full, e0, e1, Nstate, ws->scal + 11);
+                (*nl)++;
+                if(comm_active() && !comm_allreduce_sum(ws->scal + 17, 3, s)) return false;
+                T->spans[3].push_back({b, T->mark()});
+                factored_now = true;
             }
             // ---- take the step
-            combine_step_kernel<<<(Nstate + 255) / 256, 256, 0, s>>>(Nstate, cg, N.g_full, cn, ws->step_gn, cur.p, ws->step, nxt.p);
-            (*nl)++;
+            select_step_kernel<<<1, 32, 0, s>>>(ws->scal, ws->ictl, trustregion);
+            combine_step_dev_kernel<<<(Nstate + 255) / 256, 256, 0, s>>>(Nstate, ws->scal, N.g_full, ws->step_gn, cur.p, ws->step, nxt.p);
+            MB200_CUDA_CHECK(cudaMemsetAsync(ws->scal + 20, 0, 2 * sizeof(double), s));
+            jv_kernel<<<148 * 16, 256, 0, s>>>(P->d_rowptr, cur.Jcol, cur.Jval, ws->step, cur.x, Nrows_mine, ws->scal + 20);
+            *nl += 3;
+            if(!evaluate(1 - P->cur)) return false;
+            sizes_are_cur = false;
+            MB200_CUDA_CHECK(cudaMemcpyAsync(ws->scal + 22, nxt.norm2, sizeof(double), cudaMemcpyDeviceToDevice, s));
+            if(comm_active() && !comm_allreduce_sum(ws->scal + 20, 3, s)) return false;
+            if(!read_back()) return false;
+
+            const bool need_gn = ws->h_ictl[0] != 0, zero_grad = ws->h_ictl[1] != 0;
+            if(zero_grad) { done = true; break; }
+            if(factored_now && need_gn)
+            {
+                info->Nfactorizations++;
+                int bad = (ws->h_info[0] != 0 || ws->h_info[1] != 0) ? 1 : 0;
+                if(ws->h_info[1] == -9)
+                {
+                    set_error("the persistent factorization kernel gave up waiting for a tile (code -9): not a property of the matrix");
+                    return false;
+                }
+                if(comm_active())
+                {
+                    // a frame block that is singular on ONE rank must send every rank down the same path
+                    ws->h_scal[SC_N] = (double)bad;
+                    MB200_CUDA_CHECK(cudaMemcpyAsync(ws->scal + SC_N, ws->h_scal + SC_N, sizeof(double), cudaMemcpyHostToDevice, s));
+                    if(!comm_allreduce_sum(ws->scal + SC_N, 1, s)) return false;
+                    MB200_CUDA_CHECK(cudaMemcpyAsync(ws->h_scal + SC_N, ws->scal + SC_N, sizeof(double), cudaMemcpyDeviceToHost, s));
+                    MB200_CUDA_CHECK(cudaStreamSynchronize(s));
+                    bad = ws->h_scal[SC_N] != 0.;
+                }
+                if(bad)
+                {
+                    // singular JtJ: add lambda I "from now on", as libdogleg does (1e-10, then x10), and do this operating point again
+                    *lambda = (*lambda == 0.) ? 1e-10 : *lambda * 10.;
+                    if(!std::isfinite(*lambda) || *lambda > 1e30) { set_error("the normal equations stay singular even with lambda=%g", *lambda); return false; }
+                    fprintf(stderr, "mrcal_b200: singular JtJ (codes %d,%d). Adding %g I from now on\n", ws->h_info[0], ws->h_info[1], *lambda);
+                    have_system = false;
+                    continue;
+                }
+                have_gn = true;
+            }
+            const double update_lensq = ws->h_scal[SC_UPDATE];
+            const bool edge = ws->h_scal[SC_EDGE] != 0.;
             if(update_lensq < par.update_threshold)
             {
                 // libdogleg compares the SQUARED step length with update_threshold
                 done = true;
                 break;
             }
-            MB200_CUDA_CHECK(cudaMemsetAsync(ws->scal + 20, 0, 2 * sizeof(double), s));
-            jv_kernel<<<148 * 16, 256, 0, s>>>(P->d_rowptr, cur.Jcol, cur.Jval, ws->step, cur.x, Nrows_mine, ws->scal + 20);
-            (*nl)++;
-            if(!evaluate(1 - P->cur)) return false;
-            MB200_CUDA_CHECK(cudaMemcpyAsync(ws->scal + 22, nxt.norm2, sizeof(double), cudaMemcpyDeviceToDevice, s));
-            if(comm_active() && !comm_allreduce_sum(ws->scal + 20, 3, s)) return false;
-            MB200_CUDA_CHECK(cudaMemcpyAsync(ws->h_scal + 20, ws->scal + 20, 3 * sizeof(double), cudaMemcpyDeviceToHost, s));
-            MB200_CUDA_CHECK(cudaStreamSynchronize(s));
             // |x|^2 - |x + J step|^2
             const double expected = -ws->h_scal[21] - 2. * ws->h_scal[20];
             const double norm2_new = ws->h_scal[22];
@@ -504,6 +560,7 @@ static bool dogleg_pass(mrcal_b200_problem* P, const mrcal_b200_solver_parameter
                 P->cur = 1 - P->cur;
                 norm2_x = norm2_new;
                 have_system = false;
+                sizes_are_cur = true;
                 break;
             }
             // rejected: same operating point, smaller trust region
