@@ -298,8 +298,8 @@ bool mrcal_corresponding_icam_extrinsics(int* icam_extrinsics,
 // owned by the caller, exactly as in the reference)
 ////////////////////////////////////////////////////////////////////////////////
 
-// replaces mrcal.h:165-191: q = project(p), N points in camera coordinates. dq_dp may be NULL;
-// dq_dintrinsics must be NULL (not provided by this library)
+// replaces mrcal.h:165-191: q = project(p), N points in camera coordinates. dq_dp (N,2,3) and
+// dq_dintrinsics (N,2,Nintrinsics: dense, as mrcal.c:2866-2992 fills it) may be NULL
 bool mrcal_project(mrcal_point2_t* q, mrcal_point3_t* dq_dp, double* dq_dintrinsics,
                    const mrcal_point3_t* p, int N,
                    const mrcal_lensmodel_t* lensmodel, const double* intrinsics);

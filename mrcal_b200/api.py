@@ -401,6 +401,43 @@ def optimize(**kwargs):
                 b_packed=b, x=x)
 
 
+def check_gradient(**kwargs):
+    """The reference's gradient self-check, mrcal_optimize(..., check_gradient=true) (mrcal.c:6601-6605; driven by
+    test/test-gradients.c + test/test-gradients.py): every column of the Jacobian against a forward difference of
+    the residuals. The C entry point prints libdogleg's vnlog to stdout; this helper captures and parses it.
+    Returns an array of rows (ivar, imeasurement, gradient_reported, gradient_observed)."""
+    import os
+    import tempfile
+    _require_gpu()
+    I = _Inputs(kwargs)
+    ob, op = I.c_observations()
+    tri, ntri = I.c_triangulated(rays=True)
+    sys_stdout_fd = 1
+    with tempfile.TemporaryFile(mode="w+b") as tmp:
+        import sys as _sys
+        _sys.stdout.flush()
+        saved = os.dup(sys_stdout_fd)
+        os.dup2(tmp.fileno(), sys_stdout_fd)
+        try:
+            lib.mrcal_optimize(
+                None, C.c_int(0), None, C.c_int(0),
+                _ptr(I.intrinsics), _ptr(I.rt_cam_ref), _ptr(I.rt_ref_frame), _ptr(I.points),
+                _ptr(I.calobject_warp) if I.calobject_warp is not None else None,
+                I.Ncam_i, I.Ncam_e, I.Nframes, I.Npoints, I.Npoints_fixed,
+                _ptr(ob), _ptr(op), I.Nobs_board, I.Nobs_point, tri, ntri,
+                _ptr(I.observations_board), _ptr(I.observations_point),
+                I.lm_ref(), _ptr(I.imagersizes), I.selections, None,
+                C.c_double(I.spacing), max(I.W, 0), max(I.H, 0), C.c_bool(False), C.c_bool(True))
+        finally:
+            os.dup2(saved, sys_stdout_fd)
+            os.close(saved)
+        tmp.seek(0)
+        rows = [l.split() for l in tmp.read().decode().splitlines() if l and not l.startswith("#")]
+    if not rows:
+        raise RuntimeError("check_gradient produced no output: " + _capi.last_error())
+    return np.array([[float(v) for v in r[:4]] for r in rows])
+
+
 class Problem:
     """Device-resident problem (extension; include/mrcal_b200.h part 2): upload
     once, then solve / evaluate repeatedly without touching the host inputs."""
@@ -855,8 +892,8 @@ def unpack_state(b, **kwargs):
 
 def project(v, lensmodel, intrinsics_data, get_gradients=False):
     """q = project(v): the reference's mrcal.project() for one camera (mrcal-pywrap.c / mrcal.h:165-191).
-    v: (...,3) points in camera coordinates. Returns q (...,2), and dq_dv (...,2,3) too with get_gradients
-    (the gradient with respect to the intrinsics is not provided by this library)."""
+    v: (...,3) points in camera coordinates. Returns q (...,2); with get_gradients, as the reference,
+    (q, dq_dv (...,2,3), dq_dintrinsics (...,2,Nintrinsics))."""
     _require_gpu()
     v = np.ascontiguousarray(v, dtype=np.float64)
     if v.shape[-1] != 3:
@@ -868,10 +905,14 @@ def project(v, lensmodel, intrinsics_data, get_gradients=False):
     flat = v.reshape(-1, 3)
     q = np.zeros((flat.shape[0], 2))
     g = np.zeros((flat.shape[0], 2, 3)) if get_gradients else None
-    if not lib.mrcal_project(_ptr(q), _ptr(g) if g is not None else None, None, _ptr(flat), flat.shape[0], C.byref(lm), _ptr(intr)):
+    gi = np.zeros((flat.shape[0], 2, intr.shape[0])) if get_gradients else None
+    if not lib.mrcal_project(_ptr(q), _ptr(g) if g is not None else None, _ptr(gi) if gi is not None else None,
+                             _ptr(flat), flat.shape[0], C.byref(lm), _ptr(intr)):
         raise RuntimeError("mrcal_project() failed: " + _capi.last_error())
     q = q.reshape(v.shape[:-1] + (2,))
-    return (q, g.reshape(v.shape[:-1] + (2, 3))) if get_gradients else q
+    if not get_gradients:
+        return q
+    return q, g.reshape(v.shape[:-1] + (2, 3)), gi.reshape(v.shape[:-1] + (2, intr.shape[0]))
 
 
 def unproject(q, lensmodel, intrinsics_data):

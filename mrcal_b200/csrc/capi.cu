@@ -163,11 +163,6 @@ extern "C" mrcal_stats_t mrcal_optimize(double* b_packed_final, int buffer_size_
     (void)problem_constants; (void)verbose;
     mrcal_stats_t bad = {};
     bad.rms_reproj_error__pixels = -1.0;
-    if(check_gradient)
-    {
-        set_error("mrcal_optimize(check_gradient=true) is a libdogleg debugging facility and is not provided by the CUDA path");
-        return bad;
-    }
     std::lock_guard<std::mutex> lock(g_cache.mtx);
     struct { mrcal_b200_problem_t* p; } g{acquire_problem(intrinsics, rt_cam_ref, rt_ref_frame, points, calobject_warp,
                                              Ncameras_intrinsics, Ncameras_extrinsics, Nframes, Npoints, Npoints_fixed,
@@ -193,6 +188,45 @@ extern "C" mrcal_stats_t mrcal_optimize(double* b_packed_final, int buffer_size_
     if(Nmeas <= Nstate)
         fprintf(stderr, "mrcal_b200: WARNING: problem isn't overdetermined: Nmeasurements=%d, Nstate=%d\n", Nmeas, Nstate);
 
+    if(check_gradient)
+    {
+        // The reference hands every state variable to libdogleg's dogleg_testGradient() (mrcal.c:6601-6605), which
+        // compares the reported Jacobian column with a forward difference and prints a vnlog
+        // (test/test-gradients.py parses it). The same, with our own callback. Nothing is solved; like the
+        // reference, rms comes out as sqrt(-1/Nmeasurements) = NaN
+        const int nnz = mrcal_b200_problem_num_j_nonzero(g.p);
+        std::vector<double> b0(Nstate), x0(Nmeas), x1(Nmeas), Jv(nnz), b1;
+        std::vector<int32_t> Jp(Nmeas + 1), Ji(nnz);
+        if(!mrcal_b200_problem_callback(g.p, b0.data(), x0.data(), Jp.data(), Ji.data(), Jv.data())) return bad;
+        // J by columns
+        std::vector<std::vector<std::pair<int, double>>> cols(Nstate);
+        for(int m = 0; m < Nmeas; m++)
+            for(int e = Jp[m]; e < Jp[m + 1]; e++) cols[Ji[e]].push_back({m, Jv[e]});
+        const double delta = 1e-6;
+        printf("# ivar imeasurement gradient_reported gradient_observed error error_relative\n");
+        for(int ivar = 0; ivar < Nstate; ivar++)
+        {
+            b1 = b0;
+            b1[ivar] += delta;
+            if(!mrcal_b200_problem_reset(g.p, b1.data()) || !mrcal_b200_problem_callback(g.p, nullptr, x1.data(), nullptr, nullptr, nullptr)) return bad;
+            size_t k = 0;
+            for(int m = 0; m < Nmeas; m++)
+            {
+                double rep = 0.;
+                bool have = false;
+                while(k < cols[ivar].size() && cols[ivar][k].first == m) { rep += cols[ivar][k].second; have = true; k++; }
+                const double obs = (x1[m] - x0[m]) / delta;
+                if(!have && obs == 0.) continue;
+                const double err = rep - obs, den = (fabs(rep) + fabs(obs)) / 2.;
+                printf("%d %d %.6g %.6g %.6g %.6g\n", ivar, m, rep, obs, err, den > 0. ? fabs(err) / den : 0.);
+            }
+        }
+        fflush(stdout);
+        mrcal_b200_problem_reset(g.p, b0.data());
+        mrcal_stats_t st = {};
+        st.rms_reproj_error__pixels = sqrt(-1.0 / (double)Nmeas);
+        return st;
+    }
     mrcal_stats_t stats = bad;
     if(!mrcal_b200_problem_optimize(g.p, nullptr, &stats, nullptr)) return bad;
     if(!mrcal_b200_problem_download(g.p, b_packed_final, x_final, intrinsics, rt_cam_ref, rt_ref_frame, points,

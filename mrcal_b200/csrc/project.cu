@@ -36,14 +36,45 @@ __device__ __forceinline__ void project_any(double q[2], double dq_dp[2][3], con
         project_parametric<KIND>(q, dq_dp, nullptr, p, a.intr, a.cfg);
 }
 
+// dq_di: dense (N,2,Nintr), zeroed by the caller, or NULL. The layout of mrcal.c:2936-2992: the core (dq/df
+// on its own axis only, dq/dc = I), then the distortions -- dense for the parametric models, the RUN x RUN touched
+// control points of the matching surface for the splined ones
 template <int KIND>
-__global__ void project_kernel(LensArgs a, const double* __restrict__ p, int N, double* __restrict__ q, double* __restrict__ dq_dp)
+__global__ void project_kernel(LensArgs a, const double* __restrict__ p, int N, double* __restrict__ q, double* __restrict__ dq_dp,
+                               double* __restrict__ dq_di, int Nintr)
 {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if(i >= N) return;
     double qq[2], g[2][3];
     const double pp[3] = {p[3 * i], p[3 * i + 1], p[3 * i + 2]};
-    project_any<KIND>(qq, g, pp, a);
+    if(dq_di == nullptr) project_any<KIND>(qq, g, pp, a);
+    else
+    {
+        double* out = dq_di + (size_t)i * 2 * Nintr;
+        if constexpr(LensTraits<KIND>::SPLINED)
+        {
+            constexpr int RUN = LensTraits<KIND>::RUN;
+            double wx[4], wy[4], upd[2];
+            int ivar0;
+            project_splined<RUN>(qq, g, wx, wy, &ivar0, upd, pp, a.intr, a.Nx, a.Ny, a.segments_per_u);
+            out[0] = upd[0]; out[Nintr + 1] = upd[1];
+            for(int k = 0; k < 2; k++)
+                for(int iy = 0; iy < RUN; iy++)
+                    for(int ix = 0; ix < RUN; ix++)
+                        out[k * Nintr + ivar0 + 2 * a.Nx * iy + 2 * ix + k] = wx[ix] * wy[iy] * a.intr[k];
+        }
+        else
+        {
+            constexpr int ND = LensTraits<KIND>::NDIST;
+            double ddist[2][ND > 0 ? ND : 1];
+            project_parametric<KIND>(qq, g, ddist, pp, a.intr, a.cfg);
+            out[0] = (qq[0] - a.intr[2]) / a.intr[0];          // mrcal.c:1427-1431
+            out[Nintr + 1] = (qq[1] - a.intr[3]) / a.intr[1];
+            for(int k = 0; k < 2; k++)
+                for(int d = 0; d < ND; d++) out[k * Nintr + 4 + d] = ddist[k][d];
+        }
+        out[2] = 1.; out[Nintr + 3] = 1.;
+    }
     q[2 * i] = qq[0]; q[2 * i + 1] = qq[1];
     if(dq_dp)
         for(int r = 0; r < 2; r++)
@@ -122,11 +153,11 @@ __global__ void unproject_kernel(LensArgs a, const double* __restrict__ q, int N
 
 struct Scratch
 {
-    double *d_intr = nullptr, *d_in = nullptr, *d_out = nullptr, *d_grad = nullptr;
-    ~Scratch() { cudaFree(d_intr); cudaFree(d_in); cudaFree(d_out); cudaFree(d_grad); }
+    double *d_intr = nullptr, *d_in = nullptr, *d_out = nullptr, *d_grad = nullptr, *d_gi = nullptr;
+    ~Scratch() { cudaFree(d_intr); cudaFree(d_in); cudaFree(d_out); cudaFree(d_grad); cudaFree(d_gi); }
 };
 
-bool run(bool unproject, double* out, double* dq_dp, const double* in, int N, const mrcal_lensmodel_t* lensmodel, const double* intrinsics)
+bool run(bool unproject, double* out, double* dq_dp, double* dq_di, const double* in, int N, const mrcal_lensmodel_t* lensmodel, const double* intrinsics)
 {
     int ndev = 0;
     if(cudaGetDeviceCount(&ndev) != cudaSuccess || ndev <= 0)
@@ -164,6 +195,11 @@ bool run(bool unproject, double* out, double* dq_dp, const double* in, int N, co
     MB200_CUDA_CHECK(cudaMalloc(&S.d_in, nin * sizeof(double)));
     MB200_CUDA_CHECK(cudaMalloc(&S.d_out, nout * sizeof(double)));
     if(dq_dp) MB200_CUDA_CHECK(cudaMalloc(&S.d_grad, (size_t)N * 6 * sizeof(double)));
+    if(dq_di)
+    {
+        MB200_CUDA_CHECK(cudaMalloc(&S.d_gi, (size_t)N * 2 * Nintr * sizeof(double)));
+        MB200_CUDA_CHECK(cudaMemset(S.d_gi, 0, (size_t)N * 2 * Nintr * sizeof(double)));
+    }
     MB200_CUDA_CHECK(cudaMemcpy(S.d_intr, intrinsics, Nintr * sizeof(double), cudaMemcpyHostToDevice));
     MB200_CUDA_CHECK(cudaMemcpy(S.d_in, in, nin * sizeof(double), cudaMemcpyHostToDevice));
     a.intr = S.d_intr;
@@ -171,7 +207,7 @@ bool run(bool unproject, double* out, double* dq_dp, const double* in, int N, co
     const int threads = 128, blocks = (N + threads - 1) / threads;
 #define MB200_LENS_CASE(K) \
     case K: if(unproject) unproject_kernel<K><<<blocks, threads>>>(a, S.d_in, N, S.d_out, meta.can_project_behind_camera); \
-            else          project_kernel<K><<<blocks, threads>>>(a, S.d_in, N, S.d_out, S.d_grad); break;
+            else          project_kernel<K><<<blocks, threads>>>(a, S.d_in, N, S.d_out, S.d_grad, S.d_gi, Nintr); break;
     switch(kind)
     {
         MB200_LENS_CASE(LENS_PINHOLE) MB200_LENS_CASE(LENS_STEREOGRAPHIC) MB200_LENS_CASE(LENS_LONLAT) MB200_LENS_CASE(LENS_LATLON)
@@ -183,6 +219,7 @@ bool run(bool unproject, double* out, double* dq_dp, const double* in, int N, co
     MB200_CUDA_CHECK(cudaGetLastError());
     MB200_CUDA_CHECK(cudaMemcpy(out, S.d_out, nout * sizeof(double), cudaMemcpyDeviceToHost));
     if(dq_dp) MB200_CUDA_CHECK(cudaMemcpy(dq_dp, S.d_grad, (size_t)N * 6 * sizeof(double), cudaMemcpyDeviceToHost));
+    if(dq_di) MB200_CUDA_CHECK(cudaMemcpy(dq_di, S.d_gi, (size_t)N * 2 * Nintr * sizeof(double), cudaMemcpyDeviceToHost));
     return true;
 }
 
@@ -191,18 +228,16 @@ bool run(bool unproject, double* out, double* dq_dp, const double* in, int N, co
 
 using namespace mb200;
 
-// replaces mrcal.h:165-191. dq_dintrinsics is not provided here (the per-model layouts of that array belong to
-// the reference's Python-facing code, off the optimization path): pass NULL
+// replaces mrcal.h:165-191. dq_dp (N,2,3) and dq_dintrinsics (N,2,Nintrinsics; dense, mrcal.c:2866-2992) may be NULL
 extern "C" bool mrcal_project(mrcal_point2_t* q, mrcal_point3_t* dq_dp, double* dq_dintrinsics,
                               const mrcal_point3_t* p, int N, const mrcal_lensmodel_t* lensmodel, const double* intrinsics)
 {
-    if(dq_dintrinsics != nullptr) { set_error("mrcal_project(): dq_dintrinsics is not available from the CUDA library; pass NULL"); return false; }
-    return run(false, (double*)q, (double*)dq_dp, (const double*)p, N, lensmodel, intrinsics);
+    return run(false, (double*)q, (double*)dq_dp, dq_dintrinsics, (const double*)p, N, lensmodel, intrinsics);
 }
 
 // replaces mrcal.h:193-224
 extern "C" bool mrcal_unproject(mrcal_point3_t* out, const mrcal_point2_t* q, int N,
                                 const mrcal_lensmodel_t* lensmodel, const double* intrinsics)
 {
-    return run(true, (double*)out, nullptr, (const double*)q, N, lensmodel, intrinsics);
+    return run(true, (double*)out, nullptr, nullptr, (const double*)q, N, lensmodel, intrinsics);
 }

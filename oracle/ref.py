@@ -400,6 +400,20 @@ class Problem:
         return b
 
 
+def project_with_intrinsics_gradient(p, lensmodel_name, intrinsics):
+    """Reference mrcal_project with both gradients: q (N,2), dq_dp (N,2,3), dq_dintrinsics (N,2,Nintrinsics)."""
+    lm = lensmodel_from_name(lensmodel_name)
+    p = np.ascontiguousarray(p, dtype=np.float64).reshape(-1, 3)
+    intrinsics = np.ascontiguousarray(intrinsics, dtype=np.float64)
+    N = p.shape[0]
+    q = np.zeros((N, 2))
+    dq_dp = np.zeros((N, 2, 3))
+    dq_di = np.zeros((N, 2, intrinsics.shape[0]))
+    if not lib().mrcal_project(_dp(q), _dp(dq_dp), _dp(dq_di), _dp(p), N, C.byref(lm), _dp(intrinsics)):
+        raise RuntimeError("reference mrcal_project() failed")
+    return q, dq_dp, dq_di
+
+
 def project(p, lensmodel_name, intrinsics, gradients=False):
     """Reference mrcal_project (mrcal.h:165). p: (N,3). Returns q (N,2) [, dq_dp (N,2,3)]."""
     lm = lensmodel_from_name(lensmodel_name)

@@ -30,9 +30,14 @@ def test_project_matches_reference(ref, lm):
     intr = synthetic.true_intrinsics(lm, 1, np.random.default_rng(0))[0]
     p = _points(40, 1)
     q_ref, g_ref = ref.project(p, lm, intr, gradients=True)
-    q, g = mrcal_b200.project(p, lm, intr, get_gradients=True)
+    q, g, gi = mrcal_b200.project(p, lm, intr, get_gradients=True)
     assert np.abs(q - q_ref).max() <= 1e-9 * (1. + np.abs(q_ref).max())
     assert np.abs(g - g_ref).max() <= 1e-9 * (1. + np.abs(g_ref).max())
+    # the gradient with respect to the intrinsics: dense (N,2,Nintrinsics), mrcal.c:2866-2992
+    q3, g3, gi_ref = ref.project_with_intrinsics_gradient(p, lm, intr)
+    assert gi.shape == gi_ref.shape == (40, 2, len(intr))
+    assert np.abs(gi - gi_ref).max() <= 1e-9 * (1. + np.abs(gi_ref).max())
+    assert np.abs(g - g3).max() <= 1e-9 * (1. + np.abs(g3).max())
     # broadcasting over leading dimensions, and the no-gradient flavour
     q2 = mrcal_b200.project(p.reshape(8, 5, 3), lm, intr)
     assert q2.shape == (8, 5, 2) and np.array_equal(q2.reshape(-1, 2), q)
