@@ -819,4 +819,31 @@ bool launch_evaluate(const DevProblem& dp, const EvalBuffers& out, bool with_jac
     return true;
 }
 
+// development / test aid (not in the public header): the triangulated-point error function on its own
+__global__ void debug_triangulated_error_kernel(const double* __restrict__ in, int N, double* __restrict__ out)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if(i >= N) return;
+    double g_v[3], g_t[3];
+    // in: v0 (the ray without gradient), v1, t01 -- the reference's argument names (triangulation.cc:960-975)
+    const double err = triangulated_error(g_v, g_t, &in[9 * i], &in[9 * i + 3], &in[9 * i + 6]);
+    out[7 * i] = err;
+    for(int k = 0; k < 3; k++) { out[7 * i + 1 + k] = g_v[k]; out[7 * i + 4 + k] = g_t[k]; }
+}
+
 }  // namespace mb200
+
+extern "C" bool mrcal_b200_debug_triangulated_error(const double* v0_v1_t01 /*[N][9]*/, int N, double* err_dv1_dt01 /*[N][7]*/)
+{
+    double *d_in = nullptr, *d_out = nullptr;
+    bool ok = cudaMalloc(&d_in, (size_t)N * 9 * sizeof(double)) == cudaSuccess && cudaMalloc(&d_out, (size_t)N * 7 * sizeof(double)) == cudaSuccess &&
+              cudaMemcpy(d_in, v0_v1_t01, (size_t)N * 9 * sizeof(double), cudaMemcpyHostToDevice) == cudaSuccess;
+    if(ok)
+    {
+        mb200::debug_triangulated_error_kernel<<<(N + 127) / 128, 128>>>(d_in, N, d_out);
+        ok = cudaMemcpy(err_dv1_dt01, d_out, (size_t)N * 7 * sizeof(double), cudaMemcpyDeviceToHost) == cudaSuccess;
+    }
+    if(!ok) mb200::set_error("debug_triangulated_error: %s", cudaGetErrorString(cudaGetLastError()));
+    cudaFree(d_in); cudaFree(d_out);
+    return ok;
+}
