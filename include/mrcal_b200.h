@@ -409,6 +409,7 @@ typedef struct
     int    Nreduced;             // order of the reduced (camera) system that was factored
     int    Nkernel_launches;     // launches of THIS library's kernels inside the solve
     int    Nsyncs;               // host waits on the device inside the solve (one per trust-region step)
+    int    Ncollectives;         // NCCL all-reduce calls inside the solve (sharded solves)
     double norm2_x_initial, norm2_x_final;
     double ms_total;             // device time of the whole solve (CUDA events)
     double ms_evaluate;          // ... spent in residual/Jacobian kernels

@@ -61,7 +61,7 @@ class SolverParameters(C.Structure):
 
 class SolveInfo(C.Structure):
     _fields_ = [("Niterations", C.c_int), ("Nevaluations", C.c_int), ("Nfactorizations", C.c_int),
-                ("Nouter", C.c_int), ("Nreduced", C.c_int), ("Nkernel_launches", C.c_int), ("Nsyncs", C.c_int),
+                ("Nouter", C.c_int), ("Nreduced", C.c_int), ("Nkernel_launches", C.c_int), ("Nsyncs", C.c_int), ("Ncollectives", C.c_int),
                 ("norm2_x_initial", C.c_double), ("norm2_x_final", C.c_double),
                 ("ms_total", C.c_double), ("ms_evaluate", C.c_double), ("ms_assemble", C.c_double),
                 ("ms_factor", C.c_double), ("ms_solve", C.c_double), ("lambda_final", C.c_double)]

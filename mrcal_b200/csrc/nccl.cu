@@ -59,6 +59,8 @@ static bool load_nccl()
     return true;
 }
 
+static long g_collectives = 0;   // all-reduce calls issued (a figure for DESIGN.md / bench.py)
+long comm_collective_count() { return g_collectives; }
 bool comm_active() { return g_nccl.comm != nullptr && g_nccl.nranks > 1; }
 int  comm_rank() { return g_nccl.rank; }
 int  comm_size() { return g_nccl.nranks; }
@@ -66,6 +68,7 @@ int  comm_size() { return g_nccl.nranks; }
 bool comm_allreduce_sum(double* d_buf, size_t count, cudaStream_t s)
 {
     if(!comm_active()) return true;
+    g_collectives++;
     const int rc = g_nccl.AllReduce(d_buf, d_buf, count, /*ncclFloat64*/ 8, /*ncclSum*/ 0, g_nccl.comm, s);
     if(rc != 0)
     {
@@ -78,6 +81,7 @@ bool comm_allreduce_sum(double* d_buf, size_t count, cudaStream_t s)
 bool comm_allreduce_max_int(int* d_buf, size_t count, cudaStream_t s)
 {
     if(!comm_active()) return true;
+    g_collectives++;
     const int rc = g_nccl.AllReduce(d_buf, d_buf, count, /*ncclInt32*/ 2, /*ncclMax*/ 2, g_nccl.comm, s);
     if(rc != 0)
     {

@@ -16,6 +16,8 @@
 // only the reduced result goes to global memory. For splined models the touched
 // knot columns are data-dependent (mrcal.c:2171-2185), so each CTA discovers
 // its own local column set every time.
+#include <vector>
+
 #include "normal_items.cuh"
 #include "chol.h"
 
@@ -919,6 +921,53 @@ bool normal_adopt_sizes(NormalBuffers& N)
     return true;
 }
 
+// One-time cross-check of the two assembly paths against each other on the caller's own problem (first assembly of a
+// workspace): the atomics-free path must reproduce the atomic one to rounding. If it does not, it is switched off for
+// this workspace, loudly. (Costs one extra assembly; MRCAL_B200_NO_SELFCHECK=1 skips it.)
+bool normal_selfcheck(const DevProblem& dp, NormalBuffers& N, const EvalBuffers& op, const int* d_rowptr,
+                      double lambda, cudaStream_t s, int* nlaunch)
+{
+    if(N.selfchecked || !N.det_available || comm_active() || getenv("MRCAL_B200_NO_SELFCHECK") != nullptr) { N.selfchecked = true; return true; }
+    N.selfchecked = true;
+    if(!N.det || N.n_c <= 0) return true;
+    const int n = N.n_c;
+    std::vector<double> Sd((size_t)(n + 1) * n), Sa((size_t)(n + 1) * n);
+    if(!normal_finish(dp, N, op, d_rowptr, lambda, s, nlaunch)) return false;
+    MB200_CUDA_CHECK(cudaMemcpy2DAsync(Sd.data(), (size_t)n * sizeof(double), N.S, (size_t)N.ldS * sizeof(double),
+                                       (size_t)n * sizeof(double), n + 1, cudaMemcpyDeviceToHost, s));
+    MB200_CUDA_CHECK(cudaStreamSynchronize(s));
+    const bool det_saved = N.det;
+    const int ld_saved = N.ldS;
+    N.det = false;
+    const bool ok = normal_finish(dp, N, op, d_rowptr, lambda, s, nlaunch);
+    if(ok)
+    {
+        MB200_CUDA_CHECK(cudaMemcpy2DAsync(Sa.data(), (size_t)n * sizeof(double), N.S, (size_t)N.ldS * sizeof(double),
+                                           (size_t)n * sizeof(double), n + 1, cudaMemcpyDeviceToHost, s));
+        MB200_CUDA_CHECK(cudaStreamSynchronize(s));
+    }
+    N.det = det_saved;
+    N.ldS = ld_saved;
+    if(!ok) return false;
+    double scale = 0., worst = 0.;
+    for(int i = 0; i <= n; i++)
+        for(int j = 0; j < (i < n ? i + 1 : n); j++)
+        {
+            const double a = Sa[(size_t)i * n + j], d = Sd[(size_t)i * n + j];
+            if(fabs(a) > scale) scale = fabs(a);
+            if(!(fabs(a - d) <= worst)) worst = fabs(a - d);
+        }
+    if(!(worst <= 1e-9 * scale))
+    {
+        fprintf(stderr, "mrcal_b200: WARNING: the atomics-free assembly disagrees with the atomic one (|diff| %g of %g): "
+                        "using the atomic path for this problem\n", worst, scale);
+        N.det_available = false;
+        N.det = false;
+        N.ldS = chol_padded(N.n_c + 1) > N.ldS_max ? N.ldS_max : chol_padded(N.n_c + 1);
+    }
+    return true;
+}
+
 bool normal_assemble(const DevProblem& dp, NormalBuffers& N, const EvalBuffers& op, const int* d_rowptr,
                      double lambda, cudaStream_t s, int* nlaunch)
 {
@@ -951,9 +1000,6 @@ bool normal_finish(const DevProblem& dp, NormalBuffers& N, const EvalBuffers& op
             assemble_reg_kernel<<<(dp.Ntri + 127) / 128, 128, 0, s>>>(dp, N, op.x, op.Jval, op.Jcol, d_rowptr, dp.m_tri0, dp.m_reg0, N.n_c);
             (*nlaunch)++;
         }
-        // THE collective of the algorithm: the reduced normal equations (with g' and the gradient as rows n_c, n_c+1),
-        // summed over the frame shards
-        if(comm_active() && !comm_allreduce_sum(N.S, (size_t)N.ldS * N.ldS, s)) return false;
         if(!normal_det_rhs(N, s, nlaunch)) return false;
         MB200_CUDA_CHECK(cudaGetLastError());
         return true;

@@ -45,6 +45,7 @@ struct NormalBuffers
     // ---- the atomics-free assembly (normal_det.cu): every entry of S is summed by ONE thread in a fixed order
     bool    det_available;   // the buffers below exist (MRCAL_B200_ATOMIC_ASSEMBLY=1 turns the path off)
     bool    det;          // in use for this assembly
+    bool    selfchecked;  // the one-time cross-check against the atomic path has run
     cudaStream_t s_side[2];               // forked streams of the Gram kernel's size classes (owned by the workspace)
     cudaEvent_t  ev_fork, ev_join[2];
     int     capA;         // most local columns (incl. the two gradient rows) an item may have in the A pool
@@ -62,6 +63,7 @@ struct NormalBuffers
     int     gwords, wwords, bwords;
     double* grp_Linv;     // [Ngroups][36] inverse of the Cholesky factor of D (lower)
     double* grp_h;        // [Ngroups][6]  inv(L_D) gf
+    double* S_packed;     // sharded solves: the lower-triangle tiles of S, each 64x64 contiguous: what is all-reduced
 
     __host__ __device__ int reduced_index(int c) const { return c < e0 ? c : c - (e1 - e0); }
     __host__ __device__ int state_index(int r) const { return r < e0 ? r : r + (e1 - e0); }
@@ -73,6 +75,8 @@ bool normal_prepare(const DevProblem& dp, NormalBuffers& N, const EvalBuffers& o
 bool normal_adopt_sizes(NormalBuffers& N);
 bool normal_finish(const DevProblem& dp, NormalBuffers& N, const EvalBuffers& op, const int* d_rowptr,
                    double lambda, cudaStream_t s, int* nlaunch);
+bool normal_selfcheck(const DevProblem& dp, NormalBuffers& N, const EvalBuffers& op, const int* d_rowptr,
+                      double lambda, cudaStream_t s, int* nlaunch);
 // S, g', g_full at the operating point `op` (needs its x and Jacobian). lambda: diagonal loading.
 // Updates N.n_c / N.ldS (one small device->host read)
 bool normal_assemble(const DevProblem& dp, NormalBuffers& N, const EvalBuffers& op, const int* d_rowptr,

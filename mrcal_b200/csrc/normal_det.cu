@@ -283,7 +283,7 @@ __device__ __forceinline__ void build_worklist(TileCommon& sm, const unsigned* r
 
 // One CTA per 64x64 tile of the lower triangle of S
 __global__ void __launch_bounds__(256, 2)
-schur_tiles_kernel(NormalBuffers N, double lambda, int n_c, int nblk, bool add_lambda)
+schur_tiles_kernel(NormalBuffers N, double lambda, int n_c, int nblk, bool add_lambda, double* __restrict__ packed)
 {
     extern __shared__ __align__(16) unsigned char dsm_raw[];
     TileCommon& sc = *reinterpret_cast<TileCommon*>(dsm_raw);
@@ -468,6 +468,18 @@ schur_tiles_kernel(NormalBuffers N, double lambda, int n_c, int nblk, bool add_l
         }
     }
 
+    ////////////////////////////// sharded solve: the raw tile goes to the tile-packed buffer (lower-triangle tiles only, each
+    // contiguous) that is all-reduced; unpack_tiles_kernel finishes the job on the sum
+    if(packed != nullptr)
+    {
+        double* dstt = packed + (size_t)(r * (r + 1) / 2 + c) * (TB * TB);
+#pragma unroll
+        for(int a = 0; a < 2; a++)
+#pragma unroll
+            for(int b = 0; b < 4; b++)
+                *reinterpret_cast<double2*>(&dstt[(wm * 16 + a * 8 + g) * TB + wn * 32 + b * 8 + 2 * t]) = make_double2(-acc[a][b][0], -acc[a][b][1]);
+        return;
+    }
     ////////////////////////////// write the tile. Rows >= n_c: the right-hand side (row n_c), the plain gradient (row n_c+1), padding
 #pragma unroll
     for(int a = 0; a < 2; a++)
@@ -492,14 +504,41 @@ schur_tiles_kernel(NormalBuffers N, double lambda, int n_c, int nblk, bool add_l
         }
 }
 
+// tile-packed (summed over the ranks) -> the lower triangle of S, with the diagonal loading and the padding rows
+__global__ void __launch_bounds__(256)
+unpack_tiles_kernel(NormalBuffers N, const double* __restrict__ packed, double lambda, int n_c, int nblk)
+{
+    int r, c;
+    {
+        const int q = (int)blockIdx.x;
+        r = (int)((sqrtf(8.f * q + 1.f) - 1.f) * 0.5f);
+        while(r * (r + 1) / 2 > q) r--;
+        while((r + 1) * (r + 2) / 2 <= q) r++;
+        c = q - r * (r + 1) / 2;
+    }
+    const double* src = packed + (size_t)blockIdx.x * (TB * TB);
+    for(int e = threadIdx.x; e < TB * TB; e += 256)
+    {
+        const int i = TB * r + e / TB, j = TB * c + (e & (TB - 1));
+        if(j > i) continue;
+        const double v = src[e];
+        double out;
+        if(i < n_c)           out = v + (i == j ? lambda : 0.);
+        else if(i <= n_c + 1) out = j < n_c ? v : (i == j ? 1. : 0.);
+        else                  out = i == j ? 1. : 0.;
+        N.S[(size_t)i * N.ldS + j] = out;
+    }
+}
+
 // The regularization rows (mrcal.c:5655-5955): each touches 1..3 shared unknowns, and the rows of one spline knot
 // (radial, tangential) touch the same two. One thread per knot / per unknown: the single owner of what it adds to.
 // Blocks whose unknowns no observation touches stay out of S (inactive_step_kernel solves them in closed form);
 // their gradient still goes to g_full.
+// every_rank: the sharded path adds these AFTER the cross-rank reduction, on every rank alike
 __global__ void reg_blocks_kernel(DevProblem P, NormalBuffers N, int n_c, const double* __restrict__ x,
-                                  const double* __restrict__ Jval, const int* __restrict__ Jcol)
+                                  const double* __restrict__ Jval, const int* __restrict__ Jcol, bool every_rank)
 {
-    if(!P.reg_owner) return;
+    if(!P.reg_owner && !every_rank) return;
     const int Ndist_rows   = (P.reg && P.opt_dist) ? P.Ncam_i * (P.Nintr - 4) : 0;
     const int Ncenter_rows = (P.reg && P.opt_core) ? P.Ncam_i * 2 : 0;
     const int Nunity_rows  = P.reg_unity ? 1 : 0;
@@ -619,7 +658,9 @@ bool normal_det_item_prepare(const DevProblem& dp, NormalBuffers& N, cudaStream_
     return true;
 }
 
-// groups -> tiles -> regularization -> (all-reduce by the caller) ; finish_rhs afterwards
+bool comm_allreduce_sum(double* d_buf, size_t count, cudaStream_t s);
+
+// groups -> tiles -> [cross-rank sum of the lower-triangle tiles] -> regularization
 bool normal_det_finish(const DevProblem& dp, NormalBuffers& N, const EvalBuffers& op, const int* d_rowptr,
                        double lambda, cudaStream_t s, int* nlaunch)
 {
@@ -633,19 +674,30 @@ bool normal_det_finish(const DevProblem& dp, NormalBuffers& N, const EvalBuffers
         configured[dev] = true;
     }
     const int nblk = N.ldS / TB;
+    const int ntiles = nblk * (nblk + 1) / 2;
     if(N.Ngroups > 0)
     {
         groups_panels_kernel<<<N.Ngroups, 256, 0, s>>>(N, lambda, N.n_c, nblk);
         (*nlaunch)++;
     }
-    schur_tiles_kernel<<<nblk * (nblk + 1) / 2, 256, kTileSmem, s>>>(N, lambda, N.n_c, nblk, dp.reg_owner);
+    const bool sharded = comm_active();
+    if(sharded && N.S_packed == nullptr) { set_error("internal error: sharded solve without the packed tile buffer"); return false; }
+    schur_tiles_kernel<<<ntiles, 256, kTileSmem, s>>>(N, lambda, N.n_c, nblk, true, sharded ? N.S_packed : nullptr);
     (*nlaunch)++;
+    if(sharded)
+    {
+        // THE collective of the algorithm: the reduced normal equations -- lower-triangle tiles only, with g' and the
+        // gradient as rows n_c, n_c+1 of the same tiles -- summed over the frame shards
+        if(!comm_allreduce_sum(N.S_packed, (size_t)ntiles * TB * TB, s)) return false;
+        unpack_tiles_kernel<<<ntiles, 256, 0, s>>>(N, N.S_packed, lambda, N.n_c, nblk);
+        (*nlaunch)++;
+    }
     const int Ndist_rows   = (dp.reg && dp.opt_dist) ? dp.Ncam_i * (dp.Nintr - 4) : 0;
     const int Ncenter_rows = (dp.reg && dp.opt_core) ? dp.Ncam_i * 2 : 0;
     const int Nreg_blocks = (N.splined ? Ndist_rows / 2 : Ndist_rows) + Ncenter_rows + (dp.reg_unity ? 1 : 0);
     if(Nreg_blocks > 0)
     {
-        reg_blocks_kernel<<<(Nreg_blocks + 127) / 128, 128, 0, s>>>(dp, N, N.n_c, op.x, op.Jval, op.Jcol);
+        reg_blocks_kernel<<<(Nreg_blocks + 127) / 128, 128, 0, s>>>(dp, N, N.n_c, op.x, op.Jval, op.Jcol, sharded);
         (*nlaunch)++;
     }
     (void)d_rowptr;

@@ -21,6 +21,7 @@ namespace mb200 {
 bool comm_active();                                                             // nccl.cu
 bool comm_allreduce_sum(double* d_buf, size_t count, cudaStream_t s);           // nccl.cu
 int  comm_rank();
+long comm_collective_count();
 // the per-rank partial sums of the Cauchy phase sit in slots [6..8] (eliminated range) and [9..10] (row sums): one call
 static bool comm_allreduce_partial(double* scal, cudaStream_t s) { return comm_allreduce_sum(scal + 6, 5, s); }
 
@@ -248,6 +249,8 @@ static bool build_workspace(mrcal_b200_problem* P)
              A.alloc(&N.grp_blkmask, (size_t)(N.Ngroups > 0 ? N.Ngroups : 1) * N.bwords, true) &&
              A.alloc(&N.grp_Linv, (size_t)(N.Ngroups > 0 ? N.Ngroups : 1) * 36, true) && A.alloc(&N.grp_h, (size_t)(N.Ngroups > 0 ? N.Ngroups : 1) * 6, true);
         if(!ok) return false;
+        // (always there: the communicator may be created after this workspace)
+        if(!A.alloc(&N.S_packed, (size_t)N.nblk_max * (N.nblk_max + 1) / 2 * kCholBlock * kCholBlock)) return false;
     }
     MB200_CUDA_CHECK(cudaEventCreateWithFlags(&N.ev_fork, cudaEventDisableTiming));
     for(int k = 0; k < 2; k++)
@@ -413,6 +416,7 @@ static bool dogleg_pass(mrcal_b200_problem* P, const mrcal_b200_solver_parameter
     };
     auto assemble = [&](int which) -> bool
     {
+        if(!N.selfchecked && !normal_selfcheck(P->dp, N, P->op[which], P->d_rowptr, *lambda, s, nl)) return false;
         const int a = T->mark();
         if(!normal_finish(P->dp, N, P->op[which], P->d_rowptr, *lambda, s, nl)) return false;
         T->spans[1].push_back({a, T->mark()});
@@ -585,6 +589,7 @@ bool solver_run(mrcal_b200_problem* P, const mrcal_b200_solver_parameters_t* par
     const Layout& L = P->L;
     cudaStream_t s = P->stream;
     const int launches0 = P->launches;
+    const long collectives0 = comm_collective_count();
 
     // the CSR row pointers are analytic; jv_kernel and the regularization assembly read them
     if(!problem_evaluate(P, P->cur, false, true)) return false;
@@ -627,6 +632,7 @@ bool solver_run(mrcal_b200_problem* P, const mrcal_b200_solver_parameters_t* par
     info.norm2_x_final = norm2;
     info.lambda_final = lambda;
     info.Nkernel_launches = P->launches - launches0;
+    info.Ncollectives = (int)(comm_collective_count() - collectives0);
     if(stats)
     {
         // mrcal.c:6607-6612. Sharded: the measurement count of the whole problem (regularization counted once)
