@@ -110,8 +110,10 @@ __device__ __forceinline__ int emit_intrinsics(double* __restrict__ jv, int* __r
     int n = 0;
     if(P.opt_core)
     {
-        jc[n] = i_var_intr + i_xy;     jv[n] = zero ? 0. : g_f * w * kScaleFocal;  n++;
-        jc[n] = i_var_intr + i_xy + 2; jv[n] = zero ? 0. : w * kScaleCenter;       n++;
+        if(jc) jc[n] = i_var_intr + i_xy;
+        jv[n] = zero ? 0. : g_f * w * kScaleFocal;  n++;
+        if(jc) jc[n] = i_var_intr + i_xy + 2;
+        jv[n] = zero ? 0. : w * kScaleCenter;       n++;
     }
     if(P.opt_dist)
     {
@@ -123,7 +125,7 @@ __device__ __forceinline__ int emit_intrinsics(double* __restrict__ jv, int* __r
 #pragma unroll
                 for(int ix = 0; ix < RUN; ix++)
                 {
-                    jc[n] = i_var_intr + ivar0s + iy * 2 * P.Nx + ix * 2 + i_xy;
+                    if(jc) jc[n] = i_var_intr + ivar0s + iy * 2 * P.Nx + ix * 2 + i_xy;
                     jv[n] = zero ? 0. : wx[ix] * wy[iy] * f_xy * w * kScaleDistortion;
                     n++;
                 }
@@ -134,7 +136,7 @@ __device__ __forceinline__ int emit_intrinsics(double* __restrict__ jv, int* __r
 #pragma unroll
             for(int i = 0; i < ND; i++)
             {
-                jc[n] = i_var_intr + P.Ncore_state + i;
+                if(jc) jc[n] = i_var_intr + P.Ncore_state + i;
                 jv[n] = zero ? 0. : ddist[i] * w * kScaleDistortion;
                 n++;
             }
@@ -157,9 +159,12 @@ eval_boards_kernel(DevProblem P, double* __restrict__ x, double* __restrict__ Jv
 {
     __shared__ ObsGeometry G;
     __shared__ double red[32];
-    // Jacobian staging: each thread (corner) deposits its two rows here, then the CTA streams the
-    // block out with fully coalesced stores (the rows of one observation are contiguous in J).
-    // Odd strides keep the per-thread deposits free of bank conflicts
+    __shared__ int s_ivar0[256];   // per corner: where its spline window starts (the only data-dependent column index)
+    // Jacobian staging: each thread (corner) deposits the VALUES of its two rows here -- 2*nnz_row contiguous
+    // doubles, which is also how they sit in J -- and hands them to the TMA: one bulk shared->global copy per
+    // corner (cp.async.bulk), no thread spends time on the stores. The column indices are not staged at all:
+    // they are a function of (corner, entry) and are written straight from registers, coalesced.
+    // The row stride is 2 (mod 4) doubles: 16-byte aligned for the bulk copy, 2-way bank conflicts at worst
     extern __shared__ __align__(16) double stage_v[];
 
     const int iobs   = blockIdx.x;
@@ -195,8 +200,10 @@ eval_boards_kernel(DevProblem P, double* __restrict__ x, double* __restrict__ Jv
     const int NWH         = P.W * P.H;
     const double wx2 = P.u_warp[0], wy2 = P.u_warp[1];
 
-    const int row2 = 2 * nnz_row, stride = row2 + 1;
-    int* stage_c = reinterpret_cast<int*>(stage_v + (size_t)blockDim.x * stride);
+    const int row2 = 2 * nnz_row;
+    int stride = row2;
+    while((stride & 3) != 2) stride++;
+    const int nI = P.nnz_row_intr;
 
     double sumsq = 0.;
     for(int ipt0 = 0; ipt0 < NWH; ipt0 += blockDim.x)
@@ -299,7 +306,7 @@ eval_boards_kernel(DevProblem P, double* __restrict__ x, double* __restrict__ Jv
             for(int i_xy = 0; i_xy < 2; i_xy++)
             {
                 double* jv = stage_v + (size_t)threadIdx.x * stride + i_xy * nnz_row;
-                int*    jc = stage_c + (size_t)threadIdx.x * stride + i_xy * nnz_row;
+                int*    jc = nullptr;
                 double g_f;
                 if constexpr(LensTraits<KIND>::SPLINED) g_f = upd[i_xy];
                 else                                    g_f = (q[i_xy] - intr[2 + i_xy]) / intr[i_xy];   // mrcal.c:1427-1431
@@ -307,37 +314,75 @@ eval_boards_kernel(DevProblem P, double* __restrict__ x, double* __restrict__ Jv
                 if(emit_cam)
                 {
 #pragma unroll
-                    for(int k = 0; k < 3; k++) { jc[n] = i_var_cam + k;     jv[n] = outlier ? 0. : dq_drc[i_xy][k] * w * kScaleRotCam;   n++; }
+                    for(int k = 0; k < 3; k++) { jv[n] = outlier ? 0. : dq_drc[i_xy][k] * w * kScaleRotCam;   n++; }
 #pragma unroll
-                    for(int k = 0; k < 3; k++) { jc[n] = i_var_cam + 3 + k; jv[n] = outlier ? 0. : dq_dp[i_xy][k] * w * kScaleTransCam;  n++; }
+                    for(int k = 0; k < 3; k++) { jv[n] = outlier ? 0. : dq_dp[i_xy][k] * w * kScaleTransCam;  n++; }
                 }
                 if(P.opt_frames)
                 {
 #pragma unroll
-                    for(int k = 0; k < 3; k++) { jc[n] = i_var_frame + k;     jv[n] = outlier ? 0. : dq_drf[i_xy][k] * w * kScaleRotFrame; n++; }
+                    for(int k = 0; k < 3; k++) { jv[n] = outlier ? 0. : dq_drf[i_xy][k] * w * kScaleRotFrame; n++; }
 #pragma unroll
-                    for(int k = 0; k < 3; k++) { jc[n] = i_var_frame + 3 + k; jv[n] = outlier ? 0. : G2[i_xy][k] * w * kScaleTransFrame;   n++; }
+                    for(int k = 0; k < 3; k++) { jv[n] = outlier ? 0. : G2[i_xy][k] * w * kScaleTransFrame;   n++; }
                 }
                 if(P.opt_warp)
                 {
 #pragma unroll
-                    for(int k = 0; k < 2; k++) { jc[n] = P.i_warp0 + k; jv[n] = outlier ? 0. : dq_dz[i_xy] * dz[k] * w * kScaleWarp; n++; }
+                    for(int k = 0; k < 2; k++) { jv[n] = outlier ? 0. : dq_dz[i_xy] * dz[k] * w * kScaleWarp; n++; }
                 }
+            }
+            s_ivar0[threadIdx.x] = ivar0s;
+            // this corner's 2 rows: one bulk copy, shared -> global, issued by the thread that wrote them. The fence makes
+            // the generic-proxy writes above visible to the async proxy that reads them
+            {
+                const size_t ifeat0 = (size_t)ipt;
+                double* gdst = Jval + (size_t)P.board_j0[iobs] + ifeat0 * row2;
+                const unsigned ssrc = (unsigned)__cvta_generic_to_shared(stage_v + (size_t)threadIdx.x * stride);
+                asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");
+                asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;\n"
+                             ::"l"(gdst), "r"(ssrc), "r"(row2 * 8) : "memory");
+                asm volatile("cp.async.bulk.commit_group;\n" ::: "memory");
             }
         }
       }
       if constexpr(WITH_J)
       {
-        // stream this chunk of corners out: entries [ipt0*row2, (ipt0+nhere)*row2) of the observation's block
+        // the column indices of this chunk of corners: entries [ipt0*row2, (ipt0+nhere)*row2) of the observation's block
         __syncthreads();
         const int nhere = min((int)blockDim.x, NWH - ipt0);
         const size_t gbase = (size_t)P.board_j0[iobs] + (size_t)ipt0 * row2;
+        const int ncore = P.opt_core ? 2 : 0;
         for(int g = threadIdx.x; g < nhere * row2; g += blockDim.x)
         {
             const int t = g / row2, e = g - t * row2;
-            Jval[gbase + g] = stage_v[(size_t)t * stride + e];
-            Jcol[gbase + g] = stage_c[(size_t)t * stride + e];
+            const int i_xy = e >= nnz_row ? 1 : 0, k = e - i_xy * nnz_row;
+            int col;
+            if(k < nI)
+            {
+                if(k < ncore) col = i_var_intr + i_xy + 2 * k;
+                else if constexpr(LensTraits<KIND>::SPLINED)
+                {
+                    constexpr int RUN = LensTraits<KIND>::RUN;
+                    const int kk = k - ncore, iy = kk / RUN, ix = kk - iy * RUN;
+                    col = i_var_intr + s_ivar0[t] + iy * 2 * P.Nx + ix * 2 + i_xy;
+                }
+                else col = i_var_intr + P.Ncore_state + (k - ncore);
+            }
+            else
+            {
+                int kk = k - nI;
+                if(emit_cam && kk < 6) col = i_var_cam + kk;
+                else
+                {
+                    if(emit_cam) kk -= 6;
+                    if(P.opt_frames && kk < 6) col = i_var_frame + kk;
+                    else { if(P.opt_frames) kk -= 6; col = P.i_warp0 + kk; }
+                }
+            }
+            Jcol[gbase + g] = col;
         }
+        // the staging buffer is reused by the next chunk of corners: wait until the TMA has READ it
+        asm volatile("cp.async.bulk.wait_group.read 0;\n" ::: "memory");
         __syncthreads();
       }
     }
@@ -724,7 +769,9 @@ static bool launch_kind(const DevProblem& dp, const EvalBuffers& out, bool with_
         {
             // widest row: extrinsics present
             const int row2 = 2 * (dp.nnz_row_intr + (dp.opt_extr ? 6 : 0) + dp.nnz_row_board_geom);
-            const size_t smem = (size_t)threads * (row2 + 1) * (sizeof(double) + sizeof(int)) + 16;
+            int stride = row2;
+            while((stride & 3) != 2) stride++;
+            const size_t smem = (size_t)threads * stride * sizeof(double) + 16;
             // cudaFuncSetAttribute is per device: one flag per (device, lens kind)
             static bool configured[kMaxDevices][LENS_NKINDS] = {};
             int dev = 0;
