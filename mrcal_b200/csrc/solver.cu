@@ -322,10 +322,10 @@ struct PhaseTimer
 //   0..8   dots of g = J'x by range (shared head | eliminated | shared tail): a.a, -, -
 //   9,10   x.(J g), |J g|^2
 //   11..19 dots of (gn, g) by range: gn.gn, g.g, gn.g
-//   20,21  x.(J step), |J step|^2        22  |x|^2 at the trial point
-//   32 cg  33 cn  34 update_lensq  35 edge  36 cauchy_lensq  37 gn_lensq  38 kc
+//   22     |x|^2 at the trial point
+//   32 cg  33 cn  34 update_lensq  35 edge  36 cauchy_lensq  37 gn_lensq  38 kc  39 expected improvement
 // ictl[]: 0 need_gn (the factorization kernels run only if set)  1 zero gradient
-enum { SC_CG = 32, SC_CN, SC_UPDATE, SC_EDGE, SC_CAUCHY2, SC_GN2, SC_KC, SC_N = 48 };
+enum { SC_CG = 32, SC_CN, SC_UPDATE, SC_EDGE, SC_CAUCHY2, SC_GN2, SC_KC, SC_EXPECTED, SC_N = 48 };
 
 __global__ void cauchy_decide_kernel(double* __restrict__ scal, int* __restrict__ ictl, double trustregion)
 {
@@ -347,12 +347,17 @@ __global__ void cauchy_decide_kernel(double* __restrict__ scal, int* __restrict_
     ictl[0] = c2 >= trustregion * trustregion ? 0 : 1;   // Cauchy point inside the trust region: go on to Gauss-Newton
 }
 
-// Cauchy step to the edge | Gauss-Newton step | dogleg to the edge (libdogleg's takeStepFrom())
-__global__ void select_step_kernel(double* __restrict__ scal, const int* __restrict__ ictl, double trustregion)
+// Cauchy step to the edge | Gauss-Newton step | dogleg to the edge (libdogleg's takeStepFrom()), and the improvement
+// the quadratic model expects of the step s = cg g + cn gn:  |x|^2 - |x + J s|^2 = -2 x.(J s) - |J s|^2. libdogleg gets it
+// from an explicit product J s; here it follows from scalars already on the device, because the Gauss-Newton step
+// solves (JtJ + lambda I) gn = -g:   x.(J s) = g.s ;  (J g).(J gn) = -g.g - lambda g.gn ;  |J gn|^2 = -g.gn - lambda gn.gn
+__global__ void select_step_kernel(double* __restrict__ scal, const int* __restrict__ ictl, double trustregion, double lambda)
 {
     if(threadIdx.x != 0 || blockIdx.x != 0) return;
     const double kc = scal[SC_KC], a2 = scal[SC_CAUCHY2];
     const double tr2 = trustregion * trustregion;
+    const double g2 = scal[0] + scal[3] + scal[6], Jg2 = scal[10];
+    double gn2 = 0., g_dot_gn = 0.;
     double cg, cn, upd, edge;
     if(ictl[1]) { cg = 0.; cn = 0.; upd = 0.; edge = 0.; }
     else if(a2 >= tr2)
@@ -361,8 +366,8 @@ __global__ void select_step_kernel(double* __restrict__ scal, const int* __restr
     }
     else
     {
-        const double gn2 = scal[11] + scal[14] + scal[17];
-        const double g_dot_gn = scal[13] + scal[16] + scal[19];
+        gn2 = scal[11] + scal[14] + scal[17];
+        g_dot_gn = scal[13] + scal[16] + scal[19];
         scal[SC_GN2] = gn2;
         if(gn2 <= tr2) { cg = 0.; cn = 1.; upd = gn2; edge = 0.; }
         else
@@ -377,6 +382,9 @@ __global__ void select_step_kernel(double* __restrict__ scal, const int* __restr
         }
     }
     scal[SC_CG] = cg; scal[SC_CN] = cn; scal[SC_UPDATE] = upd; scal[SC_EDGE] = edge;
+    const double x_Js = cg * g2 + cn * g_dot_gn;
+    const double Js2 = cg * cg * Jg2 + 2. * cg * cn * (-g2 - lambda * g_dot_gn) + cn * cn * (-g_dot_gn - lambda * gn2);
+    scal[SC_EXPECTED] = -2. * x_Js - Js2;
 }
 
 // step = cg g + cn gn ; p_new = p + step, with cg, cn read on the device
@@ -501,15 +509,13 @@ static bool dogleg_pass(mrcal_b200_problem* P, const mrcal_b200_solver_parameter
                 factored_now = true;
             }
             // ---- take the step
-            select_step_kernel<<<1, 32, 0, s>>>(ws->scal, ws->ictl, trustregion);
+            select_step_kernel<<<1, 32, 0, s>>>(ws->scal, ws->ictl, trustregion, *lambda);
             combine_step_dev_kernel<<<(Nstate + 255) / 256, 256, 0, s>>>(Nstate, ws->scal, N.g_full, ws->step_gn, cur.p, ws->step, nxt.p);
-            MB200_CUDA_CHECK(cudaMemsetAsync(ws->scal + 20, 0, 2 * sizeof(double), s));
-            jv_kernel<<<148 * 16, 256, 0, s>>>(P->d_rowptr, cur.Jcol, cur.Jval, ws->step, cur.x, Nrows_mine, ws->scal + 20);
-            *nl += 3;
+            *nl += 2;
             if(!evaluate(1 - P->cur)) return false;
             sizes_are_cur = false;
             MB200_CUDA_CHECK(cudaMemcpyAsync(ws->scal + 22, nxt.norm2, sizeof(double), cudaMemcpyDeviceToDevice, s));
-            if(comm_active() && !comm_allreduce_sum(ws->scal + 20, 3, s)) return false;
+            if(comm_active() && !comm_allreduce_sum(ws->scal + 22, 1, s)) return false;
             if(!read_back()) return false;
 
             const bool need_gn = ws->h_ictl[0] != 0, zero_grad = ws->h_ictl[1] != 0;
@@ -552,8 +558,8 @@ static bool dogleg_pass(mrcal_b200_problem* P, const mrcal_b200_solver_parameter
                 done = true;
                 break;
             }
-            // |x|^2 - |x + J step|^2
-            const double expected = -ws->h_scal[21] - 2. * ws->h_scal[20];
+            // |x|^2 - |x + J step|^2, as the quadratic model has it
+            const double expected = ws->h_scal[SC_EXPECTED];
             const double norm2_new = ws->h_scal[22];
             const double observed = norm2_x - norm2_new;
             const double rho = observed / expected;
