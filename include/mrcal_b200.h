@@ -562,6 +562,11 @@ bool mrcal_b200_factorization_solve_sys(mrcal_b200_factorization_t* factorizatio
 // Reciprocal condition-number estimate from the diagonal of the factor, as
 // cholmod_rcond() defines it (mrcal-pywrap.c:580-593)
 double mrcal_b200_factorization_rcond(mrcal_b200_factorization_t* factorization);
+// The same object for the calibration problem the LAST mrcal_optimizer_callback() call evaluated, built from the
+// problem's structure (per-frame/point blocks eliminated, dense factor of the reduced camera system only) instead of a
+// dense Nstate x Nstate matrix: what mrcal-pywrap.c:1980-1988 does with the Jt it just filled. Takes over the device
+// problem that call left behind. NULL if there is none or if JtJ is not positive definite (see mrcal_b200_last_error())
+mrcal_b200_factorization_t* mrcal_b200_factorization_create_from_last_callback(void);
 
 // A sparse Jacobian held on the GPU, for the consumers downstream of the solve (the reference's
 // projection-uncertainty code, mrcal/model_analysis.py:716-870). J is CSR, shape (Nrows, Ncols), given as the

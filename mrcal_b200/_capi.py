@@ -113,6 +113,7 @@ EXPORTED_SYMBOLS = (
     "mrcal_b200_problem_set_sharding",
     "mrcal_b200_factorization_create", "mrcal_b200_factorization_destroy",
     "mrcal_b200_factorization_solve_xt_JtJ_bt", "mrcal_b200_factorization_solve_sys", "mrcal_b200_factorization_rcond",
+    "mrcal_b200_factorization_create_from_last_callback",
     "mrcal_b200_csr_create", "mrcal_b200_csr_destroy", "mrcal_b200_csr_Jt_x", "mrcal_b200_csr_A_Jt_J_At",
 )
 
@@ -147,6 +148,7 @@ lib.mrcal_b200_problem_create_triangulated.restype = C.c_void_p
 lib.mrcal_b200_problem_destroy.restype = None
 lib.mrcal_b200_problem_time_callback.restype = C.c_double
 lib.mrcal_b200_problem_triangulated_outliers.restype = C.c_int
+lib.mrcal_b200_factorization_create_from_last_callback.restype = C.c_void_p
 lib.mrcal_b200_csr_create.restype = C.c_void_p
 lib.mrcal_b200_csr_destroy.restype = None
 lib.mrcal_b200_csr_Jt_x.restype = C.c_bool

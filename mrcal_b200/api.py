@@ -14,6 +14,7 @@ Everything numeric happens in libmrcal_b200.so (CUDA, sm_100a). This module only
 marshals arguments, the way mrcal-pywrap.c does for the reference.
 """
 import ctypes as C
+import os
 
 import numpy as np
 import scipy.sparse
@@ -357,6 +358,14 @@ def optimizer_callback(no_jacobian=False, no_factorization=False, **kwargs):
         P, Ii, X = keep
         J = scipy.sparse.csr_matrix((X, Ii, P), shape=(Nmeas, Nstate))
         if not no_factorization:
+            # the problem's own structure first (frames/points eliminated, dense factor of the reduced system only);
+            # the dense Nstate x Nstate object only where that does not apply
+            if not os.environ.get("MRCAL_B200_DENSE_FACTORIZATION"):
+                h = lib.mrcal_b200_factorization_create_from_last_callback()   # NULL comes back as None
+                if h:
+                    return b, x, J, CHOLMOD_factorization._from_handle(h, J.shape)
+                if "not positive definite" in _capi.last_error():
+                    return b, x, J, None   # not an error: mrcal-pywrap.c:1981-1988
             try:
                 factorization = CHOLMOD_factorization(J)
             except RuntimeError as e:
@@ -575,6 +584,13 @@ class CHOLMOD_factorization:
         if not self._h:
             raise RuntimeError("CHOLMOD_factorization: " + _capi.last_error())
         self._h = C.c_void_p(self._h)
+
+    @classmethod
+    def _from_handle(cls, h, shape):
+        self = cls.__new__(cls)
+        self.shape = shape
+        self._h = C.c_void_p(h)
+        return self
 
     def __del__(self):
         if getattr(self, "_h", None):

@@ -80,6 +80,17 @@ mrcal_b200_problem_t* acquire_problem(const double* intrinsics, const mrcal_pose
 
 }  // namespace
 
+namespace mb200 {
+// factorization_schur.cu takes over the problem the last callback left in the cache
+mrcal_b200_problem_t* capi_steal_cached_problem()
+{
+    std::lock_guard<std::mutex> lock(g_cache.mtx);
+    mrcal_b200_problem_t* P = g_cache.p;
+    g_cache.p = nullptr;
+    return P;
+}
+}  // namespace mb200
+
 extern "C" bool mrcal_optimizer_callback(double* b_packed, int buffer_size_b_packed,
                                          double* x, int buffer_size_x,
                                          mrcal_b200_sparse_t* Jt,

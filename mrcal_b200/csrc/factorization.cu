@@ -6,20 +6,7 @@
 // J is arbitrary here (the object is also constructible from user matrices), so
 // no block structure is assumed: JtJ is accumulated densely and factored with
 // the same DMMA Cholesky the solver uses.
-#include "chol.h"
-#include "problem_impl.h"
-
-struct mrcal_b200_factorization
-{
-    mb200::DeviceArena arena;
-    cudaStream_t stream = nullptr;
-    int n = 0, npad = 0;
-    double* H = nullptr;      // npad x npad, lower: L after factorization
-    double* invL = nullptr;
-    int*    info = nullptr;
-    double* minmax = nullptr;
-    mb200::CholScratch chol;  // this object's own flags of the persistent kernels
-};
+#include "solver_internal.h"
 
 namespace mb200 {
 
@@ -104,6 +91,7 @@ mrcal_b200_factorization_create(const int32_t* Jrowptr, const int32_t* Jcolidx, 
 extern "C" void mrcal_b200_factorization_destroy(mrcal_b200_factorization_t* F)
 {
     if(F == nullptr) return;
+    if(F->P != nullptr) { schur_factorization_release(F); delete F; return; }
     if(F->stream) { cudaStreamSynchronize(F->stream); }
     chol_forget_graphs(F->H);
     chol_scratch_destroy(&F->chol);
@@ -124,6 +112,7 @@ extern "C" bool mrcal_b200_factorization_solve_xt_JtJ_bt(mrcal_b200_factorizatio
 extern "C" bool mrcal_b200_factorization_solve_sys(mrcal_b200_factorization_t* F, double* out, const double* bt, int Nrhs, int sys)
 {
     if(Nrhs <= 0) return true;
+    if(F->P != nullptr) return schur_factorization_solve(F, out, bt, Nrhs, sys);
     int parts;
     switch(sys)
     {
@@ -154,6 +143,7 @@ extern "C" bool mrcal_b200_factorization_solve_sys(mrcal_b200_factorization_t* F
 extern "C" double mrcal_b200_factorization_rcond(mrcal_b200_factorization_t* F)
 {
     // For an LL' factorization cholmod_rcond() returns (min diag(L) / max diag(L))^2
+    if(F->P != nullptr) return schur_factorization_rcond(F);
     double mm[2] = {0., 0.};
     if(!chol_diag_minmax(F->H, F->npad, F->n, F->minmax, F->stream)) return -1.;
     if(cudaMemcpyAsync(mm, F->minmax, sizeof(mm), cudaMemcpyDeviceToHost, F->stream) != cudaSuccess ||

@@ -12,9 +12,7 @@
 #include <algorithm>
 #include <cmath>
 
-#include "chol.h"
-#include "normal.h"
-#include "problem_impl.h"
+#include "solver_internal.h"
 
 namespace mb200 {
 
@@ -25,38 +23,8 @@ long comm_collective_count();
 // the per-rank partial sums of the Cauchy phase sit in slots [6..8] (eliminated range) and [9..10] (row sums): one call
 static bool comm_allreduce_partial(double* scal, cudaStream_t s) { return comm_allreduce_sum(scal + 6, 5, s); }
 
-struct SolverWorkspace
-{
-    DeviceArena arena;
-    NormalBuffers N{};
-    double* invL = nullptr;
-    double* rhs = nullptr;        // [ldS] compact solution
-    double* ds_r = nullptr;       // [n_r] the same in reduced numbering
-    double* step_gn = nullptr;    // [Nstate]
-    double* step = nullptr;       // [Nstate]
-    double* scal = nullptr;       // [16] device scalars
-    double* h_scal = nullptr;     // pinned mirror
-    int*    h_info = nullptr;     // pinned
-    int*    ictl = nullptr;       // [8] device control flags of the step logic
-    int*    h_ictl = nullptr;     // pinned
-    CholScratch chol;             // this workspace's own flags of the persistent factorization kernels
-    std::vector<cudaEvent_t> ev;
-    ~SolverWorkspace()
-    {
-        chol_forget_graphs(N.S);
-        for(int k = 0; k < 2; k++)
-        {
-            if(N.s_side[k]) cudaStreamDestroy(N.s_side[k]);
-            if(N.ev_join[k]) cudaEventDestroy(N.ev_join[k]);
-        }
-        if(N.ev_fork) cudaEventDestroy(N.ev_fork);
-        if(h_scal) cudaFreeHost(h_scal);
-        if(h_info) cudaFreeHost(h_info);
-        chol_scratch_destroy(&chol);
-        for(auto e : ev) cudaEventDestroy(e);
-    }
-};
 static void delete_ws(SolverWorkspace* w) { delete w; }
+static bool build_workspace(mrcal_b200_problem* P);
 
 ////////////////////////////////////////////////////////////////////////////////
 // small vector kernels
@@ -172,6 +140,7 @@ __global__ void count_negative_kernel(const double* __restrict__ pool, long n, i
 ////////////////////////////////////////////////////////////////////////////////
 // workspace
 ////////////////////////////////////////////////////////////////////////////////
+bool solver_build_workspace(mrcal_b200_problem* P) { return build_workspace(P); }
 static bool build_workspace(mrcal_b200_problem* P)
 {
     if(P->ws) return true;

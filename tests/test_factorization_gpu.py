@@ -103,3 +103,63 @@ def test_solve_systems():
         F.solve_xt_JtJ_bt(bt, sys="LL")
     # a single right-hand side takes the graph path
     assert np.allclose(F.solve_xt_JtJ_bt(bt[0], sys="L"), np.linalg.solve(L, bt[0]), **tol)
+
+
+@pytest.mark.parametrize("lensmodel,Ncameras,Npoints", [
+    ("LENSMODEL_OPENCV4", 2, 0),
+    ("LENSMODEL_SPLINED_STEREOGRAPHIC_order=3_Nx=11_Ny=8_fov_x_deg=150", 3, 0),   # most knots uncoupled: the L_I part
+    ("LENSMODEL_OPENCV8", 3, 9),                                                  # point groups next to frame groups
+])
+def test_structured_factorization_of_a_problem(lensmodel, Ncameras, Npoints):
+    """optimizer_callback()'s factorization is built from the problem's structure (factorization_schur.cu); it must
+    agree with the dense factorization of the same J for every system, up to its own (documented) permutation."""
+    from mrcal_b200 import synthetic
+    kw, _ = synthetic.make_problem(lensmodel=lensmodel, Ncameras=Ncameras, Nframes=8, W=6, H=5, seed=6, pixel_noise=0.2,
+                                   Npoints=Npoints, which="some" if Npoints else "all")
+    b, x, J, F = mrcal_b200.optimizer_callback(**kw)
+    assert F is not None
+    Fd = mrcal_b200.CHOLMOD_factorization(J)          # dense, P = I
+    JtJ = (J.T @ J).toarray()
+    rng = np.random.default_rng(0)
+    bt = rng.normal(size=(5, J.shape[1]))
+    tol = dict(rtol=0, atol=1e-8 * np.abs(np.linalg.solve(JtJ, bt.T)).max())
+    xA = F.solve_xt_JtJ_bt(bt)
+    assert np.allclose(xA, Fd.solve_xt_JtJ_bt(bt), **tol)
+    assert np.allclose(xA, np.linalg.solve(JtJ, bt.T).T, **tol)
+    assert np.allclose(F.solve_xt_JtJ_bt(bt[0]), xA[0], **tol)
+    # P is a permutation, Pt undoes it
+    Pb = F.solve_xt_JtJ_bt(bt, sys="P")
+    assert np.allclose(np.sort(Pb, axis=-1), np.sort(bt, axis=-1))
+    assert np.array_equal(F.solve_xt_JtJ_bt(Pb, sys="Pt"), bt)
+    assert np.array_equal(F.solve_xt_JtJ_bt(bt, sys="D"), bt)
+    # L is lower triangular with L L' = P JtJ P': recover it column by column from solves with unit vectors
+    n = J.shape[1]
+    I = np.eye(n)
+    Linv = F.solve_xt_JtJ_bt(I, sys="L").T          # column j = inv(L) e_j
+    L = np.linalg.inv(Linv)
+    assert np.abs(np.triu(L, 1)).max() <= 1e-9 * np.abs(L).max()
+    Pm = F.solve_xt_JtJ_bt(I, sys="P").T             # P as a matrix: P e_j in column j
+    assert np.allclose(L @ L.T, Pm @ JtJ @ Pm.T, rtol=0, atol=1e-9 * np.abs(JtJ).max())
+    assert np.allclose(F.solve_xt_JtJ_bt(bt, sys="Lt"), np.linalg.solve(L.T, bt.T).T, rtol=0, atol=1e-8 * np.abs(bt).max() / np.abs(np.diag(L)).min())
+    assert np.allclose(F.solve_xt_JtJ_bt(F.solve_xt_JtJ_bt(F.solve_xt_JtJ_bt(Pb, sys="L"), sys="Lt"), sys="Pt"), xA, **tol)
+    assert np.allclose(F.solve_xt_JtJ_bt(Pb, sys="LDLt"), F.solve_xt_JtJ_bt(xA, sys="P"), **tol)
+    # the chain the reference's uncertainty code runs (mrcal/model_analysis.py:837-841)
+    A2 = F.solve_xt_JtJ_bt(Pb, sys="L")
+    A3 = F.solve_xt_JtJ_bt(A2, sys="D")
+    assert np.allclose(A2 @ A3.T, bt @ np.linalg.solve(JtJ, bt.T), rtol=1e-8, atol=1e-12)
+    # rcond as cholmod_rcond defines it for LL': (min diag / max diag)^2 of THIS factor
+    d = np.abs(np.diag(L))
+    assert abs(F.rcond() - (d.min() / d.max()) ** 2) <= 1e-6 * (d.min() / d.max()) ** 2
+
+
+def test_structured_factorization_at_config3():
+    """BASELINE config 3 (Nstate 7220): the factorization optimizer_callback() returns by default, many right-hand sides."""
+    from mrcal_b200 import synthetic
+    kw, _ = synthetic.baseline_config(3, pixel_noise=0.3)
+    b, x, J, F = mrcal_b200.optimizer_callback(**kw)
+    assert F is not None
+    rng = np.random.default_rng(1)
+    bt = rng.normal(size=(64, J.shape[1]))
+    X = F.solve_xt_JtJ_bt(bt)
+    R = (J.T @ (J @ X.T)).T - bt
+    assert np.abs(R).max() <= 1e-8 * np.abs(bt).max()
