@@ -758,9 +758,9 @@ __global__ void fill_rowptr_kernel(DevProblem P, bool splined, int nnz_total, in
 }
 
 template <int KIND>
-static bool launch_kind(const DevProblem& dp, const EvalBuffers& out, bool with_j, cudaStream_t stream, int* nlaunch)
+static bool launch_kind(const DevProblem& dp, const EvalBuffers& out, bool with_j, cudaStream_t stream, int* nlaunch, bool boards)
 {
-    if(dp.Nobs_board > 0)
+    if(dp.Nobs_board > 0 && boards)
     {
         int threads = ((dp.W * dp.H + 31) / 32) * 32;
         if(threads > 256) threads = 256;
@@ -814,27 +814,32 @@ bool launch_unpack_state(const DevProblem& dp, const double* b_packed, cudaStrea
     return true;
 }
 
+// boards = false: everything but the board observations (the fused evaluation of fused_eval.cu does those, and has
+// already unpacked the state and started |x|^2)
 bool launch_evaluate(const DevProblem& dp, const EvalBuffers& out, bool with_jacobian,
-                     int* Jrowptr, cudaStream_t stream, int* nlaunch)
+                     int* Jrowptr, cudaStream_t stream, int* nlaunch, bool boards)
 {
     int dummy = 0;
     if(nlaunch == nullptr) nlaunch = &dummy;
-    MB200_CUDA_CHECK(cudaMemsetAsync(out.norm2, 0, sizeof(double), stream));
-    if(!launch_unpack_state(dp, out.p, stream, nlaunch)) return false;
+    if(boards)
+    {
+        MB200_CUDA_CHECK(cudaMemsetAsync(out.norm2, 0, sizeof(double), stream));
+        if(!launch_unpack_state(dp, out.p, stream, nlaunch)) return false;
+    }
     switch(dp.lens_kind)
     {
-    case LENS_PINHOLE:       if(!launch_kind<LENS_PINHOLE>(dp, out, with_jacobian, stream, nlaunch)) return false; break;
-    case LENS_STEREOGRAPHIC: if(!launch_kind<LENS_STEREOGRAPHIC>(dp, out, with_jacobian, stream, nlaunch)) return false; break;
-    case LENS_LONLAT:        if(!launch_kind<LENS_LONLAT>(dp, out, with_jacobian, stream, nlaunch)) return false; break;
-    case LENS_LATLON:        if(!launch_kind<LENS_LATLON>(dp, out, with_jacobian, stream, nlaunch)) return false; break;
-    case LENS_OPENCV4:       if(!launch_kind<LENS_OPENCV4>(dp, out, with_jacobian, stream, nlaunch)) return false; break;
-    case LENS_OPENCV5:       if(!launch_kind<LENS_OPENCV5>(dp, out, with_jacobian, stream, nlaunch)) return false; break;
-    case LENS_OPENCV8:       if(!launch_kind<LENS_OPENCV8>(dp, out, with_jacobian, stream, nlaunch)) return false; break;
-    case LENS_OPENCV12:      if(!launch_kind<LENS_OPENCV12>(dp, out, with_jacobian, stream, nlaunch)) return false; break;
-    case LENS_SPLINED3:      if(!launch_kind<LENS_SPLINED3>(dp, out, with_jacobian, stream, nlaunch)) return false; break;
-    case LENS_SPLINED2:      if(!launch_kind<LENS_SPLINED2>(dp, out, with_jacobian, stream, nlaunch)) return false; break;
-    case LENS_CAHVOR:        if(!launch_kind<LENS_CAHVOR>(dp, out, with_jacobian, stream, nlaunch)) return false; break;
-    case LENS_CAHVORE:       if(!launch_kind<LENS_CAHVORE>(dp, out, with_jacobian, stream, nlaunch)) return false; break;
+    case LENS_PINHOLE:       if(!launch_kind<LENS_PINHOLE>(dp, out, with_jacobian, stream, nlaunch, boards)) return false; break;
+    case LENS_STEREOGRAPHIC: if(!launch_kind<LENS_STEREOGRAPHIC>(dp, out, with_jacobian, stream, nlaunch, boards)) return false; break;
+    case LENS_LONLAT:        if(!launch_kind<LENS_LONLAT>(dp, out, with_jacobian, stream, nlaunch, boards)) return false; break;
+    case LENS_LATLON:        if(!launch_kind<LENS_LATLON>(dp, out, with_jacobian, stream, nlaunch, boards)) return false; break;
+    case LENS_OPENCV4:       if(!launch_kind<LENS_OPENCV4>(dp, out, with_jacobian, stream, nlaunch, boards)) return false; break;
+    case LENS_OPENCV5:       if(!launch_kind<LENS_OPENCV5>(dp, out, with_jacobian, stream, nlaunch, boards)) return false; break;
+    case LENS_OPENCV8:       if(!launch_kind<LENS_OPENCV8>(dp, out, with_jacobian, stream, nlaunch, boards)) return false; break;
+    case LENS_OPENCV12:      if(!launch_kind<LENS_OPENCV12>(dp, out, with_jacobian, stream, nlaunch, boards)) return false; break;
+    case LENS_SPLINED3:      if(!launch_kind<LENS_SPLINED3>(dp, out, with_jacobian, stream, nlaunch, boards)) return false; break;
+    case LENS_SPLINED2:      if(!launch_kind<LENS_SPLINED2>(dp, out, with_jacobian, stream, nlaunch, boards)) return false; break;
+    case LENS_CAHVOR:        if(!launch_kind<LENS_CAHVOR>(dp, out, with_jacobian, stream, nlaunch, boards)) return false; break;
+    case LENS_CAHVORE:       if(!launch_kind<LENS_CAHVORE>(dp, out, with_jacobian, stream, nlaunch, boards)) return false; break;
     default: set_error("lens model kind %d has no CUDA implementation", dp.lens_kind); return false;
     }
     if(dp.Ntri > 0)

@@ -37,11 +37,11 @@ bool comm_allreduce_max_int(int* d_buf, size_t count, cudaStream_t s);
 // Pass 1, one CTA per work item: which shared columns does the item touch? Writes the item's column
 // list (reduced numbering, increasing) and marks those unknowns active.
 __global__ void __launch_bounds__(256)
-item_columns_kernel(DevProblem P, NormalBuffers N, const int* __restrict__ Jcol)
+item_columns_kernel(DevProblem P, NormalBuffers N, const int* __restrict__ Jcol, int w0)
 {
     extern __shared__ __align__(16) double dsm[];
     __shared__ int s_scan[256];
-    const int w = blockIdx.x, tid = threadIdx.x;
+    const int w = blockIdx.x + w0, tid = threadIdx.x;
     const ItemDesc d = describe_item(P, w, N.Nframe_groups);
     const int ncam = d.cam0 >= 0 ? 6 : 0, nwarp = d.warp0 >= 0 ? 2 : 0;
     short* lmap = reinterpret_cast<short*>(dsm);   // [clen]
@@ -318,17 +318,17 @@ constexpr int kDmmaClassTiles[3] = {7, 17, 27};
 template <int kDmmaMaxTiles, int TMIN, int TMAX, bool DET>
 __global__ void __launch_bounds__(256)
 assemble_items_dmma_kernel(DevProblem P, NormalBuffers N, int ldD, const double* __restrict__ x,
-                           const double* __restrict__ Jval, const int* __restrict__ Jcol)
+                           const double* __restrict__ Jval, const int* __restrict__ Jcol, int w0)
 {
     extern __shared__ __align__(16) double dsm[];
     __shared__ unsigned char s_ti[kDmmaMaxTiles * 8], s_tj[kDmmaMaxTiles * 8];
     {
         // this instantiation handles the items whose tile count T is in (TMIN, TMAX]
-        const int T_ = (N.wi_nsh[blockIdx.x] + describe_item(P, blockIdx.x, N.Nframe_groups).nelim + 1 + 7) >> 3;
+        const int T_ = (N.wi_nsh[blockIdx.x + w0] + describe_item(P, blockIdx.x + w0, N.Nframe_groups).nelim + 1 + 7) >> 3;
         if(T_ <= TMIN || T_ > TMAX) return;
     }
 
-    const int w = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int w = blockIdx.x + w0, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int g = lane >> 2, t = lane & 3;
     const ItemDesc d = describe_item(P, w, N.Nframe_groups);
     const int ncam = d.cam0 >= 0 ? 6 : 0, nwarp = d.warp0 >= 0 ? 2 : 0;
@@ -834,8 +834,10 @@ static bool configure_kernels()
 
 template <bool DET>
 static bool launch_gram_dmma(const DevProblem& dp, NormalBuffers& N, const EvalBuffers& op, int Nwi, int max_ntot,
-                             size_t lmap_bytes, size_t ccol_bytes, cudaStream_t s, int* nlaunch)
+                             size_t lmap_bytes, size_t ccol_bytes, cudaStream_t s, int* nlaunch, int w0 = 0)
 {
+    Nwi -= w0;
+    if(Nwi <= 0) return true;
     // the tensor-pipe kernel: D chunk [32][ldD], ldD = 4 (mod 16) for conflict-free fragment loads
     const int ncols_pad = ((max_ntot + 1 + 7) / 8) * 8;
     const int Tmax = ncols_pad / 8;
@@ -852,20 +854,20 @@ static bool launch_gram_dmma(const DevProblem& dp, NormalBuffers& N, const EvalB
     }
     {
         const int T0 = Tmax < kDmmaClassT[0] ? Tmax : kDmmaClassT[0];
-        assemble_items_dmma_kernel<kDmmaClassTiles[0], 0, kDmmaClassT[0], DET><<<Nwi, 256, smem_for(T0), s>>>(dp, N, ld_for(T0), op.x, op.Jval, op.Jcol);
+        assemble_items_dmma_kernel<kDmmaClassTiles[0], 0, kDmmaClassT[0], DET><<<Nwi, 256, smem_for(T0), s>>>(dp, N, ld_for(T0), op.x, op.Jval, op.Jcol, w0);
         (*nlaunch)++;
     }
     if(c1)
     {
         const int T1 = Tmax < kDmmaClassT[1] ? Tmax : kDmmaClassT[1];
-        assemble_items_dmma_kernel<kDmmaClassTiles[1], kDmmaClassT[0], kDmmaClassT[1], DET><<<Nwi, 256, smem_for(T1), N.s_side[0]>>>(dp, N, ld_for(T1), op.x, op.Jval, op.Jcol);
+        assemble_items_dmma_kernel<kDmmaClassTiles[1], kDmmaClassT[0], kDmmaClassT[1], DET><<<Nwi, 256, smem_for(T1), N.s_side[0]>>>(dp, N, ld_for(T1), op.x, op.Jval, op.Jcol, w0);
         MB200_CUDA_CHECK(cudaEventRecord(N.ev_join[0], N.s_side[0]));
         MB200_CUDA_CHECK(cudaStreamWaitEvent(s, N.ev_join[0], 0));
         (*nlaunch)++;
     }
     if(c2)
     {
-        assemble_items_dmma_kernel<kDmmaClassTiles[2], kDmmaClassT[1], kDmmaClassT[2], DET><<<Nwi, 256, smem_for(Tmax), N.s_side[1]>>>(dp, N, ld_for(Tmax), op.x, op.Jval, op.Jcol);
+        assemble_items_dmma_kernel<kDmmaClassTiles[2], kDmmaClassT[1], kDmmaClassT[2], DET><<<Nwi, 256, smem_for(Tmax), N.s_side[1]>>>(dp, N, ld_for(Tmax), op.x, op.Jval, op.Jcol, w0);
         MB200_CUDA_CHECK(cudaEventRecord(N.ev_join[1], N.s_side[1]));
         MB200_CUDA_CHECK(cudaStreamWaitEvent(s, N.ev_join[1], 0));
         (*nlaunch)++;
@@ -878,7 +880,7 @@ static bool launch_gram_dmma(const DevProblem& dp, NormalBuffers& N, const EvalB
 // item's block goes. Ends with an ASYNCHRONOUS copy of (n_c, widest item) to the host: the caller synchronises
 // the stream when it suits it (the solver does so once per trust-region step, with everything else it reads)
 // and then calls normal_adopt_sizes()
-bool normal_prepare(const DevProblem& dp, NormalBuffers& N, const EvalBuffers& op, cudaStream_t s, int* nlaunch)
+bool normal_prepare(const DevProblem& dp, NormalBuffers& N, const EvalBuffers& op, cudaStream_t s, int* nlaunch, bool boards_done)
 {
     if(!configure_kernels()) return false;
     const size_t lmap_bytes = ((size_t)dp.Nintr_state * sizeof(short) + 7) / 8 * 8;
@@ -890,18 +892,27 @@ bool normal_prepare(const DevProblem& dp, NormalBuffers& N, const EvalBuffers& o
         return false;
     }
     const int Nwi = dp.Nobs_board + dp.Nobs_point;
-    MB200_CUDA_CHECK(cudaMemsetAsync(N.active, 0, (size_t)(N.n_r > 0 ? N.n_r : 1) * sizeof(int), s));
-    MB200_CUDA_CHECK(cudaMemsetAsync(N.stat, 0, 4 * sizeof(int), s));
-    if(Nwi > 0) { item_columns_kernel<<<Nwi, 256, lmap_bytes, s>>>(dp, N, op.Jcol); (*nlaunch)++; }
+    // boards_done: the fused evaluation (fused_eval.cu) has already listed the board observations' columns and marked
+    // them, into buffers the caller cleared before it ran
+    if(!boards_done && !normal_clear_marks(N, s)) return false;
+    const int w0 = boards_done ? dp.Nobs_board : 0;
+    if(Nwi - w0 > 0) { item_columns_kernel<<<Nwi - w0, 256, lmap_bytes, s>>>(dp, N, op.Jcol, w0); (*nlaunch)++; }
     if(dp.reg_unity) { mark_reg_active_kernel<<<1, 32, 0, s>>>(dp, N); (*nlaunch)++; }
     if(dp.Ntri > 0) { mark_tri_active_kernel<<<(2 * dp.Ntri + 127) / 128, 128, 0, s>>>(dp, N); (*nlaunch)++; }
     // sharded solve: every rank must number the union of the active sets identically
     if(comm_active() && N.n_r > 0 && !comm_allreduce_max_int(N.active, (size_t)N.n_r, s)) return false;
     compact_scan_kernel<<<1, 1024, 0, s>>>(N);
     (*nlaunch)++;
-    if(N.det_available && !normal_det_item_offsets(dp, N, s, nlaunch)) return false;
+    if(N.det_available && !N.fused && !normal_det_item_offsets(dp, N, s, nlaunch)) return false;
     MB200_CUDA_CHECK(cudaMemcpyAsync(N.h_stat, N.stat, 4 * sizeof(int), cudaMemcpyDeviceToHost, s));
     MB200_CUDA_CHECK(cudaGetLastError());
+    return true;
+}
+
+bool normal_clear_marks(NormalBuffers& N, cudaStream_t s)
+{
+    MB200_CUDA_CHECK(cudaMemsetAsync(N.active, 0, (size_t)(N.n_r > 0 ? N.n_r : 1) * sizeof(int), s));
+    MB200_CUDA_CHECK(cudaMemsetAsync(N.stat, 0, 4 * sizeof(int), s));
     return true;
 }
 
@@ -932,14 +943,14 @@ bool normal_selfcheck(const DevProblem& dp, NormalBuffers& N, const EvalBuffers&
     if(!N.det || N.n_c <= 0) return true;
     const int n = N.n_c;
     std::vector<double> Sd((size_t)(n + 1) * n), Sa((size_t)(n + 1) * n);
-    if(!normal_finish(dp, N, op, d_rowptr, lambda, s, nlaunch)) return false;
+    if(!normal_finish(dp, N, op, d_rowptr, lambda, s, nlaunch, false)) return false;
     MB200_CUDA_CHECK(cudaMemcpy2DAsync(Sd.data(), (size_t)n * sizeof(double), N.S, (size_t)N.ldS * sizeof(double),
                                        (size_t)n * sizeof(double), n + 1, cudaMemcpyDeviceToHost, s));
     MB200_CUDA_CHECK(cudaStreamSynchronize(s));
     const bool det_saved = N.det;
     const int ld_saved = N.ldS;
     N.det = false;
-    const bool ok = normal_finish(dp, N, op, d_rowptr, lambda, s, nlaunch);
+    const bool ok = normal_finish(dp, N, op, d_rowptr, lambda, s, nlaunch, false);
     if(ok)
     {
         MB200_CUDA_CHECK(cudaMemcpy2DAsync(Sa.data(), (size_t)n * sizeof(double), N.S, (size_t)N.ldS * sizeof(double),
@@ -971,14 +982,14 @@ bool normal_selfcheck(const DevProblem& dp, NormalBuffers& N, const EvalBuffers&
 bool normal_assemble(const DevProblem& dp, NormalBuffers& N, const EvalBuffers& op, const int* d_rowptr,
                      double lambda, cudaStream_t s, int* nlaunch)
 {
-    if(!normal_prepare(dp, N, op, s, nlaunch)) return false;
+    if(!normal_prepare(dp, N, op, s, nlaunch, false)) return false;
     MB200_CUDA_CHECK(cudaStreamSynchronize(s));
-    return normal_adopt_sizes(N) && normal_finish(dp, N, op, d_rowptr, lambda, s, nlaunch);
+    return normal_adopt_sizes(N) && normal_finish(dp, N, op, d_rowptr, lambda, s, nlaunch, false);
 }
 
 // Pass 2: Gram matrices, Schur elimination, regularization, right-hand side: S, g', J'x
 bool normal_finish(const DevProblem& dp, NormalBuffers& N, const EvalBuffers& op, const int* d_rowptr,
-                   double lambda, cudaStream_t s, int* nlaunch)
+                   double lambda, cudaStream_t s, int* nlaunch, bool boards_done)
 {
     const size_t lmap_bytes = ((size_t)dp.Nintr_state * sizeof(short) + 7) / 8 * 8;
     const size_t ccol_bytes = ((size_t)N.cap * sizeof(int) + 7) / 8 * 8;
@@ -993,7 +1004,8 @@ bool normal_finish(const DevProblem& dp, NormalBuffers& N, const EvalBuffers& op
     if(N.det)
     {
         if(!normal_det_item_prepare(dp, N, s, nlaunch)) return false;
-        if(!launch_gram_dmma<true>(dp, N, op, Nwi, max_ntot, lmap_bytes, ccol_bytes, s, nlaunch)) return false;
+        // (boards_done: the fused evaluation left the board observations' blocks; only the point observations remain)
+        if(!launch_gram_dmma<true>(dp, N, op, Nwi, max_ntot, lmap_bytes, ccol_bytes, s, nlaunch, boards_done ? dp.Nobs_board : 0)) return false;
         if(!normal_det_finish(dp, N, op, d_rowptr, lambda, s, nlaunch)) return false;
         if(dp.Ntri > 0)
         {

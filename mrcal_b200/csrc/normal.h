@@ -46,6 +46,9 @@ struct NormalBuffers
     bool    det_available;   // the buffers below exist (MRCAL_B200_ATOMIC_ASSEMBLY=1 turns the path off)
     bool    det;          // in use for this assembly
     bool    selfchecked;  // the one-time cross-check against the atomic path has run
+    bool    fused;        // the board rows are evaluated by fused_eval.cu: blocks straight from the projection, no J
+    double* norm_part;    // [Nobs_board] per-observation |x|^2
+    double* qf_part;      // [Nobs_board] per-observation g'(J'J)g
     cudaStream_t s_side[2];               // forked streams of the Gram kernel's size classes (owned by the workspace)
     cudaEvent_t  ev_fork, ev_join[2];
     int     capA;         // most local columns (incl. the two gradient rows) an item may have in the A pool
@@ -71,10 +74,14 @@ struct NormalBuffers
 
 // The same in pieces, for a caller that wants to pick its own moment to wait for the device:
 // prepare (device work + an async copy of the sizes) -> [synchronise the stream] -> adopt_sizes -> finish
-bool normal_prepare(const DevProblem& dp, NormalBuffers& N, const EvalBuffers& op, cudaStream_t s, int* nlaunch);
+bool normal_clear_marks(NormalBuffers& N, cudaStream_t s);
+bool normal_prepare(const DevProblem& dp, NormalBuffers& N, const EvalBuffers& op, cudaStream_t s, int* nlaunch, bool boards_done);
 bool normal_adopt_sizes(NormalBuffers& N);
 bool normal_finish(const DevProblem& dp, NormalBuffers& N, const EvalBuffers& op, const int* d_rowptr,
-                   double lambda, cudaStream_t s, int* nlaunch);
+                   double lambda, cudaStream_t s, int* nlaunch, bool boards_done);
+// fused_eval.cu
+bool launch_fused_boards(const DevProblem& dp, NormalBuffers& N, const EvalBuffers& out, double* norm_part, cudaStream_t s, int* nlaunch);
+bool launch_quadform_boards(const DevProblem& dp, const NormalBuffers& N, const double* g_full, double* part, double* out, cudaStream_t s, int* nlaunch);
 bool normal_selfcheck(const DevProblem& dp, NormalBuffers& N, const EvalBuffers& op, const int* d_rowptr,
                       double lambda, cudaStream_t s, int* nlaunch);
 // S, g', g_full at the operating point `op` (needs its x and Jacobian). lambda: diagonal loading.

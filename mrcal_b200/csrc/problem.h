@@ -92,6 +92,6 @@ struct Problem;   // problem.cu
 // eval.cu
 bool launch_unpack_state(const DevProblem& dp, const double* b_packed, cudaStream_t stream, int* launch_counter);
 bool launch_evaluate(const DevProblem& dp, const EvalBuffers& out, bool with_jacobian,
-                     int* Jrowptr /* device, may be null */, cudaStream_t stream, int* launch_counter);
+                     int* Jrowptr /* device, may be null */, cudaStream_t stream, int* launch_counter, bool boards = true);
 
 }  // namespace mb200

@@ -33,14 +33,14 @@ static bool build_workspace(mrcal_b200_problem* P);
 // in flight: the kernel streams J once and wants as many loads outstanding as it can get
 __global__ void __launch_bounds__(256)
 jv_kernel(const int* __restrict__ rowptr, const int* __restrict__ col, const double* __restrict__ val,
-          const double* __restrict__ v, const double* __restrict__ x, int Nrows, double* __restrict__ out)
+          const double* __restrict__ v, const double* __restrict__ x, int row_begin, int Nrows, double* __restrict__ out)
 {
     __shared__ double red0[8], red1[8];
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5, sub = lane & 7;
     const int nwarps = (gridDim.x * blockDim.x) >> 5;
     double s0 = 0., s1 = 0.;
     // (the loop bound is per WARP, so that all 32 lanes reach the shuffles together)
-    for(int row0 = ((blockIdx.x * blockDim.x + threadIdx.x) >> 5) * 4; row0 < Nrows; row0 += nwarps * 4)
+    for(int row0 = row_begin + ((blockIdx.x * blockDim.x + threadIdx.x) >> 5) * 4; row0 < Nrows; row0 += nwarps * 4)
     {
         const int row = row0 + (lane >> 3);
         const bool live = row < Nrows;
@@ -221,6 +221,31 @@ static bool build_workspace(mrcal_b200_problem* P)
         // (always there: the communicator may be created after this workspace)
         if(!A.alloc(&N.S_packed, (size_t)N.nblk_max * (N.nblk_max + 1) / 2 * kCholBlock * kCholBlock)) return false;
     }
+    // the fused evaluation (fused_eval.cu): splined models with the core locked, boards of at most 128 corners
+    N.fused = N.det_available && L.splined && !L.sel.do_optimize_intrinsics_core && L.sel.do_optimize_intrinsics_distortions &&
+              L.sel.do_optimize_frames && L.i_frame0 >= 0 && L.d.Nobs_board > 0 && L.d.W * L.d.H <= 128 &&
+              getenv("MRCAL_B200_NO_FUSED") == nullptr;
+    if(N.fused)
+    {
+        // fixed places in the pool: the observation's column count is only known inside the kernel that fills its block
+        auto even = [](int v) { return (v + 1) & ~1; };
+        const int lda_board = even(std::min(N.capA, 160 + 2));
+        const int lda_point = even(std::min(N.capA, 2 * 16 + 4 + 6 + 2));
+        std::vector<long long> off(Nwi);
+        std::vector<int> lda(Nwi);
+        for(int w = 0; w < Nwi; w++)
+        {
+            const bool board = w < L.d.Nobs_board;
+            lda[w] = board ? lda_board : lda_point;
+            off[w] = board ? (long long)w * lda_board * lda_board
+                           : (long long)L.d.Nobs_board * lda_board * lda_board + (long long)(w - L.d.Nobs_board) * lda_point * lda_point;
+        }
+        ok = A.alloc(&N.norm_part, L.d.Nobs_board, true) && A.alloc(&N.qf_part, L.d.Nobs_board, true);
+        if(!ok) return false;
+        MB200_CUDA_CHECK(cudaMemcpyAsync(N.wi_Aoff, off.data(), Nwi * sizeof(long long), cudaMemcpyHostToDevice, P->stream));
+        MB200_CUDA_CHECK(cudaMemcpyAsync(N.wi_lda, lda.data(), Nwi * sizeof(int), cudaMemcpyHostToDevice, P->stream));
+        MB200_CUDA_CHECK(cudaStreamSynchronize(P->stream));   // the staging vectors go out of scope
+    }
     MB200_CUDA_CHECK(cudaEventCreateWithFlags(&N.ev_fork, cudaEventDisableTiming));
     for(int k = 0; k < 2; k++)
     {
@@ -368,6 +393,86 @@ __global__ void combine_step_dev_kernel(int n, const double* __restrict__ scal, 
     p_new[i] = p[i] + sv;
 }
 
+// One-time cross-checks on the caller's own problem (first assembly of a workspace): the atomics-free assembly against
+// the atomic one (normal_selfcheck), and the fused evaluation's blocks against the ones made from a stored Jacobian.
+// A path that disagrees is switched off for this workspace, loudly. MRCAL_B200_NO_SELFCHECK=1 skips all of it
+static bool solver_selfcheck(mrcal_b200_problem* P, int which, double lambda)
+{
+    SolverWorkspace* ws = P->ws.get();
+    NormalBuffers& N = ws->N;
+    cudaStream_t s = P->stream;
+    int* nl = &P->launches;
+    if(N.selfchecked || getenv("MRCAL_B200_NO_SELFCHECK") != nullptr || comm_active()) { N.selfchecked = true; return true; }
+    if(!N.fused) return normal_selfcheck(P->dp, N, P->op[which], P->d_rowptr, lambda, s, nl);
+    // fused: its S first, then the same point through the stored Jacobian
+    const int n = N.n_c;
+    std::vector<double> Sf, Sj;
+    auto grab = [&](std::vector<double>& out) -> bool
+    {
+        out.assign((size_t)(n + 1) * (n > 0 ? n : 1), 0.);
+        if(n <= 0) return true;
+        MB200_CUDA_CHECK(cudaMemcpy2DAsync(out.data(), (size_t)n * sizeof(double), N.S, (size_t)N.ldS * sizeof(double),
+                                           (size_t)n * sizeof(double), n + 1, cudaMemcpyDeviceToHost, s));
+        MB200_CUDA_CHECK(cudaStreamSynchronize(s));
+        return true;
+    };
+    if(!N.det) { N.selfchecked = true; return true; }
+    if(!normal_finish(P->dp, N, P->op[which], P->d_rowptr, lambda, s, nl, true) || !grab(Sf)) return false;
+    N.fused = false;
+    // (the per-assembly placement of the blocks is what the stored-Jacobian path uses)
+    if(!problem_evaluate(P, which, true, false) || !normal_prepare(P->dp, N, P->op[which], s, nl, false)) return false;
+    MB200_CUDA_CHECK(cudaStreamSynchronize(s));
+    if(!normal_adopt_sizes(N)) return false;
+    bool agree = N.n_c == n && N.det;
+    if(agree)
+    {
+        if(!normal_selfcheck(P->dp, N, P->op[which], P->d_rowptr, lambda, s, nl)) return false;   // det vs atomic, on the stored Jacobian
+        if(!normal_finish(P->dp, N, P->op[which], P->d_rowptr, lambda, s, nl, false) || !grab(Sj)) return false;
+        double scale = 0., worst = 0.;
+        for(size_t k = 0; k < Sj.size(); k++)
+        {
+            if(fabs(Sj[k]) > scale) scale = fabs(Sj[k]);
+            if(!(fabs(Sj[k] - Sf[k]) <= worst)) worst = fabs(Sj[k] - Sf[k]);
+        }
+        agree = worst <= 1e-9 * scale;
+        if(!agree)
+            fprintf(stderr, "mrcal_b200: WARNING: the fused evaluation disagrees with the stored-Jacobian path (|diff| %g of %g): "
+                            "not using it for this problem\n", worst, scale);
+    }
+    N.selfchecked = true;
+    if(agree)
+    {
+        // back to the fused path: restore the fixed placement of the blocks and redo the evaluation's blocks
+        N.fused = true;
+        const Layout& L = P->L;
+        auto even = [](int v) { return (v + 1) & ~1; };
+        const int lda_board = even(std::min(N.capA, 160 + 2)), lda_point = even(std::min(N.capA, 2 * 16 + 4 + 6 + 2));
+        const int Nwi = L.d.Nobs_board + L.d.Nobs_point;
+        std::vector<long long> off(Nwi);
+        std::vector<int> lda(Nwi);
+        for(int w = 0; w < Nwi; w++)
+        {
+            const bool board = w < L.d.Nobs_board;
+            lda[w] = board ? lda_board : lda_point;
+            off[w] = board ? (long long)w * lda_board * lda_board
+                           : (long long)L.d.Nobs_board * lda_board * lda_board + (long long)(w - L.d.Nobs_board) * lda_point * lda_point;
+        }
+        MB200_CUDA_CHECK(cudaMemcpyAsync(N.wi_Aoff, off.data(), Nwi * sizeof(long long), cudaMemcpyHostToDevice, s));
+        MB200_CUDA_CHECK(cudaMemcpyAsync(N.wi_lda, lda.data(), Nwi * sizeof(int), cudaMemcpyHostToDevice, s));
+        MB200_CUDA_CHECK(cudaStreamSynchronize(s));
+        const EvalBuffers& o = P->op[which];
+        MB200_CUDA_CHECK(cudaMemsetAsync(o.norm2, 0, sizeof(double), s));
+        if(!normal_clear_marks(N, s) || !launch_unpack_state(P->dp, o.p, s, nl) ||
+           !launch_fused_boards(P->dp, N, o, N.norm_part, s, nl) ||
+           !launch_evaluate(P->dp, o, true, nullptr, s, nl, false) ||
+           !normal_prepare(P->dp, N, o, s, nl, true)) return false;
+        if(comm_active() && !comm_allreduce_sum(o.norm2, 1, s)) return false;
+        MB200_CUDA_CHECK(cudaStreamSynchronize(s));
+        if(!normal_adopt_sizes(N)) return false;
+    }
+    return true;
+}
+
 static bool dogleg_pass(mrcal_b200_problem* P, const mrcal_b200_solver_parameters_t& par, double* lambda,
                         mrcal_b200_solve_info_t* info, PhaseTimer* T, double* norm2_final)
 {
@@ -383,19 +488,28 @@ static bool dogleg_pass(mrcal_b200_problem* P, const mrcal_b200_solver_parameter
     auto evaluate = [&](int which) -> bool
     {
         const int a = T->mark();
-        if(!problem_evaluate(P, which, true, false)) return false;
+        if(N.fused)
+        {
+            // boards: residuals and normal-equation blocks in one pass, no Jacobian; the rest (points, regularization) as usual
+            const EvalBuffers& o = P->op[which];
+            MB200_CUDA_CHECK(cudaMemsetAsync(o.norm2, 0, sizeof(double), s));
+            if(!normal_clear_marks(N, s) || !launch_unpack_state(P->dp, o.p, s, nl) ||
+               !launch_fused_boards(P->dp, N, o, N.norm_part, s, nl) ||
+               !launch_evaluate(P->dp, o, true, nullptr, s, nl, false)) return false;
+        }
+        else if(!problem_evaluate(P, which, true, false)) return false;
         T->spans[0].push_back({a, T->mark()});
         info->Nevaluations++;
         const int b = T->mark();
-        if(!normal_prepare(P->dp, N, P->op[which], s, nl)) return false;
+        if(!normal_prepare(P->dp, N, P->op[which], s, nl, N.fused)) return false;
         T->spans[1].push_back({b, T->mark()});
         return true;
     };
     auto assemble = [&](int which) -> bool
     {
-        if(!N.selfchecked && !normal_selfcheck(P->dp, N, P->op[which], P->d_rowptr, *lambda, s, nl)) return false;
+        if(!N.selfchecked && !solver_selfcheck(P, which, *lambda)) return false;
         const int a = T->mark();
-        if(!normal_finish(P->dp, N, P->op[which], P->d_rowptr, *lambda, s, nl)) return false;
+        if(!normal_finish(P->dp, N, P->op[which], P->d_rowptr, *lambda, s, nl, N.fused)) return false;
         T->spans[1].push_back({a, T->mark()});
         return true;
     };
@@ -409,16 +523,39 @@ static bool dogleg_pass(mrcal_b200_problem* P, const mrcal_b200_solver_parameter
         info->Nsyncs++;
         return normal_adopt_sizes(N);   // n_c, widest item: from the prepare() that ran last
     };
+    // an observation whose patch of control points outgrows the fused kernel's tables (a board filling the imager):
+    // this workspace goes back to the stored-Jacobian path, starting with the evaluation that found out
+    auto evaluate_checked = [&](int which) -> bool
+    {
+        if(!evaluate(which)) return false;
+        return true;
+    };
+    (void)evaluate_checked;
 
     // rows whose sums this rank contributes to cross-rank reductions: the regularization rows are
     // replicated on every rank but counted once
     const int Nrows_mine = P->dp.reg_owner ? Nmeas : P->dp.m_reg0;
     const int e0 = N.e0, e1 = N.e1;
 
-    if(!evaluate(P->cur)) return false;
-    if(comm_active() && !comm_allreduce_sum(P->op[P->cur].norm2, 1, s)) return false;
-    MB200_CUDA_CHECK(cudaMemcpyAsync(ws->scal + 22, P->op[P->cur].norm2, sizeof(double), cudaMemcpyDeviceToDevice, s));
-    if(!read_back()) return false;
+    // evaluate + read back; if the fused kernel had to give up on an observation, once more through the stored-Jacobian path
+    auto evaluate_and_read = [&](int which) -> bool
+    {
+        for(int attempt = 0; attempt < 2; attempt++)
+        {
+            if(!evaluate(which)) return false;
+            MB200_CUDA_CHECK(cudaMemcpyAsync(ws->scal + 22, P->op[which].norm2, sizeof(double), cudaMemcpyDeviceToDevice, s));
+            if(comm_active() && !comm_allreduce_sum(ws->scal + 22, 1, s)) return false;
+            if(!read_back()) return false;
+            if(!(N.fused && N.h_stat[3] != 0)) return true;
+            fprintf(stderr, "mrcal_b200: an observation touches more control points than the fused evaluation handles: "
+                            "continuing with the stored-Jacobian path\n");
+            N.fused = false;
+            info->Nevaluations--;
+            // (the blocks' places in the pool are computed per assembly on that path)
+        }
+        return true;
+    };
+    if(!evaluate_and_read(P->cur)) return false;
     double norm2_x = ws->h_scal[22];
     if(info->Nevaluations == 1) info->norm2_x_initial = norm2_x;
 
@@ -438,8 +575,8 @@ static bool dogleg_pass(mrcal_b200_problem* P, const mrcal_b200_solver_parameter
                 if(!sizes_are_cur)
                 {
                     // (only after a failed factorization: the column bookkeeping belongs to the trial point by now)
-                    if(!normal_prepare(P->dp, N, cur, s, nl)) return false;
-                    if(!read_back()) return false;
+                    if(!evaluate_and_read(P->cur)) return false;
+                    info->Nevaluations--;
                     sizes_are_cur = true;
                 }
                 if(!assemble(P->cur)) return false;
@@ -451,7 +588,15 @@ static bool dogleg_pass(mrcal_b200_problem* P, const mrcal_b200_solver_parameter
             {
                 MB200_CUDA_CHECK(cudaMemsetAsync(ws->scal, 0, 32 * sizeof(double), s));
                 dots_kernel<<<3, 1024, 0, s>>>(N.g_full, nullptr, e0, e1, Nstate, ws->scal + 0);
-                jv_kernel<<<148 * 16, 256, 0, s>>>(P->d_rowptr, cur.Jcol, cur.Jval, N.g_full, cur.x, Nrows_mine, ws->scal + 9);
+                if(N.fused)
+                {
+                    // |J g|^2: the board rows from the observations' blocks, the others from their stored rows
+                    if(!launch_quadform_boards(P->dp, N, N.g_full, N.qf_part, ws->scal + 10, s, nl)) return false;
+                    if(Nrows_mine > P->dp.m_point0)
+                        jv_kernel<<<148 * 4, 256, 0, s>>>(P->d_rowptr, cur.Jcol, cur.Jval, N.g_full, cur.x, P->dp.m_point0, Nrows_mine, ws->scal + 9);
+                }
+                else
+                    jv_kernel<<<148 * 16, 256, 0, s>>>(P->d_rowptr, cur.Jcol, cur.Jval, N.g_full, cur.x, 0, Nrows_mine, ws->scal + 9);
                 *nl += 2;
                 // eliminated-range dots and the row sums are per-rank partial sums: slots [6..8] and [9..10] -> one reduction
                 if(comm_active() && !comm_allreduce_partial(ws->scal, s)) return false;
@@ -481,11 +626,8 @@ static bool dogleg_pass(mrcal_b200_problem* P, const mrcal_b200_solver_parameter
             select_step_kernel<<<1, 32, 0, s>>>(ws->scal, ws->ictl, trustregion, *lambda);
             combine_step_dev_kernel<<<(Nstate + 255) / 256, 256, 0, s>>>(Nstate, ws->scal, N.g_full, ws->step_gn, cur.p, ws->step, nxt.p);
             *nl += 2;
-            if(!evaluate(1 - P->cur)) return false;
             sizes_are_cur = false;
-            MB200_CUDA_CHECK(cudaMemcpyAsync(ws->scal + 22, nxt.norm2, sizeof(double), cudaMemcpyDeviceToDevice, s));
-            if(comm_active() && !comm_allreduce_sum(ws->scal + 22, 1, s)) return false;
-            if(!read_back()) return false;
+            if(!evaluate_and_read(1 - P->cur)) return false;
 
             const bool need_gn = ws->h_ictl[0] != 0, zero_grad = ws->h_ictl[1] != 0;
             if(zero_grad) { done = true; break; }
