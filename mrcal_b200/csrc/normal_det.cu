@@ -236,14 +236,15 @@ groups_panels_kernel(NormalBuffers N, double lambda, int n_c, int nblk)
     if(tid < 6) Yg[(size_t)(n_c >> 6) * (6 * TB) + tid * TB + (n_c & 63)] = -s_h[tid];
 }
 
-struct TileCommon
+struct alignas(16) TileCommon
 {
     int wl[2048];      // items (or groups) that reach both blocks of the tile
     int scan[256];
     int count;
-    int pad;
+    int pad[3];        // what follows in shared memory is accessed 16 bytes at a time (cp.async, double2)
 };
-struct TileSmemA
+static_assert(sizeof(TileCommon) % 16 == 0, "the tile and the staging buffers behind TileCommon need 16-byte alignment");
+struct alignas(16) TileSmemA
 {
     double tile[TB * TLD];
     int    meta[kChunkItems][4];           // a0 | na<<8,  b0 | nb<<8,  lda, (unused)
@@ -251,7 +252,7 @@ struct TileSmemA
     unsigned char rl[kChunkItems][TB + 4]; // tile row of each local row
     unsigned char cl[kChunkItems][TB + 4]; // tile column of each local column
 };
-struct TileSmemS
+struct alignas(16) TileSmemS
 {
     double R[2][6 * kChunkGroups][TLD];
     double C[2][6 * kChunkGroups][TLD];
