@@ -160,11 +160,10 @@ eval_boards_kernel(DevProblem P, double* __restrict__ x, double* __restrict__ Jv
     __shared__ ObsGeometry G;
     __shared__ double red[32];
     __shared__ int s_ivar0[256];   // per corner: where its spline window starts (the only data-dependent column index)
-    // Jacobian staging: each thread (corner) deposits the VALUES of its two rows here -- 2*nnz_row contiguous
-    // doubles, which is also how they sit in J -- and hands them to the TMA: one bulk shared->global copy per
-    // corner (cp.async.bulk), no thread spends time on the stores. The column indices are not staged at all:
+    // Jacobian staging: each thread (corner) deposits the VALUES of its two rows in shared memory (odd row stride: no bank
+    // conflicts); the CTA packs them into one linear block -- the rows of an observation are contiguous in J -- and ONE
+    // TMA bulk copy (cp.async.bulk shared -> global) writes the whole block. The column indices are not staged at all:
     // they are a function of (corner, entry) and are written straight from registers, coalesced.
-    // The row stride is 2 (mod 4) doubles: 16-byte aligned for the bulk copy, 2-way bank conflicts at worst
     extern __shared__ __align__(16) double stage_v[];
 
     const int iobs   = blockIdx.x;
@@ -200,9 +199,9 @@ eval_boards_kernel(DevProblem P, double* __restrict__ x, double* __restrict__ Jv
     const int NWH         = P.W * P.H;
     const double wx2 = P.u_warp[0], wy2 = P.u_warp[1];
 
-    const int row2 = 2 * nnz_row;
-    int stride = row2;
-    while((stride & 3) != 2) stride++;
+    const int row2 = 2 * nnz_row, stride = row2 + 1;
+    double* lin_v = stage_v + (size_t)blockDim.x * stride + 1;
+    lin_v = reinterpret_cast<double*>((reinterpret_cast<size_t>(lin_v) + 15) & ~(size_t)15);   // 16-byte aligned for the bulk copy
     const int nI = P.nnz_row_intr;
 
     double sumsq = 0.;
@@ -332,17 +331,6 @@ eval_boards_kernel(DevProblem P, double* __restrict__ x, double* __restrict__ Jv
                 }
             }
             s_ivar0[threadIdx.x] = ivar0s;
-            // this corner's 2 rows: one bulk copy, shared -> global, issued by the thread that wrote them. The fence makes
-            // the generic-proxy writes above visible to the async proxy that reads them
-            {
-                const size_t ifeat0 = (size_t)ipt;
-                double* gdst = Jval + (size_t)P.board_j0[iobs] + ifeat0 * row2;
-                const unsigned ssrc = (unsigned)__cvta_generic_to_shared(stage_v + (size_t)threadIdx.x * stride);
-                asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");
-                asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;\n"
-                             ::"l"(gdst), "r"(ssrc), "r"(row2 * 8) : "memory");
-                asm volatile("cp.async.bulk.commit_group;\n" ::: "memory");
-            }
         }
       }
       if constexpr(WITH_J)
@@ -380,9 +368,20 @@ eval_boards_kernel(DevProblem P, double* __restrict__ x, double* __restrict__ Jv
                 }
             }
             Jcol[gbase + g] = col;
+            lin_v[g] = stage_v[(size_t)t * stride + e];
         }
-        // the staging buffer is reused by the next chunk of corners: wait until the TMA has READ it
-        asm volatile("cp.async.bulk.wait_group.read 0;\n" ::: "memory");
+        // the packed block: one bulk copy, shared -> global. The fence makes the generic-proxy writes above visible to
+        // the async proxy that reads them; the buffers are reused by the next chunk of corners only after the TMA has READ them
+        asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");
+        __syncthreads();
+        if(threadIdx.x == 0)
+        {
+            const unsigned ssrc = (unsigned)__cvta_generic_to_shared(lin_v);
+            asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;\n"
+                         ::"l"(Jval + gbase), "r"(ssrc), "r"(nhere * row2 * 8) : "memory");
+            asm volatile("cp.async.bulk.commit_group;\n" ::: "memory");
+            asm volatile("cp.async.bulk.wait_group.read 0;\n" ::: "memory");
+        }
         __syncthreads();
       }
     }
@@ -769,9 +768,7 @@ static bool launch_kind(const DevProblem& dp, const EvalBuffers& out, bool with_
         {
             // widest row: extrinsics present
             const int row2 = 2 * (dp.nnz_row_intr + (dp.opt_extr ? 6 : 0) + dp.nnz_row_board_geom);
-            int stride = row2;
-            while((stride & 3) != 2) stride++;
-            const size_t smem = (size_t)threads * stride * sizeof(double) + 16;
+            const size_t smem = ((size_t)threads * (row2 + 1) + (size_t)threads * row2 + 4) * sizeof(double) + 16;
             // cudaFuncSetAttribute is per device: one flag per (device, lens kind)
             static bool configured[kMaxDevices][LENS_NKINDS] = {};
             int dev = 0;

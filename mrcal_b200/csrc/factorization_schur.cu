@@ -168,6 +168,8 @@ __global__ void __launch_bounds__(64)
 panels_forward_kernel(NormalBuffers N, const double* __restrict__ Bf, int Nelim, double* __restrict__ Bs)
 {
     const int blk = blockIdx.x, rhs = blockIdx.y, col = threadIdx.x;
+    // (the panels carry the solver's right-hand-side column at compact index n_c: not part of the factor)
+    if(TB * blk + col >= N.n_c) return;
     const unsigned* present = N.grp_present + (size_t)blk * N.gwords;
     double acc = 0.;
     for(int w = 0; w < N.gwords; w++)

@@ -408,25 +408,32 @@ sum_norm_partials_kernel(const double* __restrict__ part, int n, double* __restr
     if(tid == 0) *norm2 += s[0];
 }
 
-// |J g|^2 over the board rows from the blocks: g_w' [A B'; B D] g_w per observation. part[w] = that; one warp per item
+// |J g|^2 over the board rows from the blocks: g_w' [A B'; B D] g_w per observation. part[w] = that. One warp per item;
+// the lanes run along a row of A (coalesced), the rows are taken one after the other
 __global__ void __launch_bounds__(256)
 quadform_items_kernel(DevProblem P, NormalBuffers N, const double* __restrict__ g_full, int Nitems, double* __restrict__ part)
 {
-    const int w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    __shared__ double s_g[8][168];
+    const int wib = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int w = blockIdx.x * 8 + wib;
     if(w >= Nitems) return;
     const int nsh = N.wi_nsh[w], lda = N.wi_lda[w];
     const double* A = N.wi_A + N.wi_Aoff[w];
     const int* cols = N.wi_cols + (size_t)w * N.cap;
     const int iframe = P.obs_board[3 * w + 2];
+    double* gl = s_g[wib];
+    for(int i = lane; i < nsh; i += 32) gl[i] = g_full[N.state_index(cols[i])];
+    __syncwarp();
     double q = 0.;
     // shared x shared (A symmetric, lower stored): sum_i g_i (A_ii g_i + 2 sum_{j<i} A_ij g_j)
-    for(int i = lane; i < nsh; i += 32)
+    for(int i = 0; i < nsh; i++)
     {
-        const double gi = g_full[N.state_index(cols[i])];
         const double* row = A + (size_t)i * lda;
-        double s = 0.;
-        for(int j = 0; j < i; j++) s += row[j] * g_full[N.state_index(cols[j])];
-        q += gi * (row[i] * gi + 2. * s);
+        double sv = 0.;
+        for(int j = lane; j < i; j += 32) sv += row[j] * gl[j];
+        if(lane == (i & 31)) sv = 2. * sv + row[i] * gl[i];
+        else sv = 2. * sv;
+        q += gl[i] * sv;
     }
     // frame: 2 g_f' B g_s + g_f' D g_f
     if(P.opt_frames)
@@ -436,16 +443,15 @@ quadform_items_kernel(DevProblem P, NormalBuffers N, const double* __restrict__ 
         for(int p = 0; p < 6; p++) gf[p] = g_full[P.i_frame0 + 6 * iframe + p];
         for(int i = lane; i < nsh; i += 32)
         {
-            const double gi = g_full[N.state_index(cols[i])];
-            double s = 0.;
-            for(int p = 0; p < 6; p++) s += gf[p] * B[(size_t)p * N.cap + i];
-            q += 2. * gi * s;
+            double sv = 0.;
+            for(int p = 0; p < 6; p++) sv += gf[p] * B[(size_t)p * N.cap + i];
+            q += 2. * gl[i] * sv;
         }
         if(lane == 0)
         {
             const double* D = N.wi_D + (size_t)w * 36;
             for(int p = 0; p < 6; p++)
-                for(int r = 0; r < 6; r++) q += gf[p] * D[p * 6 + r] * gf[r];
+                for(int rr = 0; rr < 6; rr++) q += gf[p] * D[p * 6 + rr] * gf[rr];
         }
     }
 #pragma unroll
@@ -495,7 +501,7 @@ bool launch_fused_boards(const DevProblem& dp, NormalBuffers& N, const EvalBuffe
 bool launch_quadform_boards(const DevProblem& dp, const NormalBuffers& N, const double* g_full, double* part, double* out, cudaStream_t s, int* nlaunch)
 {
     if(dp.Nobs_board <= 0) return true;
-    quadform_items_kernel<<<(dp.Nobs_board * 32 + 255) / 256, 256, 0, s>>>(dp, N, g_full, dp.Nobs_board, part);
+    quadform_items_kernel<<<(dp.Nobs_board + 7) / 8, 256, 0, s>>>(dp, N, g_full, dp.Nobs_board, part);
     sum_partials_to_kernel<<<1, 256, 0, s>>>(part, dp.Nobs_board, out);
     *nlaunch += 2;
     MB200_CUDA_CHECK(cudaGetLastError());

@@ -66,6 +66,8 @@ struct NormalBuffers
     int     gwords, wwords, bwords;
     double* grp_Linv;     // [Ngroups][36] inverse of the Cholesky factor of D (lower)
     double* grp_h;        // [Ngroups][6]  inv(L_D) gf
+    double* part_scratch; // partial tiles of the tiles whose contributors are split over several CTAs
+    int*    part_arrive;  // their arrival counters
     double* S_packed;     // sharded solves: the lower-triangle tiles of S, each 64x64 contiguous: what is all-reduced
 
     __host__ __device__ int reduced_index(int c) const { return c < e0 ? c : c - (e1 - e0); }
@@ -103,6 +105,8 @@ bool normal_det_finish(const DevProblem& dp, NormalBuffers& N, const EvalBuffers
                        double lambda, cudaStream_t s, int* nlaunch);
 bool normal_det_item_prepare(const DevProblem& dp, NormalBuffers& N, cudaStream_t s, int* nlaunch);   // after the compaction
 bool normal_det_item_offsets(const DevProblem& dp, NormalBuffers& N, cudaStream_t s, int* nlaunch);   // before it
+size_t normal_det_part_scratch_doubles();
+int normal_det_part_arrive_ints();
 bool normal_det_rhs(const NormalBuffers& N, cudaStream_t s, int* nlaunch);   // after the cross-rank reduction of S
 bool normal_det_backsub(const NormalBuffers& N, const double* sol_compact, double* step_full, cudaStream_t s, int* nlaunch);
 

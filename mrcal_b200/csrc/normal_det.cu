@@ -281,37 +281,76 @@ __device__ __forceinline__ void build_worklist(TileCommon& sm, const unsigned* r
     if(tid == 255) sm.count = sm.scan[255];
     __syncthreads();
 }
+// how many ids the worklists of a tile will hold in total
+__device__ __forceinline__ int count_common(TileCommon& sm, const unsigned* rowA, const unsigned* rowB, int nwords)
+{
+    const int tid = threadIdx.x;
+    int cnt = 0;
+    for(int w = tid; w < nwords; w += 256) cnt += __popc(rowA[w] & rowB[w]);
+    sm.scan[tid] = cnt;
+    __syncthreads();
+    for(int o = 128; o > 0; o >>= 1) { if(tid < o) sm.scan[tid] += sm.scan[tid + o]; __syncthreads(); }
+    const int total = sm.scan[0];
+    __syncthreads();
+    return total;
+}
 
-// One CTA per 64x64 tile of the lower triangle of S
+constexpr int kMaxParts = 8;          // a tile's contributors may be split over this many CTAs
+constexpr int kItemsPerPart = 96;
+constexpr int kGroupsPerPart = 48;
+constexpr int kSplitTilesCap = 2048;  // tiles with a slot in the partial-sum scratch (beyond: one CTA does it all)
+
+// One CTA per (64x64 tile of the lower triangle of S, part). A tile that many items / groups reach -- the block row of
+// the extrinsics, the board warp and the right-hand side reaches all of them -- is split: each part sums its share of
+// the contributors (contiguous ranges of the worklists) into a partial tile; the part that finishes LAST adds the
+// partial tiles up in part order. Which part is last varies; what it computes does not.
 __global__ void __launch_bounds__(256, 2)
-schur_tiles_kernel(NormalBuffers N, double lambda, int n_c, int nblk, bool add_lambda, double* __restrict__ packed)
+schur_tiles_kernel(NormalBuffers N, double lambda, int n_c, int nblk, bool add_lambda, double* __restrict__ packed,
+                   double* __restrict__ part_scratch, int* __restrict__ part_arrive)
 {
     extern __shared__ __align__(16) unsigned char dsm_raw[];
     TileCommon& sc = *reinterpret_cast<TileCommon*>(dsm_raw);
     TileSmemA& sa = *reinterpret_cast<TileSmemA*>(dsm_raw + sizeof(TileCommon));
     TileSmemS& ss = *reinterpret_cast<TileSmemS*>(dsm_raw + sizeof(TileCommon));
+    __shared__ int s_last;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    // tile number -> (r >= c), the late rows first: they carry the most work
+    const int itile = (nblk * (nblk + 1) / 2 - 1) - (int)blockIdx.x;   // the late rows first: they carry the most work
     int r, c;
     {
-        const int q = (nblk * (nblk + 1) / 2 - 1) - (int)blockIdx.x;
-        r = (int)((sqrtf(8.f * q + 1.f) - 1.f) * 0.5f);
-        while(r * (r + 1) / 2 > q) r--;
-        while((r + 1) * (r + 2) / 2 <= q) r++;
-        c = q - r * (r + 1) / 2;
+        r = (int)((sqrtf(8.f * itile + 1.f) - 1.f) * 0.5f);
+        while(r * (r + 1) / 2 > itile) r--;
+        while((r + 1) * (r + 2) / 2 <= itile) r++;
+        c = itile - r * (r + 1) / 2;
     }
     const bool diag = r == c;
+    const unsigned* wiA = N.wi_present + (size_t)r * N.wwords;
+    const unsigned* wiB = N.wi_present + (size_t)c * N.wwords;
+    const unsigned* grA = N.grp_present + (size_t)r * N.gwords;
+    const unsigned* grB = N.grp_present + (size_t)c * N.gwords;
+    const int n_items = count_common(sc, wiA, wiB, N.wwords);
+    const int n_groups = N.Ngroups > 0 ? count_common(sc, grA, grB, N.gwords) : 0;
+    int parts = max((n_items + kItemsPerPart - 1) / kItemsPerPart, (n_groups + kGroupsPerPart - 1) / kGroupsPerPart);
+    parts = min(kMaxParts, max(1, parts));
+    if(itile >= kSplitTilesCap || part_scratch == nullptr) parts = 1;
+    const int part = blockIdx.y;
+    if(part >= parts) return;
+    const int item_lo = (int)((long)n_items * part / parts), item_hi = (int)((long)n_items * (part + 1) / parts);
+    const int grp_lo = (int)((long)n_groups * part / parts), grp_hi = (int)((long)n_groups * (part + 1) / parts);
 
     ////////////////////////////// phase A: the items' Gram blocks
     for(int e = tid; e < TB * TLD; e += 256) sa.tile[e] = 0.;
     __syncthreads();
-    for(int w0 = 0; w0 < N.wwords; w0 += 64)
+    int seen = 0;
+    for(int w0 = 0; w0 < N.wwords && seen < item_hi; w0 += 64)
     {
-        build_worklist(sc, N.wi_present + (size_t)r * N.wwords, N.wi_present + (size_t)c * N.wwords, w0, min(w0 + 64, N.wwords));
+        build_worklist(sc, wiA, wiB, w0, min(w0 + 64, N.wwords));
         const int nwl = sc.count;
-        for(int ch = 0; ch < nwl; ch += kChunkItems)
+        // my share of this stretch of the worklist
+        const int lo = max(item_lo - seen, 0), hi = min(item_hi - seen, nwl);
+        seen += nwl;
+        for(int ch = lo; ch < hi; ch += kChunkItems)
         {
-            const int nch = min(kChunkItems, nwl - ch);
+            const int nch = min(kChunkItems, hi - ch);
             // ---- stage: where the item's rows and columns of this tile sit
             if(tid < nch)
             {
@@ -346,53 +385,58 @@ schur_tiles_kernel(NormalBuffers N, double lambda, int n_c, int nblk, bool add_l
                 }
             }
             __syncthreads();
-            // ---- accumulate: warp `warp` owns the tile rows = warp (mod 8), so no two warps ever touch the same entry,
-            // and every entry sees its contributions in item order
-            for(int i = 0; i < nch; i++)
+            // ---- accumulate. Warp `warp` owns the tile rows = warp (mod 8): no two warps ever touch the same entry, and
+            // every entry sees its contributions in item order. A "task" is one owned row of one item (<= 64 values,
+            // two per lane); tasks are taken 8 at a time so that their loads are in flight together
             {
-                const int a0 = sa.meta[i][0] & 255, na = sa.meta[i][0] >> 8;
-                const int b0 = sa.meta[i][1] & 255, nb = sa.meta[i][1] >> 8;
-                if(na == 0 || nb == 0) continue;
-                const int lda = sa.meta[i][2];
-                const double* __restrict__ A = N.wi_A + sa.base[i];
-                const unsigned m0 = __ballot_sync(0xffffffffu, lane < na && (sa.rl[i][lane] & 7) == warp);
-                const unsigned m1 = __ballot_sync(0xffffffffu, lane + 32 < na && (sa.rl[i][lane + 32] & 7) == warp);
-                const int cb0 = lane < nb ? sa.cl[i][lane] : 0;
-                const int cb1 = lane + 32 < nb ? sa.cl[i][lane + 32] : 0;
-#pragma unroll
-                for(int half = 0; half < 2; half++)
+                int ti = -1;
+                unsigned cur0 = 0, cur1 = 0;
+                bool exhausted = false;
+                while(!exhausted || cur0 || cur1)
                 {
-                    unsigned m = half ? m1 : m0;
-                    while(m)
+                    int t_item[8], t_row[8];
+                    double v0[8], v1[8];
+                    int cnt = 0;
+#pragma unroll
+                    for(int u = 0; u < 8; u++)
                     {
-                        // up to 4 rows at a time: their loads go out together
-                        int ar[4];
-                        double v0[4], v1[4];
-#pragma unroll
-                        for(int u = 0; u < 4; u++)
+                        t_item[u] = -1;
+                        while(!exhausted && cur0 == 0 && cur1 == 0)
                         {
-                            ar[u] = -1; v0[u] = v1[u] = 0.;
-                            if(m) { ar[u] = 32 * half + __ffs(m) - 1; m &= m - 1; }
+                            ti++;
+                            if(ti >= nch) { exhausted = true; break; }
+                            const int na = sa.meta[ti][0] >> 8, nb = sa.meta[ti][1] >> 8;
+                            if(na == 0 || nb == 0) continue;
+                            cur0 = __ballot_sync(0xffffffffu, lane < na && (sa.rl[ti][lane] & 7) == warp);
+                            cur1 = __ballot_sync(0xffffffffu, lane + 32 < na && (sa.rl[ti][lane + 32] & 7) == warp);
                         }
+                        if(cur0) { t_item[u] = ti; t_row[u] = __ffs(cur0) - 1; cur0 &= cur0 - 1; cnt++; }
+                        else if(cur1) { t_item[u] = ti; t_row[u] = 32 + __ffs(cur1) - 1; cur1 &= cur1 - 1; cnt++; }
+                    }
+                    if(cnt == 0) break;
 #pragma unroll
-                        for(int u = 0; u < 4; u++)
-                        {
-                            if(ar[u] < 0) continue;
-                            const int a = a0 + ar[u];
-                            // lower triangle of the item's block: local column <= local row (always true off the diagonal tiles)
-                            const double* row = A + (size_t)a * lda + b0;
-                            if(lane < nb && b0 + lane <= a) v0[u] = __ldg(row + lane);
-                            if(lane + 32 < nb && b0 + lane + 32 <= a) v1[u] = __ldg(row + lane + 32);
-                        }
+                    for(int u = 0; u < 8; u++)
+                    {
+                        v0[u] = v1[u] = 0.;
+                        if(t_item[u] < 0) continue;
+                        const int i = t_item[u];
+                        const int a = (sa.meta[i][0] & 255) + t_row[u];
+                        const int b0 = sa.meta[i][1] & 255, nb = sa.meta[i][1] >> 8;
+                        // lower triangle of the item's block: local column <= local row (always true off the diagonal tiles)
+                        const double* row = N.wi_A + sa.base[i] + (size_t)a * sa.meta[i][2] + b0;
+                        if(lane < nb && b0 + lane <= a) v0[u] = __ldg(row + lane);
+                        if(lane + 32 < nb && b0 + lane + 32 <= a) v1[u] = __ldg(row + lane + 32);
+                    }
 #pragma unroll
-                        for(int u = 0; u < 4; u++)
-                        {
-                            if(ar[u] < 0) continue;
-                            const int a = a0 + ar[u];
-                            double* trow = sa.tile + (int)sa.rl[i][ar[u]] * TLD;
-                            if(lane < nb && b0 + lane <= a) trow[cb0] += v0[u];
-                            if(lane + 32 < nb && b0 + lane + 32 <= a) trow[cb1] += v1[u];
-                        }
+                    for(int u = 0; u < 8; u++)
+                    {
+                        if(t_item[u] < 0) continue;
+                        const int i = t_item[u];
+                        const int a = (sa.meta[i][0] & 255) + t_row[u];
+                        const int b0 = sa.meta[i][1] & 255, nb = sa.meta[i][1] >> 8;
+                        double* trow = sa.tile + (int)sa.rl[i][t_row[u]] * TLD;
+                        if(lane < nb && b0 + lane <= a) trow[sa.cl[i][lane]] += v0[u];
+                        if(lane + 32 < nb && b0 + lane + 32 <= a) trow[sa.cl[i][lane + 32]] += v1[u];
                     }
                 }
             }
@@ -401,7 +445,7 @@ schur_tiles_kernel(NormalBuffers N, double lambda, int n_c, int nblk, bool add_l
     }
 
     ////////////////////////////// phase S: minus the groups' Y'Y, through the tensor pipe
-    // accumulators start at -tile and collect +Y'Y: S = -acc. 8 warps as 4 x 2, warp tile 16 x 32
+    // accumulators start at -tile and collect +Y'Y: the tile is -acc. 8 warps as 4 x 2, warp tile 16 x 32
     const int wm = warp >> 1, wn = warp & 1, g = lane >> 2, t = lane & 3;
     double acc[2][4][2];
 #pragma unroll
@@ -414,10 +458,15 @@ schur_tiles_kernel(NormalBuffers N, double lambda, int n_c, int nblk, bool add_l
             acc[a][b][1] = -v.y;
         }
     __syncthreads();
-    for(int w0 = 0; w0 < N.gwords && N.Ngroups > 0; w0 += 64)
+    seen = 0;
+    for(int w0 = 0; w0 < N.gwords && N.Ngroups > 0 && seen < grp_hi; w0 += 64)
     {
-        build_worklist(sc, N.grp_present + (size_t)r * N.gwords, N.grp_present + (size_t)c * N.gwords, w0, min(w0 + 64, N.gwords));
-        const int nwl = sc.count;
+        build_worklist(sc, grA, grB, w0, min(w0 + 64, N.gwords));
+        const int nwl_all = sc.count;
+        const int lo = max(grp_lo - seen, 0), hi = min(grp_hi - seen, nwl_all);
+        seen += nwl_all;
+        const int nwl = hi - lo;
+        if(nwl <= 0) continue;
         const int nchunks = (nwl + kChunkGroups - 1) / kChunkGroups;
         // rows 6 i .. 6 i + 5 of the K panel <- group i of the chunk; 32 16-byte pieces per row. Rows up to the next
         // multiple of 4 past the last group are zeroed
@@ -434,14 +483,14 @@ schur_tiles_kernel(NormalBuffers N, double lambda, int n_c, int nblk, bool add_l
                 if(row < 6 * ng)
                 {
                     const int gi = row / 6, p = row - gi * 6;
-                    const int grp = sc.wl[chunk * kChunkGroups + gi];
+                    const int grp = sc.wl[lo + chunk * kChunkGroups + gi];
                     const double* src = N.Ypan + ((size_t)grp * N.nblk_max + (side == 0 ? r : c)) * (6 * TB) + p * TB + 2 * piece;
                     cp16(dst, src);
                 }
                 else { dst[0] = 0.; dst[1] = 0.; }
             }
         };
-        if(nchunks > 0) stage(0, 0);
+        stage(0, 0);
         cp_commit();
         for(int ch = 0; ch < nchunks; ch++)
         {
@@ -469,11 +518,45 @@ schur_tiles_kernel(NormalBuffers N, double lambda, int n_c, int nblk, bool add_l
         }
     }
 
+    ////////////////////////////// a split tile: leave the partial sum; the last part to arrive adds them up in part order
+    if(parts > 1)
+    {
+        double* mine = part_scratch + ((size_t)itile * kMaxParts + part) * (TB * TB);
+#pragma unroll
+        for(int a = 0; a < 2; a++)
+#pragma unroll
+            for(int b = 0; b < 4; b++)
+                *reinterpret_cast<double2*>(&mine[(wm * 16 + a * 8 + g) * TB + wn * 32 + b * 8 + 2 * t]) = make_double2(acc[a][b][0], acc[a][b][1]);
+        __threadfence();
+        __syncthreads();
+        if(tid == 0) s_last = atomicAdd(&part_arrive[itile], 1) == parts - 1;
+        __syncthreads();
+        if(!s_last) return;
+        __threadfence();
+#pragma unroll
+        for(int a = 0; a < 2; a++)
+#pragma unroll
+            for(int b = 0; b < 4; b++) acc[a][b][0] = acc[a][b][1] = 0.;
+        for(int p = 0; p < parts; p++)
+        {
+            const double* src = part_scratch + ((size_t)itile * kMaxParts + p) * (TB * TB);
+#pragma unroll
+            for(int a = 0; a < 2; a++)
+#pragma unroll
+                for(int b = 0; b < 4; b++)
+                {
+                    const double2 v = __ldcg(reinterpret_cast<const double2*>(&src[(wm * 16 + a * 8 + g) * TB + wn * 32 + b * 8 + 2 * t]));
+                    acc[a][b][0] += v.x;
+                    acc[a][b][1] += v.y;
+                }
+        }
+    }
+
     ////////////////////////////// sharded solve: the raw tile goes to the tile-packed buffer (lower-triangle tiles only, each
     // contiguous) that is all-reduced; unpack_tiles_kernel finishes the job on the sum
     if(packed != nullptr)
     {
-        double* dstt = packed + (size_t)(r * (r + 1) / 2 + c) * (TB * TB);
+        double* dstt = packed + (size_t)itile * (TB * TB);
 #pragma unroll
         for(int a = 0; a < 2; a++)
 #pragma unroll
@@ -683,7 +766,9 @@ bool normal_det_finish(const DevProblem& dp, NormalBuffers& N, const EvalBuffers
     }
     const bool sharded = comm_active();
     if(sharded && N.S_packed == nullptr) { set_error("internal error: sharded solve without the packed tile buffer"); return false; }
-    schur_tiles_kernel<<<ntiles, 256, kTileSmem, s>>>(N, lambda, N.n_c, nblk, true, sharded ? N.S_packed : nullptr);
+    MB200_CUDA_CHECK(cudaMemsetAsync(N.part_arrive, 0, (size_t)kSplitTilesCap * sizeof(int), s));
+    schur_tiles_kernel<<<dim3(ntiles, kMaxParts), 256, kTileSmem, s>>>(N, lambda, N.n_c, nblk, true, sharded ? N.S_packed : nullptr,
+                                                                      N.part_scratch, N.part_arrive);
     (*nlaunch)++;
     if(sharded)
     {
@@ -705,6 +790,10 @@ bool normal_det_finish(const DevProblem& dp, NormalBuffers& N, const EvalBuffers
     MB200_CUDA_CHECK(cudaGetLastError());
     return true;
 }
+
+// what the workspace must provide for the split tiles
+size_t normal_det_part_scratch_doubles() { return (size_t)kSplitTilesCap * kMaxParts * TB * TB; }
+int normal_det_part_arrive_ints() { return kSplitTilesCap; }
 
 bool normal_det_rhs(const NormalBuffers& N, cudaStream_t s, int* nlaunch)
 {
