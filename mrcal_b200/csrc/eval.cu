@@ -160,10 +160,11 @@ eval_boards_kernel(DevProblem P, double* __restrict__ x, double* __restrict__ Jv
     __shared__ ObsGeometry G;
     __shared__ double red[32];
     __shared__ int s_ivar0[256];   // per corner: where its spline window starts (the only data-dependent column index)
-    // Jacobian staging: each thread (corner) deposits the VALUES of its two rows in shared memory (odd row stride: no bank
-    // conflicts); the CTA packs them into one linear block -- the rows of an observation are contiguous in J -- and ONE
-    // TMA bulk copy (cp.async.bulk shared -> global) writes the whole block. The column indices are not staged at all:
-    // they are a function of (corner, entry) and are written straight from registers, coalesced.
+    // Jacobian staging: each thread (corner) deposits the VALUES of its two rows here -- 2*nnz_row contiguous
+    // doubles, which is also how they sit in J -- and hands them to the TMA: one bulk shared->global copy per
+    // corner (cp.async.bulk), no thread spends time on the value stores. The column indices are not staged at all:
+    // they are a function of (corner, entry) and are written straight from registers, coalesced, a warp per corner.
+    // The row stride is 2 (mod 4) doubles: 16-byte aligned for the bulk copy, 2-way bank conflicts at worst
     extern __shared__ __align__(16) double stage_v[];
 
     const int iobs   = blockIdx.x;
@@ -199,9 +200,9 @@ eval_boards_kernel(DevProblem P, double* __restrict__ x, double* __restrict__ Jv
     const int NWH         = P.W * P.H;
     const double wx2 = P.u_warp[0], wy2 = P.u_warp[1];
 
-    const int row2 = 2 * nnz_row, stride = row2 + 1;
-    double* lin_v = stage_v + (size_t)blockDim.x * stride + 1;
-    lin_v = reinterpret_cast<double*>((reinterpret_cast<size_t>(lin_v) + 15) & ~(size_t)15);   // 16-byte aligned for the bulk copy
+    const int row2 = 2 * nnz_row;
+    int stride = row2;
+    while((stride & 3) != 2) stride++;
     const int nI = P.nnz_row_intr;
 
     double sumsq = 0.;
@@ -331,57 +332,61 @@ eval_boards_kernel(DevProblem P, double* __restrict__ x, double* __restrict__ Jv
                 }
             }
             s_ivar0[threadIdx.x] = ivar0s;
+            // this corner's 2 rows: one bulk copy, shared -> global, issued by the thread that wrote them. The fence makes
+            // the generic-proxy writes above visible to the async proxy that reads them
+            {
+                double* gdst = Jval + (size_t)P.board_j0[iobs] + (size_t)ipt * row2;
+                const unsigned ssrc = (unsigned)__cvta_generic_to_shared(stage_v + (size_t)threadIdx.x * stride);
+                asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");
+                asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;\n"
+                             ::"l"(gdst), "r"(ssrc), "r"(row2 * 8) : "memory");
+                asm volatile("cp.async.bulk.commit_group;\n" ::: "memory");
+            }
         }
       }
       if constexpr(WITH_J)
       {
-        // the column indices of this chunk of corners: entries [ipt0*row2, (ipt0+nhere)*row2) of the observation's block
+        // the column indices of this chunk of corners: a warp per corner, a lane per entry (coalesced stores; no divisions
+        // by run-time values on the way)
         __syncthreads();
         const int nhere = min((int)blockDim.x, NWH - ipt0);
         const size_t gbase = (size_t)P.board_j0[iobs] + (size_t)ipt0 * row2;
         const int ncore = P.opt_core ? 2 : 0;
-        for(int g = threadIdx.x; g < nhere * row2; g += blockDim.x)
+        const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+        for(int t = wib; t < nhere; t += nwarps)
         {
-            const int t = g / row2, e = g - t * row2;
-            const int i_xy = e >= nnz_row ? 1 : 0, k = e - i_xy * nnz_row;
-            int col;
-            if(k < nI)
+            const int iv0 = s_ivar0[t];
+            for(int e = lane; e < row2; e += 32)
             {
-                if(k < ncore) col = i_var_intr + i_xy + 2 * k;
-                else if constexpr(LensTraits<KIND>::SPLINED)
+                const int i_xy = e >= nnz_row ? 1 : 0, k = e - i_xy * nnz_row;
+                int col;
+                if(k < nI)
                 {
-                    constexpr int RUN = LensTraits<KIND>::RUN;
-                    const int kk = k - ncore, iy = kk / RUN, ix = kk - iy * RUN;
-                    col = i_var_intr + s_ivar0[t] + iy * 2 * P.Nx + ix * 2 + i_xy;
+                    if(k < ncore) col = i_var_intr + i_xy + 2 * k;
+                    else if constexpr(LensTraits<KIND>::SPLINED)
+                    {
+                        constexpr int RUN = LensTraits<KIND>::RUN;
+                        const int kk = k - ncore, iy = kk / RUN, ix = kk - iy * RUN;   // RUN is a compile-time 3 or 4
+                        col = i_var_intr + iv0 + iy * 2 * P.Nx + ix * 2 + i_xy;
+                    }
+                    else col = i_var_intr + P.Ncore_state + (k - ncore);
                 }
-                else col = i_var_intr + P.Ncore_state + (k - ncore);
-            }
-            else
-            {
-                int kk = k - nI;
-                if(emit_cam && kk < 6) col = i_var_cam + kk;
                 else
                 {
-                    if(emit_cam) kk -= 6;
-                    if(P.opt_frames && kk < 6) col = i_var_frame + kk;
-                    else { if(P.opt_frames) kk -= 6; col = P.i_warp0 + kk; }
+                    int kk = k - nI;
+                    if(emit_cam && kk < 6) col = i_var_cam + kk;
+                    else
+                    {
+                        if(emit_cam) kk -= 6;
+                        if(P.opt_frames && kk < 6) col = i_var_frame + kk;
+                        else { if(P.opt_frames) kk -= 6; col = P.i_warp0 + kk; }
+                    }
                 }
+                Jcol[gbase + (size_t)t * row2 + e] = col;
             }
-            Jcol[gbase + g] = col;
-            lin_v[g] = stage_v[(size_t)t * stride + e];
         }
-        // the packed block: one bulk copy, shared -> global. The fence makes the generic-proxy writes above visible to
-        // the async proxy that reads them; the buffers are reused by the next chunk of corners only after the TMA has READ them
-        asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");
-        __syncthreads();
-        if(threadIdx.x == 0)
-        {
-            const unsigned ssrc = (unsigned)__cvta_generic_to_shared(lin_v);
-            asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;\n"
-                         ::"l"(Jval + gbase), "r"(ssrc), "r"(nhere * row2 * 8) : "memory");
-            asm volatile("cp.async.bulk.commit_group;\n" ::: "memory");
-            asm volatile("cp.async.bulk.wait_group.read 0;\n" ::: "memory");
-        }
+        // the staging buffer is reused by the next chunk of corners: wait until the TMA has READ it
+        asm volatile("cp.async.bulk.wait_group.read 0;\n" ::: "memory");
         __syncthreads();
       }
     }
@@ -768,7 +773,9 @@ static bool launch_kind(const DevProblem& dp, const EvalBuffers& out, bool with_
         {
             // widest row: extrinsics present
             const int row2 = 2 * (dp.nnz_row_intr + (dp.opt_extr ? 6 : 0) + dp.nnz_row_board_geom);
-            const size_t smem = ((size_t)threads * (row2 + 1) + (size_t)threads * row2 + 4) * sizeof(double) + 16;
+            int stride = row2;
+            while((stride & 3) != 2) stride++;
+            const size_t smem = (size_t)threads * stride * sizeof(double) + 16;
             // cudaFuncSetAttribute is per device: one flag per (device, lens kind)
             static bool configured[kMaxDevices][LENS_NKINDS] = {};
             int dev = 0;

@@ -27,12 +27,17 @@ mrcal_b200_problem_t* capi_steal_cached_problem();   // capi.cu
 namespace {
 constexpr int TB = 64;
 
-// rows n_c, n_c+1 of the factor carry the solver's right-hand side: here they become plain padding
-__global__ void clear_aug_rows_kernel(NormalBuffers N, int n_c)
+// rows n_c, n_c+1 of the factor carry the solver's right-hand side: here they become plain padding -- in L and in the
+// stored inverses of its diagonal blocks (row m of the inverse of a lower-triangular block depends on rows <= m only)
+__global__ void clear_aug_rows_kernel(NormalBuffers N, int n_c, double* __restrict__ invL)
 {
     const int c = blockIdx.x * blockDim.x + threadIdx.x;
     if(c >= N.ldS) return;
-    for(int r = n_c; r < n_c + 2 && r < N.ldS; r++) N.S[(size_t)r * N.ldS + c] = (c == r) ? 1. : 0.;
+    for(int r = n_c; r < n_c + 2 && r < N.ldS; r++)
+    {
+        N.S[(size_t)r * N.ldS + c] = (c == r) ? 1. : 0.;
+        if((c >> 6) == (r >> 6)) invL[(size_t)(r >> 6) * (TB * TB) + (r & 63) * TB + (c & 63)] = (c == r) ? 1. : 0.;
+    }
 }
 
 // Cholesky factors of the regularization blocks of the uncoupled shared unknowns (what inactive_step_kernel inverts)
@@ -378,7 +383,7 @@ extern "C" mrcal_b200_factorization_t* mrcal_b200_factorization_create_from_last
     if(!N.det) return fail("structured factorization: this problem takes the other assembly path");
     int h_info[2] = {0, 0}, h_bad = 0;
     if(N.n_c > 0 && !chol_factor(N.S, N.ldS, N.n_c, ws->invL, N.info + 1, s, &nl, &ws->chol)) { schur_factorization_release(F.get()); return nullptr; }
-    clear_aug_rows_kernel<<<(N.ldS + 255) / 256, 256, 0, s>>>(N, N.n_c);
+    clear_aug_rows_kernel<<<(N.ldS + 255) / 256, 256, 0, s>>>(N, N.n_c, ws->invL);
     int* d_bad = nullptr;
     if(!F->arena.alloc(&F->ia_L, 3 * (size_t)(N.n_r > 0 ? N.n_r : 1), true) || !F->arena.alloc(&F->ia_first, 2 * (size_t)(N.n_r > 0 ? N.n_r : 1), true) ||
        !F->arena.alloc(&F->minmax, 2) || !F->arena.alloc(&d_bad, 1, true)) { schur_factorization_release(F.get()); return nullptr; }

@@ -408,32 +408,31 @@ sum_norm_partials_kernel(const double* __restrict__ part, int n, double* __restr
     if(tid == 0) *norm2 += s[0];
 }
 
-// |J g|^2 over the board rows from the blocks: g_w' [A B'; B D] g_w per observation. part[w] = that. One warp per item;
-// the lanes run along a row of A (coalesced), the rows are taken one after the other
-__global__ void __launch_bounds__(256)
+// |J g|^2 over the board rows from the blocks: g_w' [A B'; B D] g_w per observation. part[w] = that. One CTA per item, one
+// entry of the lower triangle of A per thread and step (all loads independent); the per-thread sums are added in a fixed tree
+__global__ void __launch_bounds__(128)
 quadform_items_kernel(DevProblem P, NormalBuffers N, const double* __restrict__ g_full, int Nitems, double* __restrict__ part)
 {
-    __shared__ double s_g[8][168];
-    const int wib = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int w = blockIdx.x * 8 + wib;
-    if(w >= Nitems) return;
+    __shared__ double s_g[168];
+    __shared__ double s_red[128];
+    const int w = blockIdx.x, tid = threadIdx.x;
     const int nsh = N.wi_nsh[w], lda = N.wi_lda[w];
     const double* A = N.wi_A + N.wi_Aoff[w];
     const int* cols = N.wi_cols + (size_t)w * N.cap;
     const int iframe = P.obs_board[3 * w + 2];
-    double* gl = s_g[wib];
-    for(int i = lane; i < nsh; i += 32) gl[i] = g_full[N.state_index(cols[i])];
-    __syncwarp();
+    for(int i = tid; i < nsh; i += 128) s_g[i] = g_full[N.state_index(cols[i])];
+    __syncthreads();
     double q = 0.;
-    // shared x shared (A symmetric, lower stored): sum_i g_i (A_ii g_i + 2 sum_{j<i} A_ij g_j)
-    for(int i = 0; i < nsh; i++)
+    // shared x shared (A symmetric, lower stored): sum over i >= j of (2 - [i == j]) g_i A_ij g_j
+    const int nent = nsh * (nsh + 1) / 2;
+    for(int e = tid; e < nent; e += 128)
     {
-        const double* row = A + (size_t)i * lda;
-        double sv = 0.;
-        for(int j = lane; j < i; j += 32) sv += row[j] * gl[j];
-        if(lane == (i & 31)) sv = 2. * sv + row[i] * gl[i];
-        else sv = 2. * sv;
-        q += gl[i] * sv;
+        int i = (int)((sqrtf(8.f * e + 1.f) - 1.f) * 0.5f);
+        while(i * (i + 1) / 2 > e) i--;
+        while((i + 1) * (i + 2) / 2 <= e) i++;
+        const int j = e - i * (i + 1) / 2;
+        const double v = A[(size_t)i * lda + j] * s_g[i] * s_g[j];
+        q += i == j ? v : 2. * v;
     }
     // frame: 2 g_f' B g_s + g_f' D g_f
     if(P.opt_frames)
@@ -441,22 +440,23 @@ quadform_items_kernel(DevProblem P, NormalBuffers N, const double* __restrict__ 
         const double* B = N.wi_B + (size_t)w * 6 * N.cap;
         double gf[6];
         for(int p = 0; p < 6; p++) gf[p] = g_full[P.i_frame0 + 6 * iframe + p];
-        for(int i = lane; i < nsh; i += 32)
+        for(int i = tid; i < nsh; i += 128)
         {
             double sv = 0.;
             for(int p = 0; p < 6; p++) sv += gf[p] * B[(size_t)p * N.cap + i];
-            q += 2. * gl[i] * sv;
+            q += 2. * s_g[i] * sv;
         }
-        if(lane == 0)
+        if(tid == 0)
         {
             const double* D = N.wi_D + (size_t)w * 36;
             for(int p = 0; p < 6; p++)
                 for(int rr = 0; rr < 6; rr++) q += gf[p] * D[p * 6 + rr] * gf[rr];
         }
     }
-#pragma unroll
-    for(int o = 16; o > 0; o >>= 1) q += __shfl_xor_sync(0xffffffffu, q, o);
-    if(lane == 0) part[w] = q;
+    s_red[tid] = q;
+    __syncthreads();
+    for(int o = 64; o > 0; o >>= 1) { if(tid < o) s_red[tid] += s_red[tid + o]; __syncthreads(); }
+    if(tid == 0) part[w] = s_red[0];
 }
 __global__ void __launch_bounds__(256)
 sum_partials_to_kernel(const double* __restrict__ part, int n, double* __restrict__ out)
@@ -501,7 +501,7 @@ bool launch_fused_boards(const DevProblem& dp, NormalBuffers& N, const EvalBuffe
 bool launch_quadform_boards(const DevProblem& dp, const NormalBuffers& N, const double* g_full, double* part, double* out, cudaStream_t s, int* nlaunch)
 {
     if(dp.Nobs_board <= 0) return true;
-    quadform_items_kernel<<<(dp.Nobs_board + 7) / 8, 256, 0, s>>>(dp, N, g_full, dp.Nobs_board, part);
+    quadform_items_kernel<<<dp.Nobs_board, 128, 0, s>>>(dp, N, g_full, dp.Nobs_board, part);
     sum_partials_to_kernel<<<1, 256, 0, s>>>(part, dp.Nobs_board, out);
     *nlaunch += 2;
     MB200_CUDA_CHECK(cudaGetLastError());
