@@ -83,14 +83,16 @@ __global__ void csr_chunk_fill_kernel(const int* __restrict__ col, const int* __
     }
 }
 
-// y[c] = sum over the entries of column c, in row order. One warp per column would reorder the sum: one thread each
+// y[c] = sum over the entries of column c, in row order. One warp per column would reorder the sum: one thread each.
+// Product and sum are rounded separately (no fused multiply-add), as the reference's x86 loop does
+// (mrcal-genpywrap.py:505-520): the result is the same to the last bit
 __global__ void csr_jt_x_kernel(const int* __restrict__ tp, const int* __restrict__ tsrc, const int* __restrict__ trow,
                                 const double* __restrict__ val, const double* __restrict__ x, int Ncols, double* __restrict__ y)
 {
     const int c = blockIdx.x * blockDim.x + threadIdx.x;
     if(c >= Ncols) return;
     double s = 0.;
-    for(int k = tp[c]; k < tp[c + 1]; k++) s += val[tsrc[k]] * x[trow[k]];
+    for(int k = tp[c]; k < tp[c + 1]; k++) s = __dadd_rn(s, __dmul_rn(val[tsrc[k]], x[trow[k]]));
     y[c] = s;
 }
 

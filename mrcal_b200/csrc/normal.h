@@ -106,7 +106,7 @@ bool normal_det_finish(const DevProblem& dp, NormalBuffers& N, const EvalBuffers
 bool normal_det_item_prepare(const DevProblem& dp, NormalBuffers& N, cudaStream_t s, int* nlaunch);   // after the compaction
 bool normal_det_item_offsets(const DevProblem& dp, NormalBuffers& N, cudaStream_t s, int* nlaunch);   // before it
 size_t normal_det_part_scratch_doubles();
-int normal_det_part_arrive_ints();
+int normal_det_part_arrive_ints(int nblk_max);
 bool normal_det_rhs(const NormalBuffers& N, cudaStream_t s, int* nlaunch);   // after the cross-rank reduction of S
 bool normal_det_backsub(const NormalBuffers& N, const double* sol_compact, double* step_full, cudaStream_t s, int* nlaunch);
 

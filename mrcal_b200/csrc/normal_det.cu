@@ -42,15 +42,6 @@ constexpr int TLD = 68;         // row stride of tiles and panels in shared memo
 constexpr int kChunkItems = 64; // phase A: items staged per chunk
 constexpr int kChunkGroups = 6; // phase S: groups per K chunk (36 rows); two CTAs of ~88 KB per SM
 
-__device__ __forceinline__ void cp16(void* smem, const void* gmem)
-{
-    const unsigned s = (unsigned)__cvta_generic_to_shared(smem);
-    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(s), "l"(gmem));
-}
-__device__ __forceinline__ void cp_commit() { asm volatile("cp.async.commit_group;\n" ::); }
-__device__ __forceinline__ void cp_wait_all() { asm volatile("cp.async.wait_group 0;\n" ::); }
-__device__ __forceinline__ void cp_wait_one() { asm volatile("cp.async.wait_group 1;\n" ::); }
-
 }  // namespace
 
 // exclusive scan of lda^2 over the items: one CTA
@@ -241,7 +232,8 @@ struct alignas(16) TileCommon
     int wl[2048];      // items (or groups) that reach both blocks of the tile
     int scan[256];
     int count;
-    int pad[3];        // what follows in shared memory is accessed 16 bytes at a time (cp.async, double2)
+    int pad[3];        // what follows in shared memory is accessed 16 bytes at a time (bulk copies, double2)
+    unsigned long long bar[2];   // mbarriers of the two panel buffers of phase S
 };
 static_assert(sizeof(TileCommon) % 16 == 0, "the tile and the staging buffers behind TileCommon need 16-byte alignment");
 struct alignas(16) TileSmemA
@@ -281,24 +273,73 @@ __device__ __forceinline__ void build_worklist(TileCommon& sm, const unsigned* r
     if(tid == 255) sm.count = sm.scan[255];
     __syncthreads();
 }
-// how many ids the worklists of a tile will hold in total
-__device__ __forceinline__ int count_common(TileCommon& sm, const unsigned* rowA, const unsigned* rowB, int nwords)
+// ---- mbarrier / bulk-copy (TMA) plumbing of phase S
+__device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(unsigned long long* bar, int count)
 {
-    const int tid = threadIdx.x;
-    int cnt = 0;
-    for(int w = tid; w < nwords; w += 256) cnt += __popc(rowA[w] & rowB[w]);
-    sm.scan[tid] = cnt;
-    __syncthreads();
-    for(int o = 128; o > 0; o >>= 1) { if(tid < o) sm.scan[tid] += sm.scan[tid + o]; __syncthreads(); }
-    const int total = sm.scan[0];
-    __syncthreads();
-    return total;
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;\n" :: "r"(smem_u32(bar)), "r"(count) : "memory");
 }
+__device__ __forceinline__ void mbar_arrive_expect_tx(unsigned long long* bar, unsigned bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n" :: "r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long* bar, unsigned parity)
+{
+    unsigned ok;
+    do
+    {
+        asm volatile("{\n.reg .pred p;\nmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\nselp.u32 %0, 1, 0, p;\n}\n"
+                     : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+    } while(!ok);
+}
+// global -> shared, `bytes` (a multiple of 16) contiguous; completion is counted on `bar`
+__device__ __forceinline__ void bulk_load(void* smem, const void* gmem, unsigned bytes, unsigned long long* bar)
+{
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];\n"
+                 :: "r"(smem_u32(smem)), "l"(gmem), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory"); }
 
 constexpr int kMaxParts = 8;          // a tile's contributors may be split over this many CTAs
-constexpr int kItemsPerPart = 96;
-constexpr int kGroupsPerPart = 48;
 constexpr int kSplitTilesCap = 2048;  // tiles with a slot in the partial-sum scratch (beyond: one CTA does it all)
+
+__device__ __forceinline__ void tile_row_col(int itile, int& r, int& c)
+{
+    r = (int)((sqrtf(8.f * itile + 1.f) - 1.f) * 0.5f);
+    while(r * (r + 1) / 2 > itile) r--;
+    while((r + 1) * (r + 2) / 2 <= itile) r++;
+    c = itile - r * (r + 1) / 2;
+}
+
+// What each tile has to sum, and over how many CTAs: plan[itile] = (items, groups, parts, -). One warp per tile
+__global__ void __launch_bounds__(256)
+tile_plan_kernel(NormalBuffers N, int nblk, int items_per_part, int groups_per_part, bool can_split, int4* __restrict__ plan)
+{
+    const int itile = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    if(itile >= nblk * (nblk + 1) / 2) return;
+    int r, c;
+    tile_row_col(itile, r, c);
+    const unsigned* wiA = N.wi_present + (size_t)r * N.wwords;
+    const unsigned* wiB = N.wi_present + (size_t)c * N.wwords;
+    int n_items = 0, n_groups = 0;
+    for(int w = lane; w < N.wwords; w += 32) n_items += __popc(wiA[w] & wiB[w]);
+    if(N.Ngroups > 0)
+    {
+        const unsigned* grA = N.grp_present + (size_t)r * N.gwords;
+        const unsigned* grB = N.grp_present + (size_t)c * N.gwords;
+        for(int w = lane; w < N.gwords; w += 32) n_groups += __popc(grA[w] & grB[w]);
+    }
+#pragma unroll
+    for(int o = 16; o > 0; o >>= 1)
+    {
+        n_items += __shfl_xor_sync(0xffffffffu, n_items, o);
+        n_groups += __shfl_xor_sync(0xffffffffu, n_groups, o);
+    }
+    int parts = max((n_items + items_per_part - 1) / items_per_part, (n_groups + groups_per_part - 1) / groups_per_part);
+    parts = min(kMaxParts, max(1, parts));
+    if(itile >= kSplitTilesCap || !can_split) parts = 1;
+    if(lane == 0) plan[itile] = make_int4(n_items, n_groups, parts, 0);
+}
 
 // One CTA per (64x64 tile of the lower triangle of S, part). A tile that many items / groups reach -- the block row of
 // the extrinsics, the board warp and the right-hand side reaches all of them -- is split: each part sums its share of
@@ -306,7 +347,7 @@ constexpr int kSplitTilesCap = 2048;  // tiles with a slot in the partial-sum sc
 // partial tiles up in part order. Which part is last varies; what it computes does not.
 __global__ void __launch_bounds__(256, 2)
 schur_tiles_kernel(NormalBuffers N, double lambda, int n_c, int nblk, bool add_lambda, double* __restrict__ packed,
-                   double* __restrict__ part_scratch, int* __restrict__ part_arrive)
+                   double* __restrict__ part_scratch, int* __restrict__ part_arrive, const int4* __restrict__ plan)
 {
     extern __shared__ __align__(16) unsigned char dsm_raw[];
     TileCommon& sc = *reinterpret_cast<TileCommon*>(dsm_raw);
@@ -315,25 +356,23 @@ schur_tiles_kernel(NormalBuffers N, double lambda, int n_c, int nblk, bool add_l
     __shared__ int s_last;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int itile = (nblk * (nblk + 1) / 2 - 1) - (int)blockIdx.x;   // the late rows first: they carry the most work
+    const int4 pl = plan[itile];
+    const int n_items = pl.x, n_groups = pl.y, parts = pl.z;
+    const int part = blockIdx.y;
+    if(part >= parts) return;
     int r, c;
-    {
-        r = (int)((sqrtf(8.f * itile + 1.f) - 1.f) * 0.5f);
-        while(r * (r + 1) / 2 > itile) r--;
-        while((r + 1) * (r + 2) / 2 <= itile) r++;
-        c = itile - r * (r + 1) / 2;
-    }
+    tile_row_col(itile, r, c);
     const bool diag = r == c;
     const unsigned* wiA = N.wi_present + (size_t)r * N.wwords;
     const unsigned* wiB = N.wi_present + (size_t)c * N.wwords;
     const unsigned* grA = N.grp_present + (size_t)r * N.gwords;
     const unsigned* grB = N.grp_present + (size_t)c * N.gwords;
-    const int n_items = count_common(sc, wiA, wiB, N.wwords);
-    const int n_groups = N.Ngroups > 0 ? count_common(sc, grA, grB, N.gwords) : 0;
-    int parts = max((n_items + kItemsPerPart - 1) / kItemsPerPart, (n_groups + kGroupsPerPart - 1) / kGroupsPerPart);
-    parts = min(kMaxParts, max(1, parts));
-    if(itile >= kSplitTilesCap || part_scratch == nullptr) parts = 1;
-    const int part = blockIdx.y;
-    if(part >= parts) return;
+    if(tid == 0)
+    {
+        mbar_init(&sc.bar[0], 1);
+        mbar_init(&sc.bar[1], 1);
+        asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
+    }
     const int item_lo = (int)((long)n_items * part / parts), item_hi = (int)((long)n_items * (part + 1) / parts);
     const int grp_lo = (int)((long)n_groups * part / parts), grp_hi = (int)((long)n_groups * (part + 1) / parts);
 
@@ -459,6 +498,7 @@ schur_tiles_kernel(NormalBuffers N, double lambda, int n_c, int nblk, bool add_l
         }
     __syncthreads();
     seen = 0;
+    unsigned bar_phase = 0;   // bit b: the parity the next wait on buffer b looks for
     for(int w0 = 0; w0 < N.gwords && N.Ngroups > 0 && seen < grp_hi; w0 += 64)
     {
         build_worklist(sc, grA, grB, w0, min(w0 + 64, N.gwords));
@@ -468,38 +508,48 @@ schur_tiles_kernel(NormalBuffers N, double lambda, int n_c, int nblk, bool add_l
         const int nwl = hi - lo;
         if(nwl <= 0) continue;
         const int nchunks = (nwl + kChunkGroups - 1) / kChunkGroups;
-        // rows 6 i .. 6 i + 5 of the K panel <- group i of the chunk; 32 16-byte pieces per row. Rows up to the next
-        // multiple of 4 past the last group are zeroed
+        // what the generic proxy wrote to this memory (phase A, the zero rows of an earlier stretch) comes before what
+        // the bulk copies write
+        fence_proxy_async();
+        __syncthreads();
+        // rows 6 i .. 6 i + 5 of the K panel <- group i of the chunk: one 512-byte bulk copy (TMA) per row and side, issued
+        // by one thread each, all counted on the buffer's mbarrier. No thread spends instructions on moving the data
+        const int sides = diag ? 1 : 2;
         auto stage = [&](int chunk, int buf)
         {
             const int ng = min(kChunkGroups, nwl - chunk * kChunkGroups);
-            const int krows = (6 * ng + 3) & ~3;
-            const int sides = diag ? 1 : 2;
-            for(int e = tid; e < sides * krows * 32; e += 256)
+            const int nrows = 6 * ng;
+            if(tid == 0) mbar_arrive_expect_tx(&sc.bar[buf], (unsigned)(sides * nrows * TB * sizeof(double)));
+            if(tid < sides * nrows)
             {
-                const int side = e / (krows * 32), rem = e - side * (krows * 32);
-                const int row = rem >> 5, piece = rem & 31;
-                double* dst = side == 0 ? &ss.R[buf][row][2 * piece] : &ss.C[buf][row][2 * piece];
-                if(row < 6 * ng)
-                {
-                    const int gi = row / 6, p = row - gi * 6;
-                    const int grp = sc.wl[lo + chunk * kChunkGroups + gi];
-                    const double* src = N.Ypan + ((size_t)grp * N.nblk_max + (side == 0 ? r : c)) * (6 * TB) + p * TB + 2 * piece;
-                    cp16(dst, src);
-                }
-                else { dst[0] = 0.; dst[1] = 0.; }
+                const int side = tid >= nrows ? 1 : 0, row = tid - side * nrows;
+                const int gi = row / 6, p = row - gi * 6;
+                const int grp = sc.wl[lo + chunk * kChunkGroups + gi];
+                const double* src = N.Ypan + ((size_t)grp * N.nblk_max + (side == 0 ? r : c)) * (6 * TB) + p * TB;
+                bulk_load(side == 0 ? &ss.R[buf][row][0] : &ss.C[buf][row][0], src, (unsigned)(TB * sizeof(double)), &sc.bar[buf]);
             }
         };
         stage(0, 0);
-        cp_commit();
         for(int ch = 0; ch < nchunks; ch++)
         {
             const int buf = ch & 1;
-            if(ch + 1 < nchunks) { stage(ch + 1, buf ^ 1); cp_commit(); cp_wait_one(); }
-            else cp_wait_all();
-            __syncthreads();
+            if(ch + 1 < nchunks) stage(ch + 1, buf ^ 1);   // (that buffer was read last in iteration ch-1, which ended with a barrier)
+            mbar_wait(&sc.bar[buf], (bar_phase >> buf) & 1u);
+            bar_phase ^= 1u << buf;
             const int ng = min(kChunkGroups, nwl - ch * kChunkGroups);
             const int ksteps = (6 * ng + 3) >> 2;
+            if(6 * ng < 4 * ksteps)
+            {
+                // the K rows up to the next multiple of 4: zeros (only ever in the last chunk of a stretch)
+                const int npad = 4 * ksteps - 6 * ng;
+                for(int e = tid; e < sides * npad * TB; e += 256)
+                {
+                    const int side = e / (npad * TB), rem = e - side * (npad * TB);
+                    const int row = 6 * ng + rem / TB, col = rem & (TB - 1);
+                    (side == 0 ? ss.R[buf][row] : ss.C[buf][row])[col] = 0.;
+                }
+                __syncthreads();
+            }
             const double* Rb = &ss.R[buf][0][0];
             const double* Cb = diag ? Rb : &ss.C[buf][0][0];
             for(int ks = 0; ks < ksteps; ks++)
@@ -687,18 +737,22 @@ __global__ void finish_rhs_kernel(NormalBuffers N, int n_c)
     N.S[(size_t)(n_c + 1) * N.ldS + c] = 0.;
 }
 
-// df_g = -inv(L_D)' (h + Y ds): one warp per group, over the blocks the group reaches. sol: the compact solution
-__global__ void __launch_bounds__(256)
+// df_g = -inv(L_D)' (h + Y ds): one CTA of 4 warps per group; warp w takes the blocks w, w+4, ... the group reaches, the
+// four partial sums are added in warp order. sol: the compact solution
+__global__ void __launch_bounds__(128)
 backsub_panels_kernel(NormalBuffers N, const double* __restrict__ sol, double* __restrict__ step_full, int nblk)
 {
-    const int grp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
-    if(grp >= N.Ngroups) return;
+    __shared__ double s_part[4][6];
+    const int grp = blockIdx.x, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int nelim = grp < N.Nframe_groups ? 6 : 3;
     const double* Yg = N.Ypan + (size_t)grp * N.nblk_max * (6 * TB);
+    const unsigned* mask = N.grp_blkmask + (size_t)grp * N.bwords;
     double tsum[6] = {0., 0., 0., 0., 0., 0.};
+    int seen = 0;   // present blocks so far: the k-th present block goes to warp k mod 4 (an even share whatever the pattern)
     for(int b = 0; b < nblk; b++)
     {
-        if(!((N.grp_blkmask[(size_t)grp * N.bwords + (b >> 5)] >> (b & 31)) & 1u)) continue;
+        if(!((mask[b >> 5] >> (b & 31)) & 1u)) continue;
+        if(((seen++) & 3) != warp) continue;
         const double d0 = sol[TB * b + lane], d1 = sol[TB * b + 32 + lane];
 #pragma unroll
         for(int p = 0; p < 6; p++)
@@ -706,14 +760,20 @@ backsub_panels_kernel(NormalBuffers N, const double* __restrict__ sol, double* _
     }
 #pragma unroll
     for(int p = 0; p < 6; p++)
+    {
 #pragma unroll
         for(int o = 16; o > 0; o >>= 1) tsum[p] += __shfl_xor_sync(0xffffffffu, tsum[p], o);
-    if(lane < nelim)
+        if(lane == 0) s_part[warp][p] = tsum[p];
+    }
+    __syncthreads();
+    if(threadIdx.x < nelim)
     {
+        const int l = threadIdx.x;
         double v = 0.;
-        for(int p = lane; p < 6; p++) v += N.grp_Linv[(size_t)grp * 36 + p * 6 + lane] * (N.grp_h[(size_t)grp * 6 + p] + tsum[p]);
+        for(int p = l; p < 6; p++)
+            v += N.grp_Linv[(size_t)grp * 36 + p * 6 + l] * (N.grp_h[(size_t)grp * 6 + p] + (((s_part[0][p] + s_part[1][p]) + s_part[2][p]) + s_part[3][p]));
         const int col = grp < N.Nframe_groups ? N.e0 + 6 * grp : N.e0 + 6 * N.Nframe_groups + 3 * (grp - N.Nframe_groups);
-        step_full[col + lane] = -v;
+        step_full[col + l] = -v;
     }
 }
 
@@ -743,6 +803,12 @@ bool normal_det_item_prepare(const DevProblem& dp, NormalBuffers& N, cudaStream_
 }
 
 bool comm_allreduce_sum(double* d_buf, size_t count, cudaStream_t s);
+static int env_int(const char* name, int dflt)
+{
+    const char* v = getenv(name);
+    const int x = v ? atoi(v) : 0;
+    return x > 0 ? x : dflt;
+}
 
 // groups -> tiles -> [cross-rank sum of the lower-triangle tiles] -> regularization
 bool normal_det_finish(const DevProblem& dp, NormalBuffers& N, const EvalBuffers& op, const int* d_rowptr,
@@ -767,9 +833,12 @@ bool normal_det_finish(const DevProblem& dp, NormalBuffers& N, const EvalBuffers
     const bool sharded = comm_active();
     if(sharded && N.S_packed == nullptr) { set_error("internal error: sharded solve without the packed tile buffer"); return false; }
     MB200_CUDA_CHECK(cudaMemsetAsync(N.part_arrive, 0, (size_t)kSplitTilesCap * sizeof(int), s));
+    int4* plan = reinterpret_cast<int4*>(N.part_arrive + kSplitTilesCap);
+    static const int items_per_part = env_int("MRCAL_B200_TILE_ITEMS_PER_PART", 128), groups_per_part = env_int("MRCAL_B200_TILE_GROUPS_PER_PART", 96);
+    tile_plan_kernel<<<(ntiles * 32 + 255) / 256, 256, 0, s>>>(N, nblk, items_per_part, groups_per_part, N.part_scratch != nullptr, plan);
     schur_tiles_kernel<<<dim3(ntiles, kMaxParts), 256, kTileSmem, s>>>(N, lambda, N.n_c, nblk, true, sharded ? N.S_packed : nullptr,
-                                                                      N.part_scratch, N.part_arrive);
-    (*nlaunch)++;
+                                                                      N.part_scratch, N.part_arrive, plan);
+    (*nlaunch) += 2;
     if(sharded)
     {
         // THE collective of the algorithm: the reduced normal equations -- lower-triangle tiles only, with g' and the
@@ -793,7 +862,8 @@ bool normal_det_finish(const DevProblem& dp, NormalBuffers& N, const EvalBuffers
 
 // what the workspace must provide for the split tiles
 size_t normal_det_part_scratch_doubles() { return (size_t)kSplitTilesCap * kMaxParts * TB * TB; }
-int normal_det_part_arrive_ints() { return kSplitTilesCap; }
+// arrival counters of the split tiles, then the plan (int4 per tile)
+int normal_det_part_arrive_ints(int nblk_max) { return kSplitTilesCap + 4 * (nblk_max * (nblk_max + 1) / 2); }
 
 bool normal_det_rhs(const NormalBuffers& N, cudaStream_t s, int* nlaunch)
 {
@@ -809,7 +879,7 @@ bool normal_det_rhs(const NormalBuffers& N, cudaStream_t s, int* nlaunch)
 bool normal_det_backsub(const NormalBuffers& N, const double* sol_compact, double* step_full, cudaStream_t s, int* nlaunch)
 {
     if(N.Ngroups == 0) return true;
-    backsub_panels_kernel<<<(N.Ngroups * 32 + 255) / 256, 256, 0, s>>>(N, sol_compact, step_full, N.ldS / TB);
+    backsub_panels_kernel<<<N.Ngroups, 128, 0, s>>>(N, sol_compact, step_full, N.ldS / TB);
     (*nlaunch)++;
     MB200_CUDA_CHECK(cudaGetLastError());
     return true;

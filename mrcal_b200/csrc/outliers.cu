@@ -119,7 +119,7 @@ outlier_tri_kernel(DevProblem P, int phase, const double* __restrict__ x, const 
             if(e0 >= 0)
             {
                 double R0[9];
-                const double* rt0 = &P.u_rtcam[6 * e0];
+                const double* rt0 = &P.in_rt_cam[6 * e0];
                 rodrigues(R0, nullptr, rt0);
                 for(int c = 0; c < 3; c++)
                 {
@@ -141,7 +141,7 @@ outlier_tri_kernel(DevProblem P, int phase, const double* __restrict__ x, const 
                     if(e1 >= 0)
                     {
                         double R1[9];
-                        const double* rt1 = &P.u_rtcam[6 * e1];
+                        const double* rt1 = &P.in_rt_cam[6 * e1];
                         rodrigues(R1, nullptr, rt1);
                         mat3_vec(v0_cam1, R1, v0_ref);
                         mat3_vec(t_10, R1, t_r0);
@@ -300,8 +300,9 @@ bool outliers_mark(mrcal_b200_problem* P, bool* found, int* Noutliers_board, int
     const int nb = Nfeat > 0 ? kOutlierBlocks : 0;
     int* nl = &P->launches;
 
-    // the triangulated branch looks at the camera poses of the accepted state (mrcal.c:4143-4160)
-    if(Nsets > 0 && !launch_unpack_state(P->dp, P->op[P->cur].p, s, nl)) return false;
+    // The divergent-ray test of the triangulated branch (mrcal.c:4143-4230) looks at rt_cam_ref AS THE CALLER GAVE IT:
+    // mrcal_optimize() hands markOutliers() its own argument (mrcal.c:6472), which is only overwritten with the
+    // solution after the outer loop. The seed poses, then, in every pass -- matched here (P.in_rt_cam)
 
     // ---- statistics (and the divergent-ray flags)
     if(nb) { outlier_board_stats_kernel<<<nb, 256, 0, s>>>(P->d_pool_board, x, Nfeat, W->part); (*nl)++; }
@@ -318,6 +319,12 @@ bool outliers_mark(mrcal_b200_problem* P, bool* found, int* Noutliers_board, int
     MB200_CUDA_CHECK(cudaMemcpyAsync(W->h_acc, W->acc, OA_N * sizeof(double), cudaMemcpyDeviceToHost, s));
     MB200_CUDA_CHECK(cudaStreamSynchronize(s));
     *found = W->h_acc[OA_FOUND] > 0.;
+    if(getenv("MRCAL_B200_DEBUG_OUTLIERS"))
+    {
+        fprintf(stderr, "mrcal_b200 outliers: sets %d, acc", Nsets);
+        for(int i = 0; i < OA_N; i++) fprintf(stderr, " %.6g", W->h_acc[i]);
+        fprintf(stderr, "\n");
+    }
     *Noutliers_board = (int)W->h_acc[OA_NOUT_B];
     *Noutliers_tri = (int)W->h_acc[OA_NOUT_T];
     if(Nsets > 0)

@@ -218,7 +218,7 @@ static bool build_workspace(mrcal_b200_problem* P)
              A.alloc(&N.grp_blkmask, (size_t)(N.Ngroups > 0 ? N.Ngroups : 1) * N.bwords, true) &&
              A.alloc(&N.grp_Linv, (size_t)(N.Ngroups > 0 ? N.Ngroups : 1) * 36, true) && A.alloc(&N.grp_h, (size_t)(N.Ngroups > 0 ? N.Ngroups : 1) * 6, true);
         if(!ok) return false;
-        if(!A.alloc(&N.part_scratch, normal_det_part_scratch_doubles()) || !A.alloc(&N.part_arrive, normal_det_part_arrive_ints(), true)) return false;
+        if(!A.alloc(&N.part_scratch, normal_det_part_scratch_doubles()) || !A.alloc(&N.part_arrive, normal_det_part_arrive_ints(N.nblk_max), true)) return false;
         // (always there: the communicator may be created after this workspace)
         if(!A.alloc(&N.S_packed, (size_t)N.nblk_max * (N.nblk_max + 1) / 2 * kCholBlock * kCholBlock)) return false;
     }

@@ -40,7 +40,8 @@ def test_project_matches_reference(ref, lm):
     assert np.abs(g - g3).max() <= 1e-9 * (1. + np.abs(g3).max())
     # broadcasting over leading dimensions, and the no-gradient flavour
     q2 = mrcal_b200.project(p.reshape(8, 5, 3), lm, intr)
-    assert q2.shape == (8, 5, 2) and np.array_equal(q2.reshape(-1, 2), q)
+    # (another instantiation of the kernel: the compiler contracts its multiply-adds differently, last-bit differences)
+    assert q2.shape == (8, 5, 2) and np.abs(q2.reshape(-1, 2) - q).max() <= 1e-12 * (1. + np.abs(q).max())
 
 
 @pytest.mark.parametrize("lm", MODELS)
