@@ -483,6 +483,11 @@ __global__ void debug_fill_spd_kernel(double* A, int n)
     A[e] = i == j ? (double)n : 1. / (1. + (double)((i * 31 + j * 17) % 97));
 }
 
+void chol_debug_fill_spd(double* A, int npad, cudaStream_t s)
+{
+    debug_fill_spd_kernel<<<(unsigned)(((size_t)npad * npad + 255) / 256), 256, 0, s>>>(A, npad);
+}
+
 // Timing aid (not on any product path): device time of `reps` factorizations of an n x n matrix,
 // restricted to the kernel kinds in the mask (1 potrf_diag, 2 trsm, 4 panel syrk, 8 trailing syrk;
 // 15 = everything), launched directly (graph=0) or as a captured graph (graph=1)

@@ -274,6 +274,237 @@ chol_dataflow_kernel(double* __restrict__ A, int ld, int nb, int nreal, double* 
     }
 }
 
+// C = D - acc for [64][PLD] tiles in shared memory (each thread its own fragment elements)
+__device__ __forceinline__ void tile_sub_to(double* C, const double* D, const double (&acc)[2][4][2])
+{
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int wm = warp >> 1, wn = warp & 1, g = lane >> 2, t = lane & 3;
+#pragma unroll
+    for(int a = 0; a < 2; a++)
+#pragma unroll
+        for(int b = 0; b < 4; b++)
+        {
+            const int e = (wm * 16 + a * 8 + g) * PLD + wn * 32 + b * 8 + 2 * t;
+            const double2 v = *reinterpret_cast<const double2*>(&D[e]);
+            *reinterpret_cast<double2*>(&C[e]) = make_double2(v.x - acc[a][b][0], v.y - acc[a][b][1]);
+        }
+}
+// C = D - A A' on the 8x8 granules of the LOWER triangle only (36 of 64: what potrf_block reads), dealt to the 8 warps
+// in row-major order: 5 or 4 granules per warp instead of 8
+__device__ __forceinline__ void tile_syrk_lower_sub(double* C, const double* D, const double* A)
+{
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, g = lane >> 2, t = lane & 3;
+    int gr[5], gc[5];
+    double acc[5][2];
+#pragma unroll
+    for(int m = 0; m < 5; m++)
+    {
+        const int idx = warp + 8 * m;
+        int r = 0;
+        while((r + 1) * (r + 2) / 2 <= idx) r++;
+        gr[m] = idx < 36 ? r : 0;
+        gc[m] = idx < 36 ? idx - r * (r + 1) / 2 : 0;
+        acc[m][0] = acc[m][1] = 0.;
+    }
+    const bool five = warp + 32 < 36;
+#pragma unroll 4
+    for(int ks = 0; ks < T / 4; ks++)
+    {
+#pragma unroll
+        for(int m = 0; m < 5; m++)
+            if(m < 4 || five)
+                pb_dmma(acc[m][0], acc[m][1], A[(gr[m] * 8 + g) * PLD + ks * 4 + t], A[(gc[m] * 8 + g) * PLD + ks * 4 + t]);
+    }
+#pragma unroll
+    for(int m = 0; m < 5; m++)
+        if(m < 4 || five)
+        {
+            const int e = (gr[m] * 8 + g) * PLD + gc[m] * 8 + 2 * t;
+            const double2 v = *reinterpret_cast<const double2*>(&D[e]);
+            *reinterpret_cast<double2*>(&C[e]) = make_double2(v.x - acc[m][0], v.y - acc[m][1]);
+        }
+}
+// [64][PLD] tile in shared memory -> global (row stride ld); lower_only: the entries c <= r
+__device__ __forceinline__ void tile_to_global(double* __restrict__ dst, size_t ld, const double* src, bool lower_only)
+{
+    for(int e = threadIdx.x; e < T * T / 2; e += 256)
+    {
+        const int r = e >> 5, c = (e & 31) * 2;
+        const double2 v = *reinterpret_cast<const double2*>(&src[r * PLD + c]);
+        if(!lower_only || c + 1 <= r) *reinterpret_cast<double2*>(&dst[(size_t)r * ld + c]) = v;
+        else if(c <= r) dst[(size_t)r * ld + c] = v.x;
+    }
+}
+
+// The same factorization with the SPINE -- the diagonal tiles and the tiles left of them, whose chain of
+// potrf_block -> triangular product -> last rank-64 update IS the critical path -- on one CTA that does nothing else:
+// the inverse of a diagonal block goes from potrf_block to the next triangular product through shared memory, and the
+// spine CTA never spends time on the earlier updates of its tiles. Those are "pre" tasks of the other CTAs:
+//   pre(d):  A_{d,d-1} -= sum_{k<=d-2} L_dk L_{d-1,k}',   A_dd -= sum_{k<=d-2} L_dk L_dk'      in place, then flag pre[d]
+// which the spine picks up when potrf_block of step d-1 is done (they have had that long to finish).
+// Helper tasks in the order every helper CTA walks them, column by column j = 0 .. nb-3:
+//   tile (j+2, j);  pre(j+2);  tiles (i, j), i = j+3 .. nb-1
+// Every task depends on spine steps and on EARLIER helper tasks only; the spine depends on its own past and on pre
+// tasks: no cycles, all CTAs co-resident, every CTA walks its list in order: no deadlock. Waits are bounded as above.
+__global__ void __launch_bounds__(256, 1)
+chol_spine_kernel(double* __restrict__ A, int ld, int nb, int nreal, double* __restrict__ invL, int* __restrict__ info,
+                  int* __restrict__ flags, int* __restrict__ pre, int* __restrict__ abort_flag, const int* __restrict__ run_if,
+                  long long* __restrict__ stamps /* debugging aid: 8 clock64() values per spine step, or NULL */)
+{
+#define SPINE_STAMP(k) do { if(stamps != nullptr && tid == 0) stamps[8 * d + (k)] = clock64(); } while(0)
+    if(run_if != nullptr && *run_if == 0) return;
+    extern __shared__ __align__(16) unsigned char dsm_raw[];
+    DfSmem& sm = *reinterpret_cast<DfSmem*>(dsm_raw);
+    const int tid = threadIdx.x;
+    double acc[2][4][2];
+
+    if(blockIdx.x == 0)
+    {
+        ////////////////////////////// the spine
+        tile_to_smem(sm.pb.L, A, ld);
+        cp_commit();
+        cp_wait_all();
+        for(int d = 0; d < nb; d++)
+        {
+            double* Add = A + (size_t)d * T * ld + (size_t)d * T;
+            SPINE_STAMP(0);
+            if(d > 0)
+            {
+                // C2 = the pre-updated A_{d,d-1}, opB = the pre-updated A_dd: loaded at the end of the last step
+                double* Aij = A + (size_t)d * T * ld + (size_t)(d - 1) * T;
+                tile_trsm(sm.C2, sm.pb.X, Aij, ld, sm.opA);     // L_{d,d-1} = C2 inv(L_{d-1,d-1})': to global and to opA
+                __syncthreads();
+                // (the barrier orders everybody's stores before the release store of the one thread that raises the
+                // flag -- a thread of the last warp, the chain warp of potrf_block has better things to do)
+                if(tid == 255) st_release(flags + tile_flag(d, d - 1, nb), 1);
+                SPINE_STAMP(1);
+                tile_syrk_lower_sub(sm.pb.L, sm.opB, sm.opA);
+            }
+            SPINE_STAMP(2);
+            potrf_block(sm.pb, info, d * T, nreal);
+            SPINE_STAMP(3);
+            // the next step's tiles, if they are ready: their loads run under the write-out below
+            bool loading = false;
+            if(d + 1 < nb)
+            {
+                if(tid == 0) sm.ok = (d + 1 < 2 || ld_acquire(pre + d + 1) != 0) ? 1 : 0;
+                __syncthreads();
+                loading = sm.ok != 0;
+                if(loading)
+                {
+                    tile_to_smem(sm.C2, A + (size_t)(d + 1) * T * ld + (size_t)d * T, ld);
+                    tile_to_smem(sm.opB, A + (size_t)(d + 1) * T * ld + (size_t)(d + 1) * T, ld);
+                    cp_commit();
+                }
+            }
+            SPINE_STAMP(4);
+            tile_to_global(Add, ld, sm.pb.L, true);
+            {
+                double* invLd = invL + (size_t)d * T * T;
+                for(int e = tid; e < T * T / 2; e += 256)
+                {
+                    const int r = e >> 5, c = (e & 31) * 2;
+                    *reinterpret_cast<double2*>(&invLd[r * T + c]) = *reinterpret_cast<const double2*>(&sm.pb.X[r * PLD + c]);
+                }
+            }
+            SPINE_STAMP(5);
+            if(stamps != nullptr && tid == 0) stamps[8 * d + 7] = loading ? 1 : 0;
+            if(d + 1 < nb && !loading)
+            {
+                __syncthreads();
+                if(tid == 255) st_release(flags + tile_flag(d, d, nb), 1);
+                if(!wait_flags(sm, pre + d + 1, nullptr, abort_flag, info)) return;
+                tile_to_smem(sm.C2, A + (size_t)(d + 1) * T * ld + (size_t)d * T, ld);
+                tile_to_smem(sm.opB, A + (size_t)(d + 1) * T * ld + (size_t)(d + 1) * T, ld);
+                cp_commit();
+                cp_wait_all();
+                __syncthreads();
+            }
+            else
+            {
+                cp_wait_all();
+                __syncthreads();
+                if(tid == 255) st_release(flags + tile_flag(d, d, nb), 1);
+            }
+            SPINE_STAMP(6);
+        }
+        return;
+    }
+#undef SPINE_STAMP
+
+    ////////////////////////////// the helpers
+    const int nhelpers = gridDim.x - 1;
+    const int ntasks = (nb - 1) * nb / 2 - 1;       // sum over j = 0 .. nb-3 of (nb - 1 - j)
+    for(int tl = blockIdx.x - 1; tl < ntasks; tl += nhelpers)
+    {
+        int j = 0, rem = tl;
+        while(rem >= nb - 1 - j) { rem -= nb - 1 - j; j++; }
+        const bool is_pre = rem == 1;
+        if(!is_pre)
+        {
+            // ---- the tile (i, j), i >= j+2
+            const int i = rem == 0 ? j + 2 : j + 1 + rem;
+            double* Aij = A + (size_t)i * T * ld + (size_t)j * T;
+            tile_to_smem(sm.C2, Aij, ld);
+            cp_commit();
+            for(int k = 0; k < j; k++)
+            {
+                if(!wait_flags(sm, flags + tile_flag(i, k, nb), flags + tile_flag(j, k, nb), abort_flag, info)) return;
+                tile_to_smem(sm.opA, A + (size_t)i * T * ld + (size_t)k * T, ld);
+                tile_to_smem(sm.opB, A + (size_t)j * T * ld + (size_t)k * T, ld);
+                cp_commit();
+                cp_wait_all();
+                __syncthreads();
+                acc_zero(acc);
+                tile_mma(acc, sm.opA, sm.opB);
+                tile_sub(sm.C2, acc);
+                __syncthreads();
+            }
+            if(!wait_flags(sm, flags + tile_flag(j, j, nb), nullptr, abort_flag, info)) return;
+            tile_to_smem(sm.opB, invL + (size_t)j * T * T, T);
+            cp_commit();
+            cp_wait_all();
+            __syncthreads();
+            tile_trsm(sm.C2, sm.opB, Aij, ld, nullptr);
+            __threadfence();
+            __syncthreads();
+            if(tid == 0) st_release(flags + tile_flag(i, j, nb), 1);
+        }
+        else
+        {
+            // ---- pre(d), d = j+2: everything the spine's two tiles of step d get from the columns k <= d-2
+            const int d = j + 2;
+            double* Aij = A + (size_t)d * T * ld + (size_t)(d - 1) * T;
+            double* Add = A + (size_t)d * T * ld + (size_t)d * T;
+            tile_to_smem(sm.C2, Aij, ld);
+            tile_to_smem(sm.pb.L, Add, ld);
+            cp_commit();
+            for(int k = 0; k <= d - 2; k++)
+            {
+                if(!wait_flags(sm, flags + tile_flag(d, k, nb), flags + tile_flag(d - 1, k, nb), abort_flag, info)) return;
+                tile_to_smem(sm.opA, A + (size_t)d * T * ld + (size_t)k * T, ld);
+                tile_to_smem(sm.opB, A + (size_t)(d - 1) * T * ld + (size_t)k * T, ld);
+                cp_commit();
+                cp_wait_all();
+                __syncthreads();
+                acc_zero(acc);
+                tile_mma(acc, sm.opA, sm.opB);
+                tile_sub(sm.C2, acc);
+                acc_zero(acc);
+                tile_mma(acc, sm.opA, sm.opA);
+                tile_sub(sm.pb.L, acc);
+                __syncthreads();
+            }
+            tile_to_global(Aij, ld, sm.C2, false);
+            tile_to_global(Add, ld, sm.pb.L, true);
+            __threadfence();
+            __syncthreads();
+            if(tid == 0) st_release(pre + d, 1);
+        }
+        __syncthreads();
+    }
+}
+
 // Backward substitution L' x = y, one right-hand side, one CTA per 64-row block (walking
 // down from the last block). Block i needs x_j for all j > i: it polls the x values
 // themselves (the slots hold a sentinel until written), so a hop between consecutive
@@ -364,7 +595,8 @@ DeviceCfg* configure()
     int coop = 0;
     if(cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, dev) != cudaSuccess || !coop ||
        cudaDeviceGetAttribute(&c.num_sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess ||
-       cudaFuncSetAttribute(chol_dataflow_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(DfSmem)) != cudaSuccess)
+       cudaFuncSetAttribute(chol_dataflow_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(DfSmem)) != cudaSuccess ||
+       cudaFuncSetAttribute(chol_spine_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(DfSmem)) != cudaSuccess)
     {
         cudaGetLastError();
         c.unavailable = true;
@@ -373,6 +605,8 @@ DeviceCfg* configure()
     c.configured = true;
     return &c;
 }
+
+long long* g_debug_stamps = nullptr;   // set by chol_debug_spine_stamps() only
 
 CholScratch* scratch_or_default(CholScratch* sc)
 {
@@ -389,7 +623,7 @@ CholScratch* scratch_or_default(CholScratch* sc)
 bool chol_scratch_create(CholScratch* sc)
 {
     sc->flags = nullptr; sc->xbuf = nullptr;
-    if(cudaMalloc(&sc->flags, (kMaxTiles + 1) * sizeof(int)) != cudaSuccess ||
+    if(cudaMalloc(&sc->flags, (kMaxTiles + 1 + kMaxBlocks) * sizeof(int)) != cudaSuccess ||
        cudaMalloc(&sc->xbuf, (size_t)kMaxBlocks * T * sizeof(double)) != cudaSuccess)
     {
         set_error("cudaMalloc of the factorization scratch failed: %s", cudaGetErrorString(cudaGetLastError()));
@@ -425,6 +659,19 @@ bool chol_factor_dataflow(double* A, int npad, int nreal, double* invL, int* d_i
     int ld = npad;
     int* flags = sc->flags;
     int* abort_flag = sc->flags + kMaxTiles;
+    static const bool no_spine = getenv("MRCAL_B200_CHOL_NO_SPINE") != nullptr;
+    if(!no_spine && nb >= 3 && cfg->num_sms >= 2)
+    {
+        int* pre = sc->flags + kMaxTiles + 1;
+        MB200_CUDA_CHECK(cudaMemsetAsync(pre, 0, (size_t)nb * sizeof(int), s));
+        long long* stamps = g_debug_stamps;
+        void* args[] = {&A, &ld, &nb, &nreal, &invL, &d_info, &flags, &pre, &abort_flag, &d_run_if, &stamps};
+        const int nhelper_tasks = (nb - 1) * nb / 2 - 1;
+        const int grid = 1 + (nhelper_tasks < cfg->num_sms - 1 ? nhelper_tasks : cfg->num_sms - 1);
+        MB200_CUDA_CHECK(cudaLaunchCooperativeKernel((const void*)chol_spine_kernel, dim3(grid), dim3(256), args, sizeof(DfSmem), s));
+        if(nlaunch) (*nlaunch)++;
+        return true;
+    }
     void* args[] = {&A, &ld, &nb, &nreal, &invL, &d_info, &flags, &abort_flag, &d_run_if};
     const int grid = ntiles < cfg->num_sms ? ntiles : cfg->num_sms;
     MB200_CUDA_CHECK(cudaLaunchCooperativeKernel((const void*)chol_dataflow_kernel, dim3(grid), dim3(256), args, sizeof(DfSmem), s));
@@ -448,6 +695,37 @@ bool chol_solve_backward_dataflow(const double* L, int npad, const double* invL,
     MB200_CUDA_CHECK(cudaLaunchCooperativeKernel((const void*)chol_backward_dataflow_kernel, dim3(grid), dim3(256), args, 0, s));
     if(nlaunch) (*nlaunch)++;
     return true;
+}
+
+// Debugging aid (not on any product path): clock64() stamps of the spine of one factorization of an n x n matrix:
+// out[8 d + k], k = 0 step start, 1 triangular product done, 2 diagonal tile ready, 3 potrf_block done, 4 next loads
+// issued, 5 written out and flagged, 6 step end, 7 whether the next tiles were ready when asked
+void chol_debug_fill_spd(double* A, int npad, cudaStream_t s);   // chol.cu
+bool chol_debug_spine_stamps(int n, long long* out, int nmax)
+{
+    const int npad = chol_padded(n), nb = npad / T;
+    if(nmax < 8 * nb) return false;
+    double *A = nullptr, *invL = nullptr; int* info = nullptr; long long* st = nullptr;
+    cudaStream_t s;
+    MB200_CUDA_CHECK(cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking));
+    MB200_CUDA_CHECK(cudaMalloc(&A, (size_t)npad * npad * sizeof(double)));
+    MB200_CUDA_CHECK(cudaMalloc(&invL, (size_t)npad * T * sizeof(double)));
+    MB200_CUDA_CHECK(cudaMalloc(&info, sizeof(int)));
+    MB200_CUDA_CHECK(cudaMalloc(&st, (size_t)8 * nb * sizeof(long long)));
+    MB200_CUDA_CHECK(cudaMemsetAsync(st, 0, (size_t)8 * nb * sizeof(long long), s));
+    bool ok = true;
+    for(int rep = 0; rep < 3 && ok; rep++)
+    {
+        chol_debug_fill_spd(A, npad, s);
+        g_debug_stamps = rep == 2 ? st : nullptr;
+        ok = chol_factor_dataflow(A, npad, n, invL, info, s, nullptr, nullptr, nullptr);
+        g_debug_stamps = nullptr;
+    }
+    ok = ok && cudaMemcpyAsync(out, st, (size_t)8 * nb * sizeof(long long), cudaMemcpyDeviceToHost, s) == cudaSuccess &&
+         cudaStreamSynchronize(s) == cudaSuccess;
+    cudaFree(A); cudaFree(invL); cudaFree(info); cudaFree(st);
+    cudaStreamDestroy(s);
+    return ok;
 }
 
 }  // namespace mb200

@@ -159,6 +159,8 @@ extern "C" double mrcal_b200_debug_time_cholesky(int n, int reps, int kinds, int
 {
     return chol_debug_time(n, reps, kinds, graph);
 }
+namespace mb200 { bool chol_debug_spine_stamps(int n, long long* out, int nmax); }
+extern "C" bool mrcal_b200_debug_spine_stamps(int n, long long* out, int nmax) { return mb200::chol_debug_spine_stamps(n, out, nmax); }
 extern "C" bool mrcal_b200_debug_potrf_stamps(long long* out64)
 {
     return chol_debug_potrf_stamps(out64);

@@ -39,7 +39,10 @@ ALL = SMALL + ["baseline3"]
 # State gate per case. The splined solves end while still creeping along the flattest knot directions (the
 # stopping rule is "squared step < 1e-7", mrcal.c:6297): the state there is defined by the iterate sequence,
 # not by the cost, so roundoff-level differences in the factorization show up at ~1e-4 in those knots.
-TOL_B = {"baseline3": 2e-3, "splined3_outliers": 2e-3}
+TOL_B = {"baseline3": 2e-3, "splined3_outliers": 2e-3,
+         # triangulated points only, the scale held by the unity regularization alone: costs agree to 1e-6 relative when
+         # the (absolute) step threshold stops both solves, the poorly constrained translations to ~3e-4
+         "tri_divergent_rejection": 1e-3}
 # Cost gate per case (relative). The triangulated-only problems end with costs of ~1e-6 rad^2; the stopping rule is an
 # ABSOLUTE step length, so in relative terms they are less converged when the loop stops
 TOL_COST = {"tri_pinhole_unity_only_rejection": 1e-6, "tri_stereographic_unity_rejection": 1e-6, "tri_divergent_rejection": 1e-6,
