@@ -362,10 +362,13 @@ def main():
 
     ###### roofline of the dominant kernel family
     # DRAM traffic per launch of the kernels named below, from the committed ncu capture (null if absent)
-    try:
-        traffic = json.load(open(os.path.join(ROOT, "profiles", "r01c_dram_traffic.json")))
-    except Exception:
-        traffic = {}
+    traffic = {}
+    for name in ("r02_dram_traffic.json", "r01c_dram_traffic.json"):
+        try:
+            traffic = json.load(open(os.path.join(ROOT, "profiles", name)))
+            break
+        except Exception:
+            pass
     last = infos[-1]
     n_c = last["Nreduced"]
     roofline = None
@@ -374,9 +377,9 @@ def main():
         per_fact_s = 1e-3 * sum(i["ms_factor"] for i in infos) / max(1, sum(i["Nfactorizations"] for i in infos))
         flops = n_c ** 3 / 3.0
         achieved = flops / per_fact_s / 1e12
-        roofline = {"bound": "tensor", "kernel": "reduced-system Cholesky: chol_dataflow_kernel (persistent, DMMA; chol_dataflow.cu)",
+        roofline = {"bound": "tensor", "kernel": "reduced-system Cholesky: chol_spine_kernel (persistent, DMMA; chol_dataflow.cu)",
                     "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
-                    "traffic": traffic.get("chol_dataflow_kernel"), "traffic_unit": "bytes per launch (ncu dram read+write)",
+                    "traffic": traffic.get("chol_spine_kernel", traffic.get("chol_dataflow_kernel")), "traffic_unit": "bytes per launch (ncu dram read+write)",
                     "flops_per_launch": flops, "n_reduced": n_c,
                     "peak_source": "cuBLAS DGEMM 8192^3 (torch.matmul fp64) measured in this run: MEASURED_PEAKS.json has no fp64 entry"}
     except Exception as e:   # pragma: no cover
@@ -417,14 +420,17 @@ def main():
         t_flops = flops_asm / (roofline["peak"] * 1e12) if roofline and "peak" in roofline else None
         t_bytes = bytes_asm / (hbm * 1e9)
         bound = "hbm" if (t_flops is None or t_bytes >= t_flops) else "tensor"
-        assembly = {"bound": bound, "kernel": "normal-equation assembly + Schur elimination per iteration: item_columns_kernel, "
-                                              "assemble_items_dmma_kernel, groups_panels_kernel, schur_tiles_kernel, reg_blocks_kernel",
+        assembly = {"bound": bound, "kernel": "normal-equation assembly + Schur elimination per iteration: item_prepare_kernel, "
+                                              "groups_panels_kernel, tile_plan_kernel, schur_tiles_kernel, reg_blocks_kernel (the observations' "
+                                              "Gram blocks come from fused_boards_kernel, timed with the evaluation)",
                     "ms_per_iteration": per_asm_s * 1e3, "flops_per_assembly": flops_asm, "bytes_per_assembly": bytes_asm,
                     "achieved": (bytes_asm / per_asm_s / 1e9) if bound == "hbm" else (flops_asm / per_asm_s / 1e12),
                     "peak": hbm if bound == "hbm" else roofline["peak"], "unit": "GB/s" if bound == "hbm" else "TFLOP/s",
                     "frac": (t_bytes if bound == "hbm" else t_flops) / per_asm_s,
                     "frac_hbm": t_bytes / per_asm_s, "frac_fp64_tensor": (t_flops / per_asm_s) if t_flops else None,
-                    "traffic": None}
+                    "traffic": (sum(traffic[k] for k in ("fused_boards_kernel", "groups_panels_kernel", "schur_tiles_kernel") if k in traffic)
+                                if "schur_tiles_kernel" in traffic else None),
+                    "traffic_note": "ncu dram read+write per launch: fused_boards_kernel + groups_panels_kernel + schur_tiles_kernel"}
     except Exception as e:   # pragma: no cover
         assembly = {"error": str(e)}
 

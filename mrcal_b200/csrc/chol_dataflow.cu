@@ -295,7 +295,7 @@ __device__ __forceinline__ void tile_syrk_lower_sub(double* C, const double* D, 
 {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, g = lane >> 2, t = lane & 3;
     int gr[5], gc[5];
-    double acc[5][2];
+    double acc[5][2][2];   // two chains per granule (K halves): the DMMA latency, not its rate, is what a chain of 16 costs
 #pragma unroll
     for(int m = 0; m < 5; m++)
     {
@@ -304,16 +304,19 @@ __device__ __forceinline__ void tile_syrk_lower_sub(double* C, const double* D, 
         while((r + 1) * (r + 2) / 2 <= idx) r++;
         gr[m] = idx < 36 ? r : 0;
         gc[m] = idx < 36 ? idx - r * (r + 1) / 2 : 0;
-        acc[m][0] = acc[m][1] = 0.;
+        acc[m][0][0] = acc[m][0][1] = acc[m][1][0] = acc[m][1][1] = 0.;
     }
     const bool five = warp + 32 < 36;
 #pragma unroll 4
-    for(int ks = 0; ks < T / 4; ks++)
+    for(int ks = 0; ks < T / 8; ks++)
     {
 #pragma unroll
-        for(int m = 0; m < 5; m++)
-            if(m < 4 || five)
-                pb_dmma(acc[m][0], acc[m][1], A[(gr[m] * 8 + g) * PLD + ks * 4 + t], A[(gc[m] * 8 + g) * PLD + ks * 4 + t]);
+        for(int h = 0; h < 2; h++)
+#pragma unroll
+            for(int m = 0; m < 5; m++)
+                if(m < 4 || five)
+                    pb_dmma(acc[m][h][0], acc[m][h][1], A[(gr[m] * 8 + g) * PLD + (ks + h * (T / 8)) * 4 + t],
+                            A[(gc[m] * 8 + g) * PLD + (ks + h * (T / 8)) * 4 + t]);
     }
 #pragma unroll
     for(int m = 0; m < 5; m++)
@@ -321,7 +324,7 @@ __device__ __forceinline__ void tile_syrk_lower_sub(double* C, const double* D, 
         {
             const int e = (gr[m] * 8 + g) * PLD + gc[m] * 8 + 2 * t;
             const double2 v = *reinterpret_cast<const double2*>(&D[e]);
-            *reinterpret_cast<double2*>(&C[e]) = make_double2(v.x - acc[m][0], v.y - acc[m][1]);
+            *reinterpret_cast<double2*>(&C[e]) = make_double2(v.x - (acc[m][0][0] + acc[m][1][0]), v.y - (acc[m][0][1] + acc[m][1][1]));
         }
 }
 // [64][PLD] tile in shared memory -> global (row stride ld); lower_only: the entries c <= r
@@ -383,7 +386,9 @@ chol_spine_kernel(double* __restrict__ A, int ld, int nb, int nreal, double* __r
             SPINE_STAMP(2);
             potrf_block(sm.pb, info, d * T, nreal);
             SPINE_STAMP(3);
-            // the next step's tiles, if they are ready: their loads run under the write-out below
+            // the next step's tiles, if they are ready: their loads run under the write-out below. (Fetching them under the
+            // last panel of potrf_block by its idle warps was tried: the loads finish no earlier, and the barriers of the
+            // panel come later.)
             bool loading = false;
             if(d + 1 < nb)
             {

@@ -184,10 +184,10 @@ panels_forward_kernel(NormalBuffers N, const double* __restrict__ Bf, int Nelim,
         {
             const int grp = 32 * w + __ffs(m) - 1;
             m &= m - 1;
-            const double* Y = N.Ypan + ((size_t)grp * N.nblk_max + blk) * (6 * TB);
+            const double* Y = N.Ypan + ((size_t)grp * N.nblk_max + blk) * kYpanel;
             const double* z = Bf + (size_t)rhs * Nelim + group_col0(N, grp);
             const int nelim = grp < N.Nframe_groups ? 6 : 3;
-            for(int p = 0; p < nelim; p++) acc += Y[p * TB + col] * z[p];
+            for(int p = 0; p < nelim; p++) acc += Y[p * kYld + col] * z[p];
         }
     }
     Bs[(size_t)rhs * N.ldS + TB * blk + col] -= acc;
@@ -200,7 +200,7 @@ panels_backward_kernel(NormalBuffers N, double* __restrict__ Bf, int Nelim, cons
     const int lane = threadIdx.x & 31;
     if(wid >= (long)Nrhs * N.Ngroups) return;
     const int rhs = (int)(wid / N.Ngroups), grp = (int)(wid - (long)rhs * N.Ngroups);
-    const double* Yg = N.Ypan + (size_t)grp * N.nblk_max * (6 * TB);
+    const double* Yg = N.Ypan + (size_t)grp * N.nblk_max * kYpanel;
     const double* xs = Bs + (size_t)rhs * N.ldS;
     double t[6] = {0., 0., 0., 0., 0., 0.};
     for(int b = 0; b < nblk; b++)
@@ -208,7 +208,7 @@ panels_backward_kernel(NormalBuffers N, double* __restrict__ Bf, int Nelim, cons
         if(!((N.grp_blkmask[(size_t)grp * N.bwords + (b >> 5)] >> (b & 31)) & 1u)) continue;
         const double d0 = xs[TB * b + lane], d1 = xs[TB * b + 32 + lane];
 #pragma unroll
-        for(int p = 0; p < 6; p++) t[p] += Yg[(size_t)b * (6 * TB) + p * TB + lane] * d0 + Yg[(size_t)b * (6 * TB) + p * TB + 32 + lane] * d1;
+        for(int p = 0; p < 6; p++) t[p] += Yg[(size_t)b * kYpanel + p * kYld + lane] * d0 + Yg[(size_t)b * kYpanel + p * kYld + 32 + lane] * d1;
     }
 #pragma unroll
     for(int p = 0; p < 6; p++)

@@ -880,8 +880,26 @@ static bool launch_gram_dmma(const DevProblem& dp, NormalBuffers& N, const EvalB
 // item's block goes. Ends with an ASYNCHRONOUS copy of (n_c, widest item) to the host: the caller synchronises
 // the stream when it suits it (the solver does so once per trust-region step, with everything else it reads)
 // and then calls normal_adopt_sizes()
-bool normal_prepare(const DevProblem& dp, NormalBuffers& N, const EvalBuffers& op, cudaStream_t s, int* nlaunch, bool boards_done)
+// rider: a device scalar that is a per-rank partial sum (the cost of this evaluation). Sharded solves sum it over the
+// ranks in the SAME collective that unites the active sets: the marks travel as 0/1 doubles, the scalar behind them.
+// *rider_summed says whether that happened
+__global__ void marks_stage_kernel(const int* __restrict__ active, int n_r, const double* __restrict__ rider, double* __restrict__ stage)
 {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if(i < n_r) stage[i] = active[i] != 0 ? 1. : 0.;
+    else if(i == n_r) stage[i] = rider != nullptr ? *rider : 0.;
+}
+__global__ void marks_unstage_kernel(int* __restrict__ active, int n_r, double* __restrict__ rider, const double* __restrict__ stage)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if(i < n_r) active[i] = stage[i] > 0. ? 1 : 0;
+    else if(i == n_r && rider != nullptr) *rider = stage[i];
+}
+
+bool normal_prepare(const DevProblem& dp, NormalBuffers& N, const EvalBuffers& op, cudaStream_t s, int* nlaunch, bool boards_done,
+                    double* rider, bool* rider_summed)
+{
+    if(rider_summed) *rider_summed = false;
     if(!configure_kernels()) return false;
     const size_t lmap_bytes = ((size_t)dp.Nintr_state * sizeof(short) + 7) / 8 * 8;
     const size_t ccol_bytes = ((size_t)N.cap * sizeof(int) + 7) / 8 * 8;
@@ -900,7 +918,19 @@ bool normal_prepare(const DevProblem& dp, NormalBuffers& N, const EvalBuffers& o
     if(dp.reg_unity) { mark_reg_active_kernel<<<1, 32, 0, s>>>(dp, N); (*nlaunch)++; }
     if(dp.Ntri > 0) { mark_tri_active_kernel<<<(2 * dp.Ntri + 127) / 128, 128, 0, s>>>(dp, N); (*nlaunch)++; }
     // sharded solve: every rank must number the union of the active sets identically
-    if(comm_active() && N.n_r > 0 && !comm_allreduce_max_int(N.active, (size_t)N.n_r, s)) return false;
+    if(comm_active() && N.n_r > 0)
+    {
+        if(N.S_packed != nullptr)
+        {
+            // (the packed-tile buffer is idle between assemblies)
+            marks_stage_kernel<<<(N.n_r + 1 + 255) / 256, 256, 0, s>>>(N.active, N.n_r, rider, N.S_packed);
+            if(!comm_allreduce_sum(N.S_packed, (size_t)N.n_r + 1, s)) return false;
+            marks_unstage_kernel<<<(N.n_r + 1 + 255) / 256, 256, 0, s>>>(N.active, N.n_r, rider, N.S_packed);
+            (*nlaunch) += 2;
+            if(rider_summed) *rider_summed = rider != nullptr;
+        }
+        else if(!comm_allreduce_max_int(N.active, (size_t)N.n_r, s)) return false;
+    }
     compact_scan_kernel<<<1, 1024, 0, s>>>(N);
     (*nlaunch)++;
     if(N.det_available && !N.fused && !normal_det_item_offsets(dp, N, s, nlaunch)) return false;

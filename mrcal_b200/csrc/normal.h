@@ -7,6 +7,9 @@ namespace mb200 {
 // All device pointers. "work item" = one board observation or one point
 // observation; "group" = one eliminated block (a frame: 6 unknowns, or a
 // non-fixed point: 3 unknowns) with the work items that see it.
+constexpr int kYld = 68;              // row stride of the panels of Ypan (doubles)
+constexpr int kYpanel = 6 * kYld;     // one (group, block) panel
+
 struct NormalBuffers
 {
     double* S;        // [ldS][ldS] row-major, lower: reduced normal matrix over the ACTIVE shared unknowns
@@ -59,7 +62,9 @@ struct NormalBuffers
     unsigned short* wi_ccol;    // [Nwi][capA] compact index of each local column (increasing); then n_c, n_c+1
     unsigned char*  wi_segoff;  // [Nwi][nblk_max+1] first local column of each 64-column block of S
     int     nblk_max;     // ldS_max / 64
-    double* Ypan;         // [Ngroups][nblk_max][6][64] inv(L_D) B of each group, dense per 64-column block (present blocks only)
+    double* Ypan;         // [Ngroups][nblk_max][6][kYld] inv(L_D) B of each group, dense per 64-column block (present blocks
+                          // only). Rows padded to kYld: a panel goes to shared memory as ONE bulk copy and lands with a
+                          // row stride whose DMMA fragment loads are free of bank conflicts
     unsigned* grp_present;   // [nblk_max][gwords] bit g: group g has columns in this block
     unsigned* wi_present;    // [nblk_max][wwords]
     unsigned* grp_blkmask;   // [Ngroups][bwords] the blocks a group is present in
@@ -77,7 +82,8 @@ struct NormalBuffers
 // The same in pieces, for a caller that wants to pick its own moment to wait for the device:
 // prepare (device work + an async copy of the sizes) -> [synchronise the stream] -> adopt_sizes -> finish
 bool normal_clear_marks(NormalBuffers& N, cudaStream_t s);
-bool normal_prepare(const DevProblem& dp, NormalBuffers& N, const EvalBuffers& op, cudaStream_t s, int* nlaunch, bool boards_done);
+bool normal_prepare(const DevProblem& dp, NormalBuffers& N, const EvalBuffers& op, cudaStream_t s, int* nlaunch, bool boards_done,
+                    double* rider = nullptr, bool* rider_summed = nullptr);
 bool normal_adopt_sizes(NormalBuffers& N);
 bool normal_finish(const DevProblem& dp, NormalBuffers& N, const EvalBuffers& op, const int* d_rowptr,
                    double lambda, cudaStream_t s, int* nlaunch, bool boards_done);
@@ -107,6 +113,7 @@ bool normal_det_item_prepare(const DevProblem& dp, NormalBuffers& N, cudaStream_
 bool normal_det_item_offsets(const DevProblem& dp, NormalBuffers& N, cudaStream_t s, int* nlaunch);   // before it
 size_t normal_det_part_scratch_doubles();
 int normal_det_part_arrive_ints(int nblk_max);
+size_t normal_det_packed_doubles(int nblk_max);
 bool normal_det_rhs(const NormalBuffers& N, cudaStream_t s, int* nlaunch);   // after the cross-rank reduction of S
 bool normal_det_backsub(const NormalBuffers& N, const double* sol_compact, double* step_full, cudaStream_t s, int* nlaunch);
 

@@ -189,11 +189,11 @@ groups_panels_kernel(NormalBuffers N, double lambda, int n_c, int nblk)
     }
     if(tid == 0) { const int b = n_c >> 6; atomicOr(&s_blk[b >> 5], 1u << (b & 31)); }
     __syncthreads();
-    double* Yg = N.Ypan + (size_t)grp * N.nblk_max * (6 * TB);
+    double* Yg = N.Ypan + (size_t)grp * N.nblk_max * kYpanel;
     for(int b = 0; b < nblk; b++)
     {
         if(!((s_blk[b >> 5] >> (b & 31)) & 1u)) continue;   // uniform
-        for(int e = tid; e < 6 * TB; e += 256) Yg[(size_t)b * (6 * TB) + e] = 0.;
+        for(int e = tid; e < kYpanel; e += 256) Yg[(size_t)b * kYpanel + e] = 0.;
         if(tid == 0) atomicOr(&N.grp_present[(size_t)b * N.gwords + (grp >> 5)], 1u << (grp & 31));
     }
     if(tid < N.bwords) N.grp_blkmask[(size_t)grp * N.bwords + tid] = s_blk[tid];
@@ -209,7 +209,7 @@ groups_panels_kernel(NormalBuffers N, double lambda, int n_c, int nblk)
         for(int l = tid; l < nsh; l += 256)
         {
             const int c = cc[l];
-            double* y = Yg + (size_t)(c >> 6) * (6 * TB) + (c & 63);
+            double* y = Yg + (size_t)(c >> 6) * kYpanel + (c & 63);
             double bq[6];
 #pragma unroll
             for(int q = 0; q < 6; q++) bq[q] = q < nelim ? B[(size_t)q * N.cap + l] : 0.;
@@ -219,12 +219,12 @@ groups_panels_kernel(NormalBuffers N, double lambda, int n_c, int nblk)
                 double t = 0.;
 #pragma unroll
                 for(int q = 0; q < 6; q++) if(q <= p) t += s_Linv[p * 6 + q] * bq[q];
-                if(p < nelim) y[p * TB] += t;
+                if(p < nelim) y[p * kYld] += t;
             }
         }
         __syncthreads();
     }
-    if(tid < 6) Yg[(size_t)(n_c >> 6) * (6 * TB) + tid * TB + (n_c & 63)] = -s_h[tid];
+    if(tid < 6) Yg[(size_t)(n_c >> 6) * kYpanel + tid * kYld + (n_c & 63)] = -s_h[tid];
 }
 
 struct alignas(16) TileCommon
@@ -300,6 +300,7 @@ __device__ __forceinline__ void bulk_load(void* smem, const void* gmem, unsigned
 }
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory"); }
 
+constexpr int kPackedExtras = 8;      // doubles behind the packed tiles (sharded solves)
 constexpr int kMaxParts = 8;          // a tile's contributors may be split over this many CTAs
 constexpr int kSplitTilesCap = 2048;  // tiles with a slot in the partial-sum scratch (beyond: one CTA does it all)
 
@@ -512,21 +513,22 @@ schur_tiles_kernel(NormalBuffers N, double lambda, int n_c, int nblk, bool add_l
         // the bulk copies write
         fence_proxy_async();
         __syncthreads();
-        // rows 6 i .. 6 i + 5 of the K panel <- group i of the chunk: one 512-byte bulk copy (TMA) per row and side, issued
-        // by one thread each, all counted on the buffer's mbarrier. No thread spends instructions on moving the data
+        // rows 6 i .. 6 i + 5 of the K panel <- group i of the chunk: ONE bulk copy (TMA) per group and side -- the panels
+        // are contiguous in Ypan and carry the row padding of the shared-memory layout; a bulk copy has a fixed cost of
+        // some 45 cycles in the copy engine, whatever its size -- issued by one thread each, all counted on the buffer's
+        // mbarrier. No thread spends instructions on moving the data
+        static_assert(kYld == TLD, "the panels of Ypan are copied as they are");
         const int sides = diag ? 1 : 2;
         auto stage = [&](int chunk, int buf)
         {
             const int ng = min(kChunkGroups, nwl - chunk * kChunkGroups);
-            const int nrows = 6 * ng;
-            if(tid == 0) mbar_arrive_expect_tx(&sc.bar[buf], (unsigned)(sides * nrows * TB * sizeof(double)));
-            if(tid < sides * nrows)
+            if(tid == 0) mbar_arrive_expect_tx(&sc.bar[buf], (unsigned)(sides * ng * kYpanel * sizeof(double)));
+            if(tid < sides * ng)
             {
-                const int side = tid >= nrows ? 1 : 0, row = tid - side * nrows;
-                const int gi = row / 6, p = row - gi * 6;
+                const int side = tid >= ng ? 1 : 0, gi = tid - side * ng;
                 const int grp = sc.wl[lo + chunk * kChunkGroups + gi];
-                const double* src = N.Ypan + ((size_t)grp * N.nblk_max + (side == 0 ? r : c)) * (6 * TB) + p * TB;
-                bulk_load(side == 0 ? &ss.R[buf][row][0] : &ss.C[buf][row][0], src, (unsigned)(TB * sizeof(double)), &sc.bar[buf]);
+                const double* src = N.Ypan + ((size_t)grp * N.nblk_max + (side == 0 ? r : c)) * kYpanel;
+                bulk_load(side == 0 ? &ss.R[buf][6 * gi][0] : &ss.C[buf][6 * gi][0], src, (unsigned)(kYpanel * sizeof(double)), &sc.bar[buf]);
             }
         };
         stage(0, 0);
@@ -638,6 +640,18 @@ schur_tiles_kernel(NormalBuffers N, double lambda, int n_c, int nblk, bool add_l
         }
 }
 
+// Sharded solves: what every rank has to know about the others' frame blocks rides behind the tiles in the same
+// all-reduce: extras[0] = this rank has a singular elimination block
+__global__ void pack_extras_kernel(NormalBuffers N, double* __restrict__ extras)
+{
+    if(threadIdx.x == 0 && blockIdx.x == 0) extras[0] = N.info[0] != 0 ? 1. : 0.;
+}
+__global__ void unpack_extras_kernel(NormalBuffers N, const double* __restrict__ extras)
+{
+    // a block that is singular on ONE rank sends every rank down the same path
+    if(threadIdx.x == 0 && blockIdx.x == 0 && extras[0] != 0. && N.info[0] == 0) N.info[0] = 2000000000;
+}
+
 // tile-packed (summed over the ranks) -> the lower triangle of S, with the diagonal loading and the padding rows
 __global__ void __launch_bounds__(256)
 unpack_tiles_kernel(NormalBuffers N, const double* __restrict__ packed, double lambda, int n_c, int nblk)
@@ -745,7 +759,7 @@ backsub_panels_kernel(NormalBuffers N, const double* __restrict__ sol, double* _
     __shared__ double s_part[4][6];
     const int grp = blockIdx.x, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int nelim = grp < N.Nframe_groups ? 6 : 3;
-    const double* Yg = N.Ypan + (size_t)grp * N.nblk_max * (6 * TB);
+    const double* Yg = N.Ypan + (size_t)grp * N.nblk_max * kYpanel;
     const unsigned* mask = N.grp_blkmask + (size_t)grp * N.bwords;
     double tsum[6] = {0., 0., 0., 0., 0., 0.};
     int seen = 0;   // present blocks so far: the k-th present block goes to warp k mod 4 (an even share whatever the pattern)
@@ -756,7 +770,7 @@ backsub_panels_kernel(NormalBuffers N, const double* __restrict__ sol, double* _
         const double d0 = sol[TB * b + lane], d1 = sol[TB * b + 32 + lane];
 #pragma unroll
         for(int p = 0; p < 6; p++)
-            tsum[p] += Yg[(size_t)b * (6 * TB) + p * TB + lane] * d0 + Yg[(size_t)b * (6 * TB) + p * TB + 32 + lane] * d1;
+            tsum[p] += Yg[(size_t)b * kYpanel + p * kYld + lane] * d0 + Yg[(size_t)b * kYpanel + p * kYld + 32 + lane] * d1;
     }
 #pragma unroll
     for(int p = 0; p < 6; p++)
@@ -843,9 +857,12 @@ bool normal_det_finish(const DevProblem& dp, NormalBuffers& N, const EvalBuffers
     {
         // THE collective of the algorithm: the reduced normal equations -- lower-triangle tiles only, with g' and the
         // gradient as rows n_c, n_c+1 of the same tiles -- summed over the frame shards
-        if(!comm_allreduce_sum(N.S_packed, (size_t)ntiles * TB * TB, s)) return false;
+        double* extras = N.S_packed + (size_t)ntiles * TB * TB;
+        pack_extras_kernel<<<1, 32, 0, s>>>(N, extras);
+        if(!comm_allreduce_sum(N.S_packed, (size_t)ntiles * TB * TB + kPackedExtras, s)) return false;
+        unpack_extras_kernel<<<1, 32, 0, s>>>(N, extras);
         unpack_tiles_kernel<<<ntiles, 256, 0, s>>>(N, N.S_packed, lambda, N.n_c, nblk);
-        (*nlaunch)++;
+        (*nlaunch) += 3;
     }
     const int Ndist_rows   = (dp.reg && dp.opt_dist) ? dp.Ncam_i * (dp.Nintr - 4) : 0;
     const int Ncenter_rows = (dp.reg && dp.opt_core) ? dp.Ncam_i * 2 : 0;
@@ -860,6 +877,7 @@ bool normal_det_finish(const DevProblem& dp, NormalBuffers& N, const EvalBuffers
     return true;
 }
 
+size_t normal_det_packed_doubles(int nblk_max) { return (size_t)nblk_max * (nblk_max + 1) / 2 * TB * TB + kPackedExtras; }
 // what the workspace must provide for the split tiles
 size_t normal_det_part_scratch_doubles() { return (size_t)kSplitTilesCap * kMaxParts * TB * TB; }
 // arrival counters of the split tiles, then the plan (int4 per tile)

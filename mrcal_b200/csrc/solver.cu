@@ -21,7 +21,6 @@ bool comm_allreduce_sum(double* d_buf, size_t count, cudaStream_t s);           
 int  comm_rank();
 long comm_collective_count();
 // the per-rank partial sums of the Cauchy phase sit in slots [6..8] (eliminated range) and [9..10] (row sums): one call
-static bool comm_allreduce_partial(double* scal, cudaStream_t s) { return comm_allreduce_sum(scal + 6, 5, s); }
 
 static void delete_ws(SolverWorkspace* w) { delete w; }
 static bool build_workspace(mrcal_b200_problem* P);
@@ -213,14 +212,14 @@ static bool build_workspace(mrcal_b200_problem* P)
         N.bwords = (N.nblk_max + 31) / 32;
         ok = A.alloc(&N.wi_A, (size_t)N.A_pool) && A.alloc(&N.wi_Aoff, Nwi, true) && A.alloc(&N.wi_lda, Nwi, true) &&
              A.alloc(&N.wi_ccol, (size_t)Nwi * N.capA, true) && A.alloc(&N.wi_segoff, (size_t)Nwi * (N.nblk_max + 1), true) &&
-             A.alloc(&N.Ypan, (size_t)(N.Ngroups > 0 ? N.Ngroups : 1) * N.nblk_max * 6 * kCholBlock) &&
+             A.alloc(&N.Ypan, (size_t)(N.Ngroups > 0 ? N.Ngroups : 1) * N.nblk_max * kYpanel) &&
              A.alloc(&N.grp_present, (size_t)N.nblk_max * N.gwords, true) && A.alloc(&N.wi_present, (size_t)N.nblk_max * N.wwords, true) &&
              A.alloc(&N.grp_blkmask, (size_t)(N.Ngroups > 0 ? N.Ngroups : 1) * N.bwords, true) &&
              A.alloc(&N.grp_Linv, (size_t)(N.Ngroups > 0 ? N.Ngroups : 1) * 36, true) && A.alloc(&N.grp_h, (size_t)(N.Ngroups > 0 ? N.Ngroups : 1) * 6, true);
         if(!ok) return false;
         if(!A.alloc(&N.part_scratch, normal_det_part_scratch_doubles()) || !A.alloc(&N.part_arrive, normal_det_part_arrive_ints(N.nblk_max), true)) return false;
         // (always there: the communicator may be created after this workspace)
-        if(!A.alloc(&N.S_packed, (size_t)N.nblk_max * (N.nblk_max + 1) / 2 * kCholBlock * kCholBlock)) return false;
+        if(!A.alloc(&N.S_packed, normal_det_packed_doubles(N.nblk_max))) return false;
     }
     // the fused evaluation (fused_eval.cu): splined models with the core locked, boards of at most 128 corners
     N.fused = N.det_available && L.splined && !L.sel.do_optimize_intrinsics_core && L.sel.do_optimize_intrinsics_distortions &&
@@ -321,6 +320,18 @@ struct PhaseTimer
 //   32 cg  33 cn  34 update_lensq  35 edge  36 cauchy_lensq  37 gn_lensq  38 kc  39 expected improvement
 // ictl[]: 0 need_gn (the factorization kernels run only if set)  1 zero gradient
 enum { SC_CG = 32, SC_CN, SC_UPDATE, SC_EDGE, SC_CAUCHY2, SC_GN2, SC_KC, SC_EXPECTED, SC_N = 48 };
+
+// Sharded solves: the per-rank partial sums among the scalars -- [6..10] (eliminated part of |g|^2, the row sums of
+// |J g|^2) and [17..19] (eliminated parts of the Gauss-Newton dots) -- through ONE reduction: gathered to [50..57],
+// summed over the ranks there, scattered back
+__global__ void stage_partials_kernel(double* __restrict__ scal, bool gather)
+{
+    const int i = threadIdx.x;
+    if(blockIdx.x != 0 || i >= 8) return;
+    const int slot = i < 5 ? 6 + i : 17 + (i - 5);
+    if(gather) scal[50 + i] = scal[slot];
+    else       scal[slot] = scal[50 + i];
+}
 
 __global__ void cauchy_decide_kernel(double* __restrict__ scal, int* __restrict__ ictl, double trustregion)
 {
@@ -486,6 +497,7 @@ static bool dogleg_pass(mrcal_b200_problem* P, const mrcal_b200_solver_parameter
 
     // evaluate the cost function at op[which] and, in the same breath, find out which shared unknowns its rows touch:
     // the size of the reduced system then reaches the host with the same read as everything else
+    bool norm2_summed = false;
     auto evaluate = [&](int which) -> bool
     {
         const int a = T->mark();
@@ -502,7 +514,8 @@ static bool dogleg_pass(mrcal_b200_problem* P, const mrcal_b200_solver_parameter
         T->spans[0].push_back({a, T->mark()});
         info->Nevaluations++;
         const int b = T->mark();
-        if(!normal_prepare(P->dp, N, P->op[which], s, nl, N.fused)) return false;
+        // (sharded: the cost of this evaluation is summed over the ranks in the collective that unites the active sets)
+        if(!normal_prepare(P->dp, N, P->op[which], s, nl, N.fused, P->op[which].norm2, &norm2_summed)) return false;
         T->spans[1].push_back({b, T->mark()});
         return true;
     };
@@ -545,7 +558,7 @@ static bool dogleg_pass(mrcal_b200_problem* P, const mrcal_b200_solver_parameter
         {
             if(!evaluate(which)) return false;
             MB200_CUDA_CHECK(cudaMemcpyAsync(ws->scal + 22, P->op[which].norm2, sizeof(double), cudaMemcpyDeviceToDevice, s));
-            if(comm_active() && !comm_allreduce_sum(ws->scal + 22, 1, s)) return false;
+            if(comm_active() && !norm2_summed && !comm_allreduce_sum(ws->scal + 22, 1, s)) return false;
             if(!read_back()) return false;
             if(!(N.fused && N.h_stat[3] != 0)) return true;
             fprintf(stderr, "mrcal_b200: an observation touches more control points than the fused evaluation handles: "
@@ -599,27 +612,42 @@ static bool dogleg_pass(mrcal_b200_problem* P, const mrcal_b200_solver_parameter
                 else
                     jv_kernel<<<148 * 16, 256, 0, s>>>(P->d_rowptr, cur.Jcol, cur.Jval, N.g_full, cur.x, 0, Nrows_mine, ws->scal + 9);
                 *nl += 2;
-                // eliminated-range dots and the row sums are per-rank partial sums: slots [6..8] and [9..10] -> one reduction
-                if(comm_active() && !comm_allreduce_partial(ws->scal, s)) return false;
+                // eliminated-range dots and the row sums are per-rank partial sums. Sharded: they wait for the partial sums
+                // of the Gauss-Newton dots and go through ONE reduction with them (below)
                 have_cauchy = true;
             }
-            cauchy_decide_kernel<<<1, 32, 0, s>>>(ws->scal, ws->ictl, trustregion);
-            (*nl)++;
+            // Sharded solves always factor: whether the Cauchy point is outside the trust region (and the Gauss-Newton
+            // step unnecessary) is only known after that reduction. One collective less per iteration, and the rare
+            // unnecessary factorization costs less than a collective per iteration does
+            const bool sharded = comm_active();
+            if(!sharded || have_gn)
+            {
+                cauchy_decide_kernel<<<1, 32, 0, s>>>(ws->scal, ws->ictl, trustregion);
+                (*nl)++;
+            }
             bool factored_now = false;
             if(!have_gn)
             {
                 // ---- Gauss-Newton step: factor the reduced system, solve, back-substitute. The kernels look at ictl[0] and
                 // do nothing if the Cauchy point is outside the trust region
+                const int* run_if = sharded ? nullptr : ws->ictl;
                 const int a = T->mark();
-                if(!chol_factor(N.S, N.ldS, N.n_c, ws->invL, N.info + 1, s, nl, &ws->chol, ws->ictl)) return false;
+                if(!chol_factor(N.S, N.ldS, N.n_c, ws->invL, N.info + 1, s, nl, &ws->chol, run_if)) return false;
                 T->spans[2].push_back({a, T->mark()});
                 const int b = T->mark();
                 if(!normal_extract_y(N, ws->rhs, s, nl)) return false;
-                if(N.n_c > 0 && !chol_solve_backward(N.S, N.ldS, ws->invL, ws->rhs, N.ldS, N.info + 1, s, nl, &ws->chol, ws->ictl)) return false;
+                if(N.n_c > 0 && !chol_solve_backward(N.S, N.ldS, ws->invL, ws->rhs, N.ldS, N.info + 1, s, nl, &ws->chol, run_if)) return false;
                 if(!normal_expand_step(P->dp, N, P->op[P->cur], *lambda, ws->rhs, ws->ds_r, ws->step_gn, s, nl)) return false;
                 dots_kernel<<<3, 1024, 0, s>>>(ws->step_gn, N.g_full, e0, e1, Nstate, ws->scal + 11);
                 (*nl)++;
-                if(comm_active() && !comm_allreduce_sum(ws->scal + 17, 3, s)) return false;
+                if(sharded)
+                {
+                    stage_partials_kernel<<<1, 32, 0, s>>>(ws->scal, true);
+                    if(!comm_allreduce_sum(ws->scal + 50, 8, s)) return false;
+                    stage_partials_kernel<<<1, 32, 0, s>>>(ws->scal, false);
+                    cauchy_decide_kernel<<<1, 32, 0, s>>>(ws->scal, ws->ictl, trustregion);
+                    *nl += 3;
+                }
                 T->spans[3].push_back({b, T->mark()});
                 factored_now = true;
             }
@@ -641,9 +669,11 @@ static bool dogleg_pass(mrcal_b200_problem* P, const mrcal_b200_solver_parameter
                     set_error("the persistent factorization kernel gave up waiting for a tile (code -9): not a property of the matrix");
                     return false;
                 }
-                if(comm_active())
+                // sharded: a frame block that is singular on ONE rank has been reported to every rank with the reduced system
+                // itself (normal_det.cu:unpack_extras_kernel) and the factorization is replicated. The other assembly path
+                // asks around
+                if(comm_active() && !N.det)
                 {
-                    // a frame block that is singular on ONE rank must send every rank down the same path
                     ws->h_scal[SC_N] = (double)bad;
                     MB200_CUDA_CHECK(cudaMemcpyAsync(ws->scal + SC_N, ws->h_scal + SC_N, sizeof(double), cudaMemcpyHostToDevice, s));
                     if(!comm_allreduce_sum(ws->scal + SC_N, 1, s)) return false;
