@@ -252,25 +252,33 @@ struct alignas(16) TileSmemS
 constexpr size_t kTileSmemBody = sizeof(TileSmemA) > sizeof(TileSmemS) ? sizeof(TileSmemA) : sizeof(TileSmemS);
 constexpr size_t kTileSmem = sizeof(TileCommon) + kTileSmemBody;
 
-// worklist of the set bits of (rowA[w] & rowB[w]), w in [w0, w1), at most 64 words: ids -> sm.wl, count -> sm.count
+// worklist of the set bits of (rowA[w] & rowB[w]), w in [w0, w1), at most 64 words: ids -> sm.wl, count -> sm.count.
+// (the first two warps hold a word per lane; their scan goes through shuffles)
 __device__ __forceinline__ void build_worklist(TileCommon& sm, const unsigned* rowA, const unsigned* rowB, int w0, int w1)
 {
-    const int tid = threadIdx.x;
+    const int tid = threadIdx.x, lane = tid & 31;
     unsigned m = 0;
-    if(tid < w1 - w0) m = rowA[w0 + tid] & rowB[w0 + tid];
-    const int cnt = __popc(m);
-    sm.scan[tid] = cnt;
-    __syncthreads();
-    for(int o = 1; o < 256; o <<= 1)
+    int cnt = 0, inc = 0;
+    if(tid < 64)
     {
-        const int v = tid >= o ? sm.scan[tid - o] : 0;
-        __syncthreads();
-        sm.scan[tid] += v;
-        __syncthreads();
+        if(tid < w1 - w0) m = rowA[w0 + tid] & rowB[w0 + tid];
+        cnt = __popc(m);
+        inc = cnt;
+#pragma unroll
+        for(int o = 1; o < 32; o <<= 1)
+        {
+            const int v = __shfl_up_sync(0xffffffffu, inc, o);
+            if(lane >= o) inc += v;
+        }
+        if(lane == 31) sm.scan[tid >> 5] = inc;
     }
-    int pos = sm.scan[tid] - cnt;
-    while(m) { const int b = __ffs(m) - 1; m &= m - 1; sm.wl[pos++] = 32 * (w0 + tid) + b; }
-    if(tid == 255) sm.count = sm.scan[255];
+    __syncthreads();
+    if(tid < 64)
+    {
+        int pos = inc - cnt + (tid >= 32 ? sm.scan[0] : 0);
+        while(m) { const int b = __ffs(m) - 1; m &= m - 1; sm.wl[pos++] = 32 * (w0 + tid) + b; }
+    }
+    if(tid == 0) sm.count = sm.scan[0] + sm.scan[1];
     __syncthreads();
 }
 // ---- mbarrier / bulk-copy (TMA) plumbing of phase S
@@ -312,9 +320,13 @@ __device__ __forceinline__ void tile_row_col(int itile, int& r, int& c)
     c = itile - r * (r + 1) / 2;
 }
 
-// What each tile has to sum, and over how many CTAs: plan[itile] = (items, groups, parts, -). One warp per tile
+// What each tile has to sum, and over how many CTAs: plan[itile] = (items, groups, parts, -), then the numbers of items
+// and of groups in each stretch of 64 bitmap words (kPlanStretches + kPlanGroupStretches ints; a tile CTA walks past the
+// stretches that hold nothing of its share without looking at the bitmaps). One warp per tile
+constexpr int kPlanStretches = 32, kPlanGroupStretches = 8;
+constexpr int kPlanInts = 4 + kPlanStretches + kPlanGroupStretches;
 __global__ void __launch_bounds__(256)
-tile_plan_kernel(NormalBuffers N, int nblk, int items_per_part, int groups_per_part, bool can_split, int4* __restrict__ plan)
+tile_plan_kernel(NormalBuffers N, int nblk, int items_per_part, int groups_per_part, bool can_split, int* __restrict__ plan)
 {
     const int itile = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
     if(itile >= nblk * (nblk + 1) / 2) return;
@@ -323,23 +335,34 @@ tile_plan_kernel(NormalBuffers N, int nblk, int items_per_part, int groups_per_p
     const unsigned* wiA = N.wi_present + (size_t)r * N.wwords;
     const unsigned* wiB = N.wi_present + (size_t)c * N.wwords;
     int n_items = 0, n_groups = 0;
-    for(int w = lane; w < N.wwords; w += 32) n_items += __popc(wiA[w] & wiB[w]);
+    int* mine = plan + (size_t)itile * kPlanInts;
+    for(int st = 0; 64 * st < N.wwords; st++)
+    {
+        int cnt = 0;
+        for(int w = 64 * st + lane; w < min(64 * st + 64, N.wwords); w += 32) cnt += __popc(wiA[w] & wiB[w]);
+#pragma unroll
+        for(int o = 16; o > 0; o >>= 1) cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
+        if(lane == 0 && st < kPlanStretches) mine[4 + st] = cnt;
+        n_items += cnt;
+    }
     if(N.Ngroups > 0)
     {
         const unsigned* grA = N.grp_present + (size_t)r * N.gwords;
         const unsigned* grB = N.grp_present + (size_t)c * N.gwords;
-        for(int w = lane; w < N.gwords; w += 32) n_groups += __popc(grA[w] & grB[w]);
-    }
+        for(int st = 0; 64 * st < N.gwords; st++)
+        {
+            int cnt = 0;
+            for(int w = 64 * st + lane; w < min(64 * st + 64, N.gwords); w += 32) cnt += __popc(grA[w] & grB[w]);
 #pragma unroll
-    for(int o = 16; o > 0; o >>= 1)
-    {
-        n_items += __shfl_xor_sync(0xffffffffu, n_items, o);
-        n_groups += __shfl_xor_sync(0xffffffffu, n_groups, o);
+            for(int o = 16; o > 0; o >>= 1) cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
+            if(lane == 0 && st < kPlanGroupStretches) mine[4 + kPlanStretches + st] = cnt;
+            n_groups += cnt;
+        }
     }
     int parts = max((n_items + items_per_part - 1) / items_per_part, (n_groups + groups_per_part - 1) / groups_per_part);
     parts = min(kMaxParts, max(1, parts));
     if(itile >= kSplitTilesCap || !can_split) parts = 1;
-    if(lane == 0) plan[itile] = make_int4(n_items, n_groups, parts, 0);
+    if(lane == 0) { mine[0] = n_items; mine[1] = n_groups; mine[2] = parts; mine[3] = 0; }
 }
 
 // One CTA per (64x64 tile of the lower triangle of S, part). A tile that many items / groups reach -- the block row of
@@ -348,7 +371,7 @@ tile_plan_kernel(NormalBuffers N, int nblk, int items_per_part, int groups_per_p
 // partial tiles up in part order. Which part is last varies; what it computes does not.
 __global__ void __launch_bounds__(256, 2)
 schur_tiles_kernel(NormalBuffers N, double lambda, int n_c, int nblk, bool add_lambda, double* __restrict__ packed,
-                   double* __restrict__ part_scratch, int* __restrict__ part_arrive, const int4* __restrict__ plan)
+                   double* __restrict__ part_scratch, int* __restrict__ part_arrive, const int* __restrict__ plan)
 {
     extern __shared__ __align__(16) unsigned char dsm_raw[];
     TileCommon& sc = *reinterpret_cast<TileCommon*>(dsm_raw);
@@ -357,8 +380,8 @@ schur_tiles_kernel(NormalBuffers N, double lambda, int n_c, int nblk, bool add_l
     __shared__ int s_last;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int itile = (nblk * (nblk + 1) / 2 - 1) - (int)blockIdx.x;   // the late rows first: they carry the most work
-    const int4 pl = plan[itile];
-    const int n_items = pl.x, n_groups = pl.y, parts = pl.z;
+    const int* pl = plan + (size_t)itile * kPlanInts;
+    const int n_items = pl[0], n_groups = pl[1], parts = pl[2];
     const int part = blockIdx.y;
     if(part >= parts) return;
     int r, c;
@@ -383,6 +406,12 @@ schur_tiles_kernel(NormalBuffers N, double lambda, int n_c, int nblk, bool add_l
     int seen = 0;
     for(int w0 = 0; w0 < N.wwords && seen < item_hi; w0 += 64)
     {
+        // a stretch that holds nothing of this part's share: past it without a look at the bitmaps
+        if((w0 >> 6) < kPlanStretches)
+        {
+            const int cnt = pl[4 + (w0 >> 6)];
+            if(cnt == 0 || seen + cnt <= item_lo) { seen += cnt; continue; }
+        }
         build_worklist(sc, wiA, wiB, w0, min(w0 + 64, N.wwords));
         const int nwl = sc.count;
         // my share of this stretch of the worklist
@@ -502,6 +531,11 @@ schur_tiles_kernel(NormalBuffers N, double lambda, int n_c, int nblk, bool add_l
     unsigned bar_phase = 0;   // bit b: the parity the next wait on buffer b looks for
     for(int w0 = 0; w0 < N.gwords && N.Ngroups > 0 && seen < grp_hi; w0 += 64)
     {
+        if((w0 >> 6) < kPlanGroupStretches)
+        {
+            const int cnt = pl[4 + kPlanStretches + (w0 >> 6)];
+            if(cnt == 0 || seen + cnt <= grp_lo) { seen += cnt; continue; }
+        }
         build_worklist(sc, grA, grB, w0, min(w0 + 64, N.gwords));
         const int nwl_all = sc.count;
         const int lo = max(grp_lo - seen, 0), hi = min(grp_hi - seen, nwl_all);
@@ -847,7 +881,7 @@ bool normal_det_finish(const DevProblem& dp, NormalBuffers& N, const EvalBuffers
     const bool sharded = comm_active();
     if(sharded && N.S_packed == nullptr) { set_error("internal error: sharded solve without the packed tile buffer"); return false; }
     MB200_CUDA_CHECK(cudaMemsetAsync(N.part_arrive, 0, (size_t)kSplitTilesCap * sizeof(int), s));
-    int4* plan = reinterpret_cast<int4*>(N.part_arrive + kSplitTilesCap);
+    int* plan = N.part_arrive + kSplitTilesCap;
     static const int items_per_part = env_int("MRCAL_B200_TILE_ITEMS_PER_PART", 128), groups_per_part = env_int("MRCAL_B200_TILE_GROUPS_PER_PART", 96);
     tile_plan_kernel<<<(ntiles * 32 + 255) / 256, 256, 0, s>>>(N, nblk, items_per_part, groups_per_part, N.part_scratch != nullptr, plan);
     schur_tiles_kernel<<<dim3(ntiles, kMaxParts), 256, kTileSmem, s>>>(N, lambda, N.n_c, nblk, true, sharded ? N.S_packed : nullptr,
@@ -880,8 +914,8 @@ bool normal_det_finish(const DevProblem& dp, NormalBuffers& N, const EvalBuffers
 size_t normal_det_packed_doubles(int nblk_max) { return (size_t)nblk_max * (nblk_max + 1) / 2 * TB * TB + kPackedExtras; }
 // what the workspace must provide for the split tiles
 size_t normal_det_part_scratch_doubles() { return (size_t)kSplitTilesCap * kMaxParts * TB * TB; }
-// arrival counters of the split tiles, then the plan (int4 per tile)
-int normal_det_part_arrive_ints(int nblk_max) { return kSplitTilesCap + 4 * (nblk_max * (nblk_max + 1) / 2); }
+// arrival counters of the split tiles, then the plan (kPlanInts per tile)
+int normal_det_part_arrive_ints(int nblk_max) { return kSplitTilesCap + kPlanInts * (nblk_max * (nblk_max + 1) / 2); }
 
 bool normal_det_rhs(const NormalBuffers& N, cudaStream_t s, int* nlaunch)
 {
