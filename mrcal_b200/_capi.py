@@ -109,6 +109,7 @@ EXPORTED_SYMBOLS = (
     "mrcal_b200_problem_reduced_system",
     "mrcal_b200_problem_time_callback",
     "mrcal_b200_problem_triangulated_outliers",
+    "mrcal_b200_problem_drt_cross_reprojection__dbpacked",
     "mrcal_b200_nccl_get_unique_id", "mrcal_b200_nccl_comm_init", "mrcal_b200_nccl_comm_destroy",
     "mrcal_b200_problem_set_sharding",
     "mrcal_b200_factorization_create", "mrcal_b200_factorization_destroy",
@@ -148,6 +149,8 @@ lib.mrcal_b200_problem_create_triangulated.restype = C.c_void_p
 lib.mrcal_b200_problem_destroy.restype = None
 lib.mrcal_b200_problem_time_callback.restype = C.c_double
 lib.mrcal_b200_problem_triangulated_outliers.restype = C.c_int
+lib.mrcal_b200_problem_drt_cross_reprojection__dbpacked.restype = C.c_bool
+lib.mrcal_b200_problem_drt_cross_reprojection__dbpacked.argtypes = [C.c_void_p, C.c_int, C.c_void_p]
 lib.mrcal_b200_factorization_create_from_last_callback.restype = C.c_void_p
 lib.mrcal_b200_csr_create.restype = C.c_void_p
 lib.mrcal_b200_csr_destroy.restype = None

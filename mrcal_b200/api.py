@@ -314,6 +314,20 @@ def _require_gpu():
 ####################################################################################################
 # the hot path
 ####################################################################################################
+def drt_cross_reprojection__dbpacked(icam_intrinsics=-1, **kwargs):
+    """K = drt_ref_refperturbed/db_packed (icam_intrinsics < 0) or drt_cam_camperturbed/db_packed for that camera, as
+    mrcal.drt_cross_reprojection__dbpacked(icam_intrinsics=..., **optimization_inputs) returns it (mrcal-pywrap.c:2016-2110;
+    used by mrcal/model_analysis.py:1379,1441): shape (6, Nstate), zero outside the extrinsics, frames, points and
+    calobject_warp columns. The Jacobian is evaluated at the given state and reduced on the device
+    (csrc/cross_reprojection.cu; reference: _mrcal_drt_cross_reprojection__dbpacked, uncertainty.c:798)."""
+    _require_gpu()
+    P = Problem(**kwargs)
+    try:
+        return P.drt_cross_reprojection__dbpacked(icam_intrinsics)
+    finally:
+        P.close()
+
+
 def optimizer_callback(no_jacobian=False, no_factorization=False, **kwargs):
     """One evaluation of the cost function at the given seed.
 
@@ -493,6 +507,13 @@ class Problem:
                                              _ptr(I.calobject_warp) if I.calobject_warp is not None else None,
                                              _ptr(I.observations_board), _ptr(I.observations_point)):
             raise RuntimeError(_capi.last_error())
+
+    def drt_cross_reprojection__dbpacked(self, icam_intrinsics=-1):
+        """K (6, Nstate) at the problem's current state: see the module-level function."""
+        K = np.zeros((6, self.Nstate))
+        if not lib.mrcal_b200_problem_drt_cross_reprojection__dbpacked(self._h, int(icam_intrinsics), _ptr(K)):
+            raise RuntimeError("_mrcal_drt_cross_reprojection__dbpacked() failed: " + _capi.last_error())
+        return K
 
     def callback(self, jacobian=True):
         b = np.zeros(self.Nstate)

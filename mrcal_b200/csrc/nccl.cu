@@ -123,6 +123,29 @@ extern "C" bool mrcal_b200_nccl_comm_init(const void* id128, int rank, int nrank
     return true;
 }
 
+// Timing aid (not on any product path): device milliseconds per all-reduce (sum) of `count` doubles, back to back
+extern "C" double mrcal_b200_debug_time_allreduce(size_t count, int reps)
+{
+    if(!comm_active()) { set_error("no communicator"); return -1.; }
+    double* buf = nullptr;
+    cudaStream_t s;
+    if(cudaMalloc(&buf, count * sizeof(double)) != cudaSuccess || cudaMemset(buf, 0, count * sizeof(double)) != cudaSuccess ||
+       cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking) != cudaSuccess) return -1.;
+    cudaEvent_t e0, e1;
+    cudaEventCreate(&e0); cudaEventCreate(&e1);
+    for(int r = -3; r < reps; r++)
+    {
+        if(r == 0) cudaEventRecord(e0, s);
+        if(!comm_allreduce_sum(buf, count, s)) return -1.;
+    }
+    cudaEventRecord(e1, s);
+    cudaEventSynchronize(e1);
+    float ms = 0.f;
+    cudaEventElapsedTime(&ms, e0, e1);
+    cudaEventDestroy(e0); cudaEventDestroy(e1); cudaStreamDestroy(s); cudaFree(buf);
+    return ms / reps;
+}
+
 extern "C" void mrcal_b200_nccl_comm_destroy(void)
 {
     if(g_nccl.comm) { g_nccl.CommDestroy(g_nccl.comm); g_nccl.comm = nullptr; }

@@ -343,6 +343,37 @@ class Problem:
             J = scipy.sparse.csr_matrix((X, I, P), shape=(Nmeas, Nstate))
         return b, x, J
 
+    def drt_cross_reprojection__dbpacked(self, icam_intrinsics=-1):
+        """K = drt_ref_refperturbed/db_packed (icam_intrinsics < 0) or drt_cam_camperturbed/db_packed, shape (6, Nstate),
+        as mrcal.drt_cross_reprojection__dbpacked() returns it (mrcal-pywrap.c:2016-2110): the callback at the current
+        state, then _mrcal_drt_cross_reprojection__dbpacked() (uncertainty.c:798) into the extrinsics / frames / points /
+        calobject_warp columns of a zero matrix."""
+        b, x, J = self.callback()
+        Nstate, Nmeas = J.shape[1], J.shape[0]
+        P = np.ascontiguousarray(J.indptr, np.int32)
+        I = np.ascontiguousarray(J.indices, np.int32)
+        X = np.ascontiguousarray(J.data, np.float64)
+        Jt = CholmodSparse(nrow=Nstate, ncol=Nmeas, nzmax=len(X), p=P.ctypes.data, i=I.ctypes.data, x=X.ctypes.data,
+                           sorted=1, packed=1)
+        K = np.zeros((6, Nstate))
+        s0, s1 = K.strides
+
+        def sub(what):
+            i0 = self.state_index(what) if what == "calobject_warp" else self.state_index(what, 0)
+            if i0 < 0 or self.num_states_of(what) == 0:
+                return None
+            return C.c_void_p(K.ctypes.data + 8 * i0)
+        f = lib()._mrcal_drt_cross_reprojection__dbpacked
+        f.restype = C.c_bool
+        ok = f(sub("extrinsics"), C.c_int(s0), C.c_int(s1), sub("frames"), C.c_int(s0), C.c_int(s1),
+               sub("points"), C.c_int(s0), C.c_int(s1), sub("calobject_warp"), C.c_int(s0), C.c_int(s1),
+               C.c_int(icam_intrinsics), _dp(b), C.c_int(b.nbytes), C.byref(Jt),
+               self.Ncam_i, self.Ncam_e, self.Nframes, self.Npoints, self.Npoints_fixed, self.Nobs_board, self.Nobs_point,
+               C.byref(self.lensmodel), self.effective_selections(), self.W, self.H)
+        if not ok:
+            raise RuntimeError("reference _mrcal_drt_cross_reprojection__dbpacked() failed")
+        return K, b, J
+
     def optimize(self, verbose=False, iteration_cap=0):
         """The reference's own mrcal_optimize() (mrcal.c:6179) on top of the restated libdogleg
         (oracle/port/dogleg_port.c). Modifies this Problem's state arrays and observation weights in
