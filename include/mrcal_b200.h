@@ -522,7 +522,7 @@ int mrcal_b200_problem_triangulated_outliers(mrcal_b200_problem_t* problem, int*
 /* K = drt_ref_refperturbed/db_packed (icam_intrinsics < 0) or drt_cam_camperturbed/db_packed (that camera), shape
    (6, Nstate) row-major, zero outside the extrinsics / frames / points / calobject_warp columns: what
    mrcal.drt_cross_reprojection__dbpacked() returns (mrcal-pywrap.c:2016-2110), computed as the reference's
-   _mrcal_drt_cross_reprojection__dbpacked() defines it (mrcal.h:611-660, uncertainty.c:798-1577) from the Jacobian at the
+   internal entry point of the same name with a leading underscore defines it (mrcal.h:611-660, uncertainty.c:798-1577) from the Jacobian at the
    problem's current state, which is evaluated on the device by this call. The reference's entry point takes a CHOLMOD
    matrix of J on the host; this one takes the device-resident problem (the Jacobian never leaves the GPU). Refuses what
    the reference refuses (uncertainty.c:944-989). */
