@@ -349,7 +349,8 @@ __device__ __forceinline__ void tile_to_global(double* __restrict__ dst, size_t 
 //   tile (j+2, j);  pre(j+2);  tiles (i, j), i = j+3 .. nb-1
 // Every task depends on spine steps and on EARLIER helper tasks only; the spine depends on its own past and on pre
 // tasks: no cycles, all CTAs co-resident, every CTA walks its list in order: no deadlock. Waits are bounded as above.
-__global__ void __launch_bounds__(256, 1)
+// (registers capped -- no spills at 160 -- so that the small kernels of the Cauchy side fit next to a CTA of this one)
+__global__ void __maxnreg__(160)
 chol_spine_kernel(double* __restrict__ A, int ld, int nb, int nreal, double* __restrict__ invL, int* __restrict__ info,
                   int* __restrict__ flags, int* __restrict__ pre, int* __restrict__ abort_flag, const int* __restrict__ run_if,
                   long long* __restrict__ stamps /* debugging aid: 8 clock64() values per spine step, or NULL */)

@@ -597,40 +597,57 @@ static bool dogleg_pass(mrcal_b200_problem* P, const mrcal_b200_solver_parameter
                 have_system = true;
                 have_cauchy = have_gn = false;
             }
-            // ---- Cauchy step: -k g, k = |g|^2 / |J g|^2
+            // ---- Cauchy step: -k g, k = |g|^2 / |J g|^2. Its sums need nothing of the factorization and the factorization
+            // nothing of them: they run on a second stream, UNDER the factorization (whose spine leaves the machine mostly
+            // idle). The price: whether the Cauchy point already leaves the trust region -- and the Gauss-Newton step is
+            // unnecessary -- is only known afterwards, so every new operating point is factored; the rare unnecessary
+            // factorization (the first few steps of a solve) costs less than ~50 us on the critical path of every step
+            const bool overlap = N.s_side[0] != nullptr && getenv("MRCAL_B200_NO_OVERLAP") == nullptr;
             if(!have_cauchy)
             {
                 MB200_CUDA_CHECK(cudaMemsetAsync(ws->scal, 0, 32 * sizeof(double), s));
-                dots_kernel<<<3, 1024, 0, s>>>(N.g_full, nullptr, e0, e1, Nstate, ws->scal + 0);
+                cudaStream_t sc = s;
+                if(overlap)
+                {
+                    sc = N.s_side[0];
+                    MB200_CUDA_CHECK(cudaEventRecord(N.ev_fork, s));
+                    MB200_CUDA_CHECK(cudaStreamWaitEvent(sc, N.ev_fork, 0));
+                }
+                dots_kernel<<<3, 1024, 0, sc>>>(N.g_full, nullptr, e0, e1, Nstate, ws->scal + 0);
                 if(N.fused)
                 {
                     // |J g|^2: the board rows from the observations' blocks, the others from their stored rows
-                    if(!launch_quadform_boards(P->dp, N, N.g_full, N.qf_part, ws->scal + 10, s, nl)) return false;
+                    if(!launch_quadform_boards(P->dp, N, N.g_full, N.qf_part, ws->scal + 10, sc, nl)) return false;
                     if(Nrows_mine > P->dp.m_point0)
-                        jv_kernel<<<148 * 4, 256, 0, s>>>(P->d_rowptr, cur.Jcol, cur.Jval, N.g_full, cur.x, P->dp.m_point0, Nrows_mine, ws->scal + 9);
+                        jv_kernel<<<148 * 4, 256, 0, sc>>>(P->d_rowptr, cur.Jcol, cur.Jval, N.g_full, cur.x, P->dp.m_point0, Nrows_mine, ws->scal + 9);
                 }
                 else
-                    jv_kernel<<<148 * 16, 256, 0, s>>>(P->d_rowptr, cur.Jcol, cur.Jval, N.g_full, cur.x, 0, Nrows_mine, ws->scal + 9);
+                    jv_kernel<<<148 * 16, 256, 0, sc>>>(P->d_rowptr, cur.Jcol, cur.Jval, N.g_full, cur.x, 0, Nrows_mine, ws->scal + 9);
                 *nl += 2;
+                if(overlap) MB200_CUDA_CHECK(cudaEventRecord(N.ev_join[0], sc));
                 // eliminated-range dots and the row sums are per-rank partial sums. Sharded: they wait for the partial sums
                 // of the Gauss-Newton dots and go through ONE reduction with them (below)
                 have_cauchy = true;
             }
-            // Sharded solves always factor: whether the Cauchy point is outside the trust region (and the Gauss-Newton
-            // step unnecessary) is only known after that reduction. One collective less per iteration, and the rare
-            // unnecessary factorization costs less than a collective per iteration does
             const bool sharded = comm_active();
-            if(!sharded || have_gn)
+            if(have_gn)
             {
+                // (same operating point, smaller trust region: everything is there)
                 cauchy_decide_kernel<<<1, 32, 0, s>>>(ws->scal, ws->ictl, trustregion);
                 (*nl)++;
             }
             bool factored_now = false;
             if(!have_gn)
             {
-                // ---- Gauss-Newton step: factor the reduced system, solve, back-substitute. The kernels look at ictl[0] and
-                // do nothing if the Cauchy point is outside the trust region
-                const int* run_if = sharded ? nullptr : ws->ictl;
+                // ---- Gauss-Newton step: factor the reduced system, solve, back-substitute. Without the overlap (and not
+                // sharded) the kernels look at ictl[0] and do nothing if the Cauchy point is outside the trust region
+                const int* run_if = nullptr;
+                if(!sharded && !overlap)
+                {
+                    cauchy_decide_kernel<<<1, 32, 0, s>>>(ws->scal, ws->ictl, trustregion);
+                    (*nl)++;
+                    run_if = ws->ictl;
+                }
                 const int a = T->mark();
                 if(!chol_factor(N.S, N.ldS, N.n_c, ws->invL, N.info + 1, s, nl, &ws->chol, run_if)) return false;
                 T->spans[2].push_back({a, T->mark()});
@@ -640,13 +657,18 @@ static bool dogleg_pass(mrcal_b200_problem* P, const mrcal_b200_solver_parameter
                 if(!normal_expand_step(P->dp, N, P->op[P->cur], *lambda, ws->rhs, ws->ds_r, ws->step_gn, s, nl)) return false;
                 dots_kernel<<<3, 1024, 0, s>>>(ws->step_gn, N.g_full, e0, e1, Nstate, ws->scal + 11);
                 (*nl)++;
+                if(overlap) MB200_CUDA_CHECK(cudaStreamWaitEvent(s, N.ev_join[0], 0));
                 if(sharded)
                 {
                     stage_partials_kernel<<<1, 32, 0, s>>>(ws->scal, true);
                     if(!comm_allreduce_sum(ws->scal + 50, 8, s)) return false;
                     stage_partials_kernel<<<1, 32, 0, s>>>(ws->scal, false);
+                    *nl += 2;
+                }
+                if(sharded || overlap)
+                {
                     cauchy_decide_kernel<<<1, 32, 0, s>>>(ws->scal, ws->ictl, trustregion);
-                    *nl += 3;
+                    (*nl)++;
                 }
                 T->spans[3].push_back({b, T->mark()});
                 factored_now = true;
