@@ -153,13 +153,15 @@ struct ObsGeometry   // per observation, in shared memory
 
 // One CTA per board observation, one thread per corner (strided if W*H > blockDim)
 template <int KIND, bool WITH_J>
-__global__ void __launch_bounds__(256)
+__global__ void __maxnreg__(160)   // 3 CTAs of 128 threads per SM
 eval_boards_kernel(DevProblem P, double* __restrict__ x, double* __restrict__ Jval, int* __restrict__ Jcol,
                    double* __restrict__ norm2)
 {
     __shared__ ObsGeometry G;
     __shared__ double red[32];
     __shared__ int s_ivar0[256];   // per corner: where its spline window starts (the only data-dependent column index)
+    __shared__ __align__(8) int s_pat[2 * 256]; // per entry of a corner's two rows: its column for a window at 0, and whether the window's
+                                   // start adds to it (pattern[2 e], pattern[2 e + 1]): the same for every corner of the view
     // Jacobian staging: each thread (corner) deposits the VALUES of its two rows here -- 2*nnz_row contiguous
     // doubles, which is also how they sit in J -- and hands them to the TMA: one bulk shared->global copy per
     // corner (cp.async.bulk), no thread spends time on the value stores. The column indices are not staged at all:
@@ -204,6 +206,42 @@ eval_boards_kernel(DevProblem P, double* __restrict__ x, double* __restrict__ Jv
     int stride = row2;
     while((stride & 3) != 2) stride++;
     const int nI = P.nnz_row_intr;
+    if constexpr(WITH_J)
+    {
+        // the column pattern of this view's rows (mrcal.c:4575-4760 lay the rows out in this order): once per CTA
+        const int ncore = P.opt_core ? 2 : 0;
+        for(int e = threadIdx.x; e < row2 && e < 256; e += blockDim.x)
+        {
+            const int i_xy = e >= nnz_row ? 1 : 0, k = e - i_xy * nnz_row;
+            int col, dep = 0;
+            if(k < nI)
+            {
+                if(k < ncore) col = i_var_intr + i_xy + 2 * k;
+                else if constexpr(LensTraits<KIND>::SPLINED)
+                {
+                    constexpr int RUN = LensTraits<KIND>::RUN;
+                    const int kk = k - ncore, iy = kk / RUN, ix = kk - iy * RUN;
+                    col = i_var_intr + iy * 2 * P.Nx + ix * 2 + i_xy;
+                    dep = 1;
+                }
+                else col = i_var_intr + P.Ncore_state + (k - ncore);
+            }
+            else
+            {
+                int kk = k - nI;
+                if(emit_cam && kk < 6) col = i_var_cam + kk;
+                else
+                {
+                    if(emit_cam) kk -= 6;
+                    if(P.opt_frames && kk < 6) col = i_var_frame + kk;
+                    else { if(P.opt_frames) kk -= 6; col = P.i_warp0 + kk; }
+                }
+            }
+            s_pat[2 * e] = col;
+            s_pat[2 * e + 1] = dep;
+        }
+        // (visible to everybody after the barrier that precedes the first use below)
+    }
 
     double sumsq = 0.;
     for(int ipt0 = 0; ipt0 < NWH; ipt0 += blockDim.x)
@@ -346,43 +384,19 @@ eval_boards_kernel(DevProblem P, double* __restrict__ x, double* __restrict__ Jv
       }
       if constexpr(WITH_J)
       {
-        // the column indices of this chunk of corners: a warp per corner, a lane per entry (coalesced stores; no divisions
-        // by run-time values on the way)
+        // the column indices of this chunk of corners: a warp per corner, a lane per entry (coalesced stores): the view's
+        // pattern plus, for the entries of the spline window, where this corner's window starts
         __syncthreads();
         const int nhere = min((int)blockDim.x, NWH - ipt0);
         const size_t gbase = (size_t)P.board_j0[iobs] + (size_t)ipt0 * row2;
-        const int ncore = P.opt_core ? 2 : 0;
         const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
         for(int t = wib; t < nhere; t += nwarps)
         {
             const int iv0 = s_ivar0[t];
             for(int e = lane; e < row2; e += 32)
             {
-                const int i_xy = e >= nnz_row ? 1 : 0, k = e - i_xy * nnz_row;
-                int col;
-                if(k < nI)
-                {
-                    if(k < ncore) col = i_var_intr + i_xy + 2 * k;
-                    else if constexpr(LensTraits<KIND>::SPLINED)
-                    {
-                        constexpr int RUN = LensTraits<KIND>::RUN;
-                        const int kk = k - ncore, iy = kk / RUN, ix = kk - iy * RUN;   // RUN is a compile-time 3 or 4
-                        col = i_var_intr + iv0 + iy * 2 * P.Nx + ix * 2 + i_xy;
-                    }
-                    else col = i_var_intr + P.Ncore_state + (k - ncore);
-                }
-                else
-                {
-                    int kk = k - nI;
-                    if(emit_cam && kk < 6) col = i_var_cam + kk;
-                    else
-                    {
-                        if(emit_cam) kk -= 6;
-                        if(P.opt_frames && kk < 6) col = i_var_frame + kk;
-                        else { if(P.opt_frames) kk -= 6; col = P.i_warp0 + kk; }
-                    }
-                }
-                Jcol[gbase + (size_t)t * row2 + e] = col;
+                const int2 pd = *reinterpret_cast<const int2*>(&s_pat[2 * e]);
+                Jcol[gbase + (size_t)t * row2 + e] = pd.x + (pd.y ? iv0 : 0);
             }
         }
         // the staging buffer is reused by the next chunk of corners: wait until the TMA has READ it

@@ -466,7 +466,6 @@ schur_tiles_kernel(NormalBuffers N, double lambda, int n_c, int nblk, bool add_l
                     int t_item[8], t_row[8];
                     double v0[8], v1[8];
                     int cnt = 0;
-                    bool wide = false;   // does any task of the batch reach past column 32 of its item's stretch? (rarely)
 #pragma unroll
                     for(int u = 0; u < 8; u++)
                     {
@@ -482,7 +481,6 @@ schur_tiles_kernel(NormalBuffers N, double lambda, int n_c, int nblk, bool add_l
                         }
                         if(cur0) { t_item[u] = ti; t_row[u] = __ffs(cur0) - 1; cur0 &= cur0 - 1; cnt++; }
                         else if(cur1) { t_item[u] = ti; t_row[u] = 32 + __ffs(cur1) - 1; cur1 &= cur1 - 1; cnt++; }
-                        if(t_item[u] >= 0) wide = wide || (sa.meta[t_item[u]][1] >> 8) > 32;
                     }
                     if(cnt == 0) break;
 #pragma unroll
@@ -496,7 +494,7 @@ schur_tiles_kernel(NormalBuffers N, double lambda, int n_c, int nblk, bool add_l
                         // lower triangle of the item's block: local column <= local row (always true off the diagonal tiles)
                         const double* row = N.wi_A + sa.base[i] + (size_t)a * sa.meta[i][2] + b0;
                         if(lane < nb && b0 + lane <= a) v0[u] = __ldg(row + lane);
-                        if(wide && lane + 32 < nb && b0 + lane + 32 <= a) v1[u] = __ldg(row + lane + 32);
+                        if(lane + 32 < nb && b0 + lane + 32 <= a) v1[u] = __ldg(row + lane + 32);
                     }
 #pragma unroll
                     for(int u = 0; u < 8; u++)
@@ -507,7 +505,7 @@ schur_tiles_kernel(NormalBuffers N, double lambda, int n_c, int nblk, bool add_l
                         const int b0 = sa.meta[i][1] & 255, nb = sa.meta[i][1] >> 8;
                         double* trow = sa.tile + (int)sa.rl[i][t_row[u]] * TLD;
                         if(lane < nb && b0 + lane <= a) trow[sa.cl[i][lane]] += v0[u];
-                        if(wide && lane + 32 < nb && b0 + lane + 32 <= a) trow[sa.cl[i][lane + 32]] += v1[u];
+                        if(lane + 32 < nb && b0 + lane + 32 <= a) trow[sa.cl[i][lane + 32]] += v1[u];
                     }
                 }
             }

@@ -74,8 +74,9 @@ def test_optimize_matches_cpu_restatement(ref, lensmodel, Ncameras, Nframes):
     # packed-state agreement at the converged point: limited by how flat the cost is along the least-constrained
     # direction (the spline knots at the edge of the data; CAHVOR's r1/r2 terms), not by the arithmetic
     tol_b = 5e-3 if "SPLINED" in lensmodel else 1e-4 if "CAHVOR" in lensmodel else 1e-5
-    # (CAHVOR: the two runs stop a step apart in a flat valley; the cost agrees to 1e-7 rather than 1e-9)
-    check_parity(r_gpu, kw_gpu, r_cpu, tol_b=tol_b, tol_cost=1e-7 if "CAHVOR" in lensmodel else 1e-9)
+    # (CAHVOR: the two runs stop a step apart in a flat valley; the cost agrees to a few 1e-7 rather than 1e-9 -- which
+    # side of the stopping threshold the last step falls on moves with the summation order of the factorization)
+    check_parity(r_gpu, kw_gpu, r_cpu, tol_b=tol_b, tol_cost=5e-7 if "CAHVOR" in lensmodel else 1e-9)
     assert r_gpu["rms_reproj_error__pixels"] < 0.3
 
 
