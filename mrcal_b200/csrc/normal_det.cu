@@ -463,13 +463,18 @@ schur_tiles_kernel(NormalBuffers N, double lambda, int n_c, int nblk, bool add_l
                 bool exhausted = false;
                 while(!exhausted || cur0 || cur1)
                 {
-                    int t_item[8], t_row[8];
-                    double v0[8], v1[8];
+                    // every task is decoded ONCE: where its values are (an element offset into the pool), where they go
+                    // in the tile, which of the lane's two columns exist. The kernel is bound by the instructions it
+                    // issues here, not by the latency of the loads: 4 tasks in flight are enough
+                    constexpr int NT = 4;
+                    unsigned src[NT];
+                    int dst0[NT], dst1[NT];
+                    unsigned have = 0;   // bit 2u: column `lane` of task u exists, bit 2u+1: column lane+32
                     int cnt = 0;
 #pragma unroll
-                    for(int u = 0; u < 8; u++)
+                    for(int u = 0; u < NT; u++)
                     {
-                        t_item[u] = -1;
+                        int item = -1, lrow = 0;
                         while(!exhausted && cur0 == 0 && cur1 == 0)
                         {
                             ti++;
@@ -479,33 +484,35 @@ schur_tiles_kernel(NormalBuffers N, double lambda, int n_c, int nblk, bool add_l
                             cur0 = __ballot_sync(0xffffffffu, lane < na && (sa.rl[ti][lane] & 7) == warp);
                             cur1 = __ballot_sync(0xffffffffu, lane + 32 < na && (sa.rl[ti][lane + 32] & 7) == warp);
                         }
-                        if(cur0) { t_item[u] = ti; t_row[u] = __ffs(cur0) - 1; cur0 &= cur0 - 1; cnt++; }
-                        else if(cur1) { t_item[u] = ti; t_row[u] = 32 + __ffs(cur1) - 1; cur1 &= cur1 - 1; cnt++; }
+                        if(cur0) { item = ti; lrow = __ffs(cur0) - 1; cur0 &= cur0 - 1; cnt++; }
+                        else if(cur1) { item = ti; lrow = 32 + __ffs(cur1) - 1; cur1 &= cur1 - 1; cnt++; }
+                        src[u] = 0u; dst0[u] = dst1[u] = 0;
+                        if(item >= 0)
+                        {
+                            const int a = (sa.meta[item][0] & 255) + lrow;
+                            const int b0 = sa.meta[item][1] & 255, nb = sa.meta[item][1] >> 8;
+                            // lower triangle of the item's block: local column <= local row (always true off the diagonal tiles)
+                            const bool p0 = lane < nb && b0 + lane <= a, p1 = lane + 32 < nb && b0 + lane + 32 <= a;
+                            have |= (p0 ? 1u : 0u) << (2 * u) | (p1 ? 2u : 0u) << (2 * u);
+                            src[u] = (unsigned)(sa.base[item] + (long long)a * sa.meta[item][2] + b0 + lane);
+                            const int trow = (int)sa.rl[item][lrow] * TLD;
+                            dst0[u] = trow + (p0 ? sa.cl[item][lane] : 0);
+                            dst1[u] = trow + (p1 ? sa.cl[item][lane + 32] : 0);
+                        }
                     }
                     if(cnt == 0) break;
+                    double v0[NT], v1[NT];
 #pragma unroll
-                    for(int u = 0; u < 8; u++)
+                    for(int u = 0; u < NT; u++)
                     {
-                        v0[u] = v1[u] = 0.;
-                        if(t_item[u] < 0) continue;
-                        const int i = t_item[u];
-                        const int a = (sa.meta[i][0] & 255) + t_row[u];
-                        const int b0 = sa.meta[i][1] & 255, nb = sa.meta[i][1] >> 8;
-                        // lower triangle of the item's block: local column <= local row (always true off the diagonal tiles)
-                        const double* row = N.wi_A + sa.base[i] + (size_t)a * sa.meta[i][2] + b0;
-                        if(lane < nb && b0 + lane <= a) v0[u] = __ldg(row + lane);
-                        if(lane + 32 < nb && b0 + lane + 32 <= a) v1[u] = __ldg(row + lane + 32);
+                        v0[u] = (have >> (2 * u)) & 1u ? __ldg(N.wi_A + src[u]) : 0.;
+                        v1[u] = (have >> (2 * u + 1)) & 1u ? __ldg(N.wi_A + src[u] + 32) : 0.;
                     }
 #pragma unroll
-                    for(int u = 0; u < 8; u++)
+                    for(int u = 0; u < NT; u++)
                     {
-                        if(t_item[u] < 0) continue;
-                        const int i = t_item[u];
-                        const int a = (sa.meta[i][0] & 255) + t_row[u];
-                        const int b0 = sa.meta[i][1] & 255, nb = sa.meta[i][1] >> 8;
-                        double* trow = sa.tile + (int)sa.rl[i][t_row[u]] * TLD;
-                        if(lane < nb && b0 + lane <= a) trow[sa.cl[i][lane]] += v0[u];
-                        if(lane + 32 < nb && b0 + lane + 32 <= a) trow[sa.cl[i][lane + 32]] += v1[u];
+                        if((have >> (2 * u)) & 1u) sa.tile[dst0[u]] += v0[u];
+                        if((have >> (2 * u + 1)) & 1u) sa.tile[dst1[u]] += v1[u];
                     }
                 }
             }

@@ -207,6 +207,12 @@ static bool build_workspace(mrcal_b200_problem* P)
         const int lda_board = even(std::min(N.capA, (L.splined ? 160 : L.Nintr_state + 8) + 2));
         const int lda_point = even(std::min(N.capA, (L.splined ? 2 * 16 + 4 + 6 : L.Nintr_state + 6) + 2));
         N.A_pool = (long long)L.d.Nobs_board * lda_board * lda_board + (long long)L.d.Nobs_point * lda_point * lda_point;
+        // (schur_tiles_kernel addresses the pool with 32-bit element offsets: 4 G doubles = 34 GB, more than a problem this
+        // library's other buffers would leave room for)
+        if(N.A_pool >= (1ll << 32)) N.det_available = false;
+    }
+    if(N.det_available)
+    {
         N.gwords = (N.Ngroups + 31) / 32; if(N.gwords < 1) N.gwords = 1;
         N.wwords = (Nwi + 31) / 32;
         N.bwords = (N.nblk_max + 31) / 32;

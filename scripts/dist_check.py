@@ -20,6 +20,13 @@ which = sys.argv[1] if len(sys.argv) > 1 else "small"
 if which == "small":
     kw, _ = synthetic.make_problem(lensmodel="LENSMODEL_SPLINED_STEREOGRAPHIC_order=3_Nx=8_Ny=6_fov_x_deg=100", Ncameras=2,
                                    Nframes=40, W=6, H=5, seed=2, pixel_noise=0.2)
+elif which == "outliers":
+    # gross outliers and outlier rejection on: the sharded markOutliers() against the single-GPU one
+    sys.path.insert(0, "tests")
+    import problems
+    kw, _ = synthetic.baseline_config(1, pixel_noise=0.3)
+    problems.inject_gross_outliers(kw, 0.01, 101)
+    kw["do_apply_outlier_rejection"] = True
 elif which == "points":
     kw, _ = synthetic.make_problem(lensmodel="LENSMODEL_OPENCV4", Ncameras=3, Nframes=9, W=6, H=5, seed=4,
                                    pixel_noise=0.2, Npoints=12, Npoints_fixed=3, which="some")
@@ -38,7 +45,7 @@ if rank == 0:
     kw1 = {k: (v.copy() if isinstance(v, np.ndarray) else v) for k, v in kw.items()}
     kw1["do_apply_outlier_rejection"] = False
     mrcal_b200._capi.lib.mrcal_b200_nccl_comm_destroy() if world == 1 else None
-print(f"rank {rank}: iterations {s['Niterations']} norm2 {s['norm2_x_final']:.9g} ms {s['ms_total']:.1f} "
+print(f"rank {rank}: outer passes {s['Nouter']} outliers {s['Noutliers_board']} iterations {s['Niterations']} norm2 {s['norm2_x_final']:.9g} ms {s['ms_total']:.1f} "
       f"(eval {s['ms_evaluate']:.1f} assemble {s['ms_assemble']:.1f} factor {s['ms_factor']:.1f} solve {s['ms_solve']:.1f})", flush=True)
 # every rank must have taken identical decisions
 t = torch.tensor([s["Niterations"], s["norm2_x_final"]], device="cuda", dtype=torch.float64)
