@@ -111,7 +111,7 @@ bool normal_det_finish(const DevProblem& dp, NormalBuffers& N, const EvalBuffers
                        double lambda, cudaStream_t s, int* nlaunch);
 bool normal_det_item_prepare(const DevProblem& dp, NormalBuffers& N, cudaStream_t s, int* nlaunch);   // after the compaction
 bool normal_det_item_offsets(const DevProblem& dp, NormalBuffers& N, cudaStream_t s, int* nlaunch);   // before it
-size_t normal_det_part_scratch_doubles();
+size_t normal_det_part_scratch_doubles(int nblk_max);
 int normal_det_part_arrive_ints(int nblk_max);
 size_t normal_det_packed_doubles(int nblk_max);
 bool normal_det_rhs(const NormalBuffers& N, cudaStream_t s, int* nlaunch);   // after the cross-rank reduction of S

@@ -309,8 +309,9 @@ __device__ __forceinline__ void bulk_load(void* smem, const void* gmem, unsigned
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory"); }
 
 constexpr int kPackedExtras = 8;      // doubles behind the packed tiles (sharded solves)
-constexpr int kMaxParts = 8;          // a tile's contributors may be split over this many CTAs
-constexpr int kSplitTilesCap = 2048;  // tiles with a slot in the partial-sum scratch (beyond: one CTA does it all)
+constexpr int kMaxParts = 64;         // a tile's contributors may be split over this many CTAs
+constexpr int kCtasPerTile = 4;       // the grid: this many CTAs per tile on average (kernel_ctas()); parts are cut to fit
+__host__ __device__ inline int kernel_ctas(int ntiles) { return kCtasPerTile * ntiles; }
 
 __device__ __forceinline__ void tile_row_col(int itile, int& r, int& c)
 {
@@ -326,7 +327,7 @@ __device__ __forceinline__ void tile_row_col(int itile, int& r, int& c)
 constexpr int kPlanStretches = 32, kPlanGroupStretches = 8;
 constexpr int kPlanInts = 4 + kPlanStretches + kPlanGroupStretches;
 __global__ void __launch_bounds__(256)
-tile_plan_kernel(NormalBuffers N, int nblk, int items_per_part, int groups_per_part, bool can_split, int* __restrict__ plan)
+tile_plan_kernel(NormalBuffers N, int nblk, int ns_per_item, int ns_per_group, int ns_per_part, bool can_split, int* __restrict__ plan)
 {
     const int itile = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
     if(itile >= nblk * (nblk + 1) / 2) return;
@@ -359,10 +360,73 @@ tile_plan_kernel(NormalBuffers N, int nblk, int items_per_part, int groups_per_p
             n_groups += cnt;
         }
     }
-    int parts = max((n_items + items_per_part - 1) / items_per_part, (n_groups + groups_per_part - 1) / groups_per_part);
+    // what the tile costs one CTA (measured: ~1 us per item of phase A, ~0.27 us per group of phase S), cut into parts of
+    // ns_per_part each: the kernel ends when its longest CTA does
+    const long cost = (long)n_items * ns_per_item + (long)n_groups * ns_per_group;
+    int parts = (int)((cost + ns_per_part - 1) / ns_per_part);
     parts = min(kMaxParts, max(1, parts));
-    if(itile >= kSplitTilesCap || !can_split) parts = 1;
+    if(!can_split) parts = 1;
     if(lane == 0) { mine[0] = n_items; mine[1] = n_groups; mine[2] = parts; mine[3] = 0; }
+}
+
+// The CTAs of schur_tiles_kernel: cta[k] = (tile << 8) | part, the tiles in the kernel's order (late block rows first: they
+// carry the most work), the parts of a tile next to each other: slot k of the partial-sum scratch belongs to CTA k, so a
+// tile's partial sums are contiguous. The grid holds kernel_ctas(ntiles) CTAs: every tile gets one, the parts beyond
+// that as long as there is room. plan[tile][2] <- the parts it got, plan[tile][3] <- its first slot; cta[nctas_max] <- the
+// number of CTAs with work. One CTA of 1024 threads
+__global__ void __launch_bounds__(1024)
+tile_slots_kernel(int ntiles, int* __restrict__ plan, int* __restrict__ cta)
+{
+    __shared__ int s_scan[1024];
+    __shared__ int s_carry, s_room;
+    const int tid = threadIdx.x;
+    const int nctas_max = kernel_ctas(ntiles);
+    if(tid == 0) { s_carry = 0; s_room = nctas_max - ntiles; }
+    // if the tiles wish for more extra parts than there is room for, every wish is scaled down alike
+    long wish = 0;
+    for(int k = tid; k < ntiles; k += 1024) wish += plan[(size_t)k * kPlanInts + 2] - 1;
+    s_scan[tid] = (int)wish;
+    __syncthreads();
+    for(int o = 512; o > 0; o >>= 1) { if(tid < o) s_scan[tid] += s_scan[tid + o]; __syncthreads(); }
+    const long wish_total = s_scan[0];
+    __syncthreads();
+    for(int k0 = 0; k0 < ntiles; k0 += 1024)
+    {
+        const int k = k0 + tid;                        // position in launch order
+        const int itile = ntiles - 1 - k;
+        int extra = k < ntiles ? plan[(size_t)itile * kPlanInts + 2] - 1 : 0;
+        if(wish_total > nctas_max - ntiles) extra = (int)((long)extra * (nctas_max - ntiles) / wish_total);
+        // the extra parts, granted in launch order while there is room: inclusive scan of the wishes
+        s_scan[tid] = extra;
+        __syncthreads();
+        for(int o = 1; o < 1024; o <<= 1)
+        {
+            const int v = tid >= o ? s_scan[tid - o] : 0;
+            __syncthreads();
+            s_scan[tid] += v;
+            __syncthreads();
+        }
+        const int before = s_scan[tid] - extra;        // extra parts wished for by the tiles ahead of this one in the chunk
+        const int room = s_room;
+        const int granted = max(0, min(extra, room - before));
+        // slots: the tiles ahead took (their 1 + granted): granted_before = min(before, room)
+        const int slot0 = s_carry + tid + min(before, room);
+        if(k < ntiles)
+        {
+            plan[(size_t)itile * kPlanInts + 2] = 1 + granted;
+            plan[(size_t)itile * kPlanInts + 3] = slot0;
+            for(int p = 0; p <= granted; p++) cta[slot0 + p] = (itile << 8) | p;
+        }
+        __syncthreads();
+        if(tid == 1023)
+        {
+            const int used = min(s_scan[1023], room);
+            s_carry += min(1024, ntiles - k0) + used;
+            s_room = room - used;
+        }
+        __syncthreads();
+    }
+    if(tid == 0) cta[nctas_max] = s_carry;
 }
 
 // One CTA per (64x64 tile of the lower triangle of S, part). A tile that many items / groups reach -- the block row of
@@ -371,7 +435,8 @@ tile_plan_kernel(NormalBuffers N, int nblk, int items_per_part, int groups_per_p
 // partial tiles up in part order. Which part is last varies; what it computes does not.
 __global__ void __launch_bounds__(256, 2)
 schur_tiles_kernel(NormalBuffers N, double lambda, int n_c, int nblk, bool add_lambda, double* __restrict__ packed,
-                   double* __restrict__ part_scratch, int* __restrict__ part_arrive, const int* __restrict__ plan)
+                   double* __restrict__ part_scratch, int* __restrict__ part_arrive, const int* __restrict__ plan,
+                   const int* __restrict__ cta)
 {
     extern __shared__ __align__(16) unsigned char dsm_raw[];
     TileCommon& sc = *reinterpret_cast<TileCommon*>(dsm_raw);
@@ -379,11 +444,11 @@ schur_tiles_kernel(NormalBuffers N, double lambda, int n_c, int nblk, bool add_l
     TileSmemS& ss = *reinterpret_cast<TileSmemS*>(dsm_raw + sizeof(TileCommon));
     __shared__ int s_last;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int itile = (nblk * (nblk + 1) / 2 - 1) - (int)blockIdx.x;   // the late rows first: they carry the most work
+    const int ntiles_all = nblk * (nblk + 1) / 2;
+    if((int)blockIdx.x >= cta[kernel_ctas(ntiles_all)]) return;
+    const int itile = cta[blockIdx.x] >> 8, part = cta[blockIdx.x] & 255;
     const int* pl = plan + (size_t)itile * kPlanInts;
-    const int n_items = pl[0], n_groups = pl[1], parts = pl[2];
-    const int part = blockIdx.y;
-    if(part >= parts) return;
+    const int n_items = pl[0], n_groups = pl[1], parts = pl[2], slot0 = pl[3];
     int r, c;
     tile_row_col(itile, r, c);
     const bool diag = r == c;
@@ -614,7 +679,7 @@ schur_tiles_kernel(NormalBuffers N, double lambda, int n_c, int nblk, bool add_l
     ////////////////////////////// a split tile: leave the partial sum; the last part to arrive adds them up in part order
     if(parts > 1)
     {
-        double* mine = part_scratch + ((size_t)itile * kMaxParts + part) * (TB * TB);
+        double* mine = part_scratch + (size_t)(slot0 + part) * (TB * TB);
 #pragma unroll
         for(int a = 0; a < 2; a++)
 #pragma unroll
@@ -632,7 +697,7 @@ schur_tiles_kernel(NormalBuffers N, double lambda, int n_c, int nblk, bool add_l
             for(int b = 0; b < 4; b++) acc[a][b][0] = acc[a][b][1] = 0.;
         for(int p = 0; p < parts; p++)
         {
-            const double* src = part_scratch + ((size_t)itile * kMaxParts + p) * (TB * TB);
+            const double* src = part_scratch + (size_t)(slot0 + p) * (TB * TB);
 #pragma unroll
             for(int a = 0; a < 2; a++)
 #pragma unroll
@@ -887,13 +952,18 @@ bool normal_det_finish(const DevProblem& dp, NormalBuffers& N, const EvalBuffers
     }
     const bool sharded = comm_active();
     if(sharded && N.S_packed == nullptr) { set_error("internal error: sharded solve without the packed tile buffer"); return false; }
-    MB200_CUDA_CHECK(cudaMemsetAsync(N.part_arrive, 0, (size_t)kSplitTilesCap * sizeof(int), s));
-    int* plan = N.part_arrive + kSplitTilesCap;
-    static const int items_per_part = env_int("MRCAL_B200_TILE_ITEMS_PER_PART", 128), groups_per_part = env_int("MRCAL_B200_TILE_GROUPS_PER_PART", 96);
-    tile_plan_kernel<<<(ntiles * 32 + 255) / 256, 256, 0, s>>>(N, nblk, items_per_part, groups_per_part, N.part_scratch != nullptr, plan);
-    schur_tiles_kernel<<<dim3(ntiles, kMaxParts), 256, kTileSmem, s>>>(N, lambda, N.n_c, nblk, true, sharded ? N.S_packed : nullptr,
-                                                                      N.part_scratch, N.part_arrive, plan);
-    (*nlaunch) += 2;
+    // part_arrive: [ntiles] arrival counters | the plan | the CTA list (+ its length)
+    const int ntiles_max = N.nblk_max * (N.nblk_max + 1) / 2;
+    MB200_CUDA_CHECK(cudaMemsetAsync(N.part_arrive, 0, (size_t)ntiles * sizeof(int), s));
+    int* plan = N.part_arrive + ntiles_max;
+    int* cta = plan + (size_t)kPlanInts * ntiles_max;
+    static const int ns_per_item = env_int("MRCAL_B200_TILE_NS_PER_ITEM", 1000), ns_per_group = env_int("MRCAL_B200_TILE_NS_PER_GROUP", 270),
+                     ns_per_part = env_int("MRCAL_B200_TILE_NS_PER_PART", 40000);
+    tile_plan_kernel<<<(ntiles * 32 + 255) / 256, 256, 0, s>>>(N, nblk, ns_per_item, ns_per_group, ns_per_part, N.part_scratch != nullptr, plan);
+    tile_slots_kernel<<<1, 1024, 0, s>>>(ntiles, plan, cta);
+    schur_tiles_kernel<<<kernel_ctas(ntiles), 256, kTileSmem, s>>>(N, lambda, N.n_c, nblk, true, sharded ? N.S_packed : nullptr,
+                                                                 N.part_scratch, N.part_arrive, plan, cta);
+    (*nlaunch) += 3;
     if(sharded)
     {
         // THE collective of the algorithm: the reduced normal equations -- lower-triangle tiles only, with g' and the
@@ -920,9 +990,13 @@ bool normal_det_finish(const DevProblem& dp, NormalBuffers& N, const EvalBuffers
 
 size_t normal_det_packed_doubles(int nblk_max) { return (size_t)nblk_max * (nblk_max + 1) / 2 * TB * TB + kPackedExtras; }
 // what the workspace must provide for the split tiles
-size_t normal_det_part_scratch_doubles() { return (size_t)kSplitTilesCap * kMaxParts * TB * TB; }
-// arrival counters of the split tiles, then the plan (kPlanInts per tile)
-int normal_det_part_arrive_ints(int nblk_max) { return kSplitTilesCap + kPlanInts * (nblk_max * (nblk_max + 1) / 2); }
+size_t normal_det_part_scratch_doubles(int nblk_max) { return (size_t)kernel_ctas(nblk_max * (nblk_max + 1) / 2) * TB * TB; }
+// arrival counters of the tiles, the plan (kPlanInts per tile), the CTA list and its length
+int normal_det_part_arrive_ints(int nblk_max)
+{
+    const int nt = nblk_max * (nblk_max + 1) / 2;
+    return nt + kPlanInts * nt + kernel_ctas(nt) + 1;
+}
 
 bool normal_det_rhs(const NormalBuffers& N, cudaStream_t s, int* nlaunch)
 {

@@ -223,7 +223,7 @@ static bool build_workspace(mrcal_b200_problem* P)
              A.alloc(&N.grp_blkmask, (size_t)(N.Ngroups > 0 ? N.Ngroups : 1) * N.bwords, true) &&
              A.alloc(&N.grp_Linv, (size_t)(N.Ngroups > 0 ? N.Ngroups : 1) * 36, true) && A.alloc(&N.grp_h, (size_t)(N.Ngroups > 0 ? N.Ngroups : 1) * 6, true);
         if(!ok) return false;
-        if(!A.alloc(&N.part_scratch, normal_det_part_scratch_doubles()) || !A.alloc(&N.part_arrive, normal_det_part_arrive_ints(N.nblk_max), true)) return false;
+        if(!A.alloc(&N.part_scratch, normal_det_part_scratch_doubles(N.nblk_max)) || !A.alloc(&N.part_arrive, normal_det_part_arrive_ints(N.nblk_max), true)) return false;
         // (always there: the communicator may be created after this workspace)
         if(!A.alloc(&N.S_packed, normal_det_packed_doubles(N.nblk_max))) return false;
     }
