@@ -578,6 +578,9 @@ schur_tiles_kernel(NormalBuffers N, double lambda, int n_c, int nblk, bool add_l
                     {
                         if((have >> (2 * u)) & 1u) sa.tile[dst0[u]] += v0[u];
                         if((have >> (2 * u + 1)) & 1u) sa.tile[dst1[u]] += v1[u];
+                        // two items may bring the same tile entry to DIFFERENT lanes of this warp: the additions of one task
+                        // are done (and visible to the warp) before those of the next
+                        __syncwarp();
                     }
                 }
             }

@@ -23,6 +23,8 @@ kw, _ = synthetic.make_problem(lensmodel="LENSMODEL_SPLINED_STEREOGRAPHIC_order=
                                W=6, H=5, seed=2, pixel_noise=0.2)
 P = mrcal_b200.Problem(**kw)
 print("solve", P.optimize(max_iterations=6)["Niterations"])
+for icam in (-1, 1):
+    print("drt_cross_reprojection__dbpacked", icam, np.abs(mrcal_b200.drt_cross_reprojection__dbpacked(icam_intrinsics=icam, **kw)).max())
 intr = synthetic.true_intrinsics("LENSMODEL_OPENCV8", 1, np.random.default_rng(0))[0]
 q = mrcal_b200.project(np.array(((0.1, 0.2, 2.), (-.3, .1, 3.))), "LENSMODEL_OPENCV8", intr)
 print("unproject", mrcal_b200.unproject(q, "LENSMODEL_OPENCV8", intr))
