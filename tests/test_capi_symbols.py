@@ -21,6 +21,22 @@ def test_library_loads_and_exports_header_symbols():
     assert set(_capi.EXPORTED_SYMBOLS) == declared, set(_capi.EXPORTED_SYMBOLS) ^ declared
 
 
+def test_header_is_plain_c(tmp_path):
+    """include/mrcal_b200.h is the drop-in boundary: it has to compile as C (gnu11, the reference's dialect: its types use
+    anonymous structs, basic-geometry.h:19-60) and as C++"""
+    import shutil
+    import subprocess
+    src = tmp_path / "h.c"
+    src.write_text('#include "mrcal_b200.h"\nint main(void) { return (int)sizeof(mrcal_lensmodel_t) - (int)sizeof(mrcal_lensmodel_t); }\n')
+    inc = os.path.join(ROOT, "include")
+    for cc, std in (("gcc", "-std=gnu11"), ("g++", "-std=c++17")):
+        if shutil.which(cc) is None:
+            pytest.skip(cc + " not found")
+        r = subprocess.run([cc, std, "-Wall", "-Wextra", "-Werror", "-fsyntax-only", "-x", "c" if cc == "gcc" else "c++", "-I", inc, str(src)],
+                           capture_output=True, text=True)
+        assert r.returncode == 0, r.stderr
+
+
 def test_struct_sizes_match_reference_abi():
     from mrcal_b200 import _capi
     assert ctypes.sizeof(_capi.Lensmodel) == 16      # types.h:122-136
